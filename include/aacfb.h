@@ -1,0 +1,171 @@
+/*
+ * aacfb.h -- C ABI of the B200-native AAC-LC filterbank-synthesis path.
+ *
+ * This is the drop-in boundary for ONE hot path of audiocogs/aac.js:
+ *
+ *     TNS.process            (reference src/tns.js:105-177)
+ *  -> FilterBank.process     (reference src/filter_bank.js:88-204)
+ *       -> MDCT.process      (reference src/mdct.js:62-115)
+ *            -> FFT.process  (reference src/fft.js:105-192)
+ *  -> interleave + /32768    (reference src/decoder.js:204-213)
+ *
+ * Everything above it (ADTS / Huffman / ICS bit parse, M/S, IS) stays in the
+ * JavaScript host.  The entry points below are exactly what an N-API addon
+ * for that path binds; they use plain pointers and sizes
+ * only -- no torch, no C++ types.  The library has NO CPU fallback: every
+ * compute entry point fails with AACFB_ERR_CUDA when no sm_100 device/kernel
+ * image is usable.
+ *
+ * Vocabulary (the reference's): a *frame* is one AAC access unit = 1024
+ * samples for each of C channels; a *channel-frame* is one channel of one
+ * frame = 1024 dequantised spectral coefficients in, 1024 PCM samples out.
+ * A *stream* is one decoder instance (one FilterBank with its per-channel
+ * `overlaps`, filter_bank.js:38-41).  A context batches S independent streams
+ * of identical channel count that are decoded in lockstep.
+ */
+#ifndef AACFB_H_
+#define AACFB_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AACFB_FRAME_LEN 1024   /* config.frameLength, decoder.js:86            */
+#define AACFB_SHORT_LEN 128    /* FilterBank.shortLength, filter_bank.js:30    */
+#define AACFB_MAX_CHANNELS 8
+#define AACFB_TNS_MAX_ORDER 20 /* tns.js:46                                    */
+
+/* ICStream window sequences, reference src/ics.js:44-47 */
+enum {
+    AACFB_ONLY_LONG_SEQUENCE   = 0,
+    AACFB_LONG_START_SEQUENCE  = 1,
+    AACFB_EIGHT_SHORT_SEQUENCE = 2,
+    AACFB_LONG_STOP_SEQUENCE   = 3
+};
+
+/* window shapes: index into LONG_WINDOWS / SHORT_WINDOWS, filter_bank.js:85-86 */
+enum { AACFB_SHAPE_SINE = 0, AACFB_SHAPE_KBD = 1 };
+
+/* error codes (negative); 0 = success */
+enum {
+    AACFB_OK            =  0,
+    AACFB_ERR_ARG       = -1,  /* bad argument (null, range)                    */
+    AACFB_ERR_SMALL     = -2,  /* smallFrames requested: filter_bank.js:25-27   */
+    AACFB_ERR_SEQUENCE  = -3,  /* window_sequence > 3                           */
+    AACFB_ERR_TNS       = -4,  /* TNS order > 20 (tns.js:84-85) or bad blob     */
+    AACFB_ERR_CUDA      = -5,  /* CUDA runtime failure / no usable device       */
+    AACFB_ERR_NOMEM     = -6
+};
+
+/* create() flags ---------------------------------------------------------- */
+/* TNS behaviour (reference defect C1, tns.js:122 reads `tmp` for `top`):
+ *   AS_SHIPPED : identity, literally what the reference does today.
+ *   FIXED_AR   : `tmp`->`top`, decode=true  -> all-pole filter tns.js:156-162
+ *   FIXED_MA   : `tmp`->`top`, decode=false -> FIR branch     tns.js:163-174
+ *                (what decoder.js:264,310,313 would select once C1 is fixed) */
+#define AACFB_TNS_AS_SHIPPED 0u
+#define AACFB_TNS_FIXED_AR   1u
+#define AACFB_TNS_FIXED_MA   2u
+#define AACFB_TNS_MODE_MASK  3u
+
+/* One per channel-frame, laid out [S][T][C].  Mirrors the ICSInfo fields that
+ * FilterBank.process and TNS.process read (filter_bank.js:89-91,104;
+ * tns.js:106,113; ics.js:278-307). */
+typedef struct aacfb_frame_info {
+    uint8_t window_sequence; /* info.windowSequence, 0..3                       */
+    uint8_t shape_prev;      /* info.windowShape[0]                              */
+    uint8_t shape_cur;       /* info.windowShape[1]                              */
+    uint8_t max_sfb;         /* ics.maxSFB (TNS band clamp, tns.js:106)          */
+    uint8_t tns_present;     /* ics.tnsPresent (decoder.js:263,309,312)          */
+    uint8_t reserved[3];     /* must be 0                                        */
+} aacfb_frame_info;
+
+/* TNS side info is a packed blob, one block per channel-frame that has
+ * tns_present != 0, located by tns_offsets[] (byte offsets, 4-byte aligned,
+ * [S*T*C + 1] entries; an empty block has offsets[i+1]==offsets[i]).
+ * Block layout (mirrors TNS.nFilt/length/order/direction/coef, tns.js:24-40):
+ *     uint8_t n_filt[8];                     // per window w (only w<windowCount used)
+ *     then for w in 0..7, for filt in 0..n_filt[w]-1:
+ *         aacfb_tns_filter hdr;              // 4 bytes
+ *         float coef[hdr.order];             // the dequantised reflection
+ *                                            // coefficients, tns.js:97      */
+typedef struct aacfb_tns_filter {
+    uint8_t length;     /* length[w][filt]    in scalefactor bands              */
+    uint8_t order;      /* order[w][filt]     0..20                             */
+    uint8_t direction;  /* direction[w][filt] 0 = upward, 1 = downward          */
+    uint8_t reserved;
+} aacfb_tns_filter;
+
+typedef struct aacfb_ctx aacfb_ctx;
+
+/* Construct.  Replaces `new FilterBank(smallFrames, channels)`
+ * (filter_bank.js:24-44, called at decoder.js:112) for `n_streams` decoder
+ * instances at once, and carries config.sampleIndex for TNS (tns.js:23).
+ * Overlap state is zero-initialised (filter_bank.js:38-41). */
+int aacfb_create(aacfb_ctx **out, int device, int n_streams, int channels,
+                 int sample_index, int small_frames, uint32_t flags);
+int aacfb_destroy(aacfb_ctx *ctx);
+
+/* Zero the overlap state of every stream/channel. */
+int aacfb_reset(aacfb_ctx *ctx);
+
+/* The batched hot path with HOST buffers (what the N-API addon calls from the
+ * decoder's readChunk).  For each stream s, frame t, channel c:
+ *     TNS.process (per ctx TNS mode)  -> FilterBank.process -> interleave,/32768
+ *   spectra     [S][T][C][1024] float  (ics.data after M/S, IS, coupling)
+ *   info        [S][T][C]
+ *   tns_blob / tns_offsets: see above; both may be NULL when no frame has TNS
+ *   pcm         [S][T][1024][C] float  (readChunk's return value, per frame)
+ * Blocking: returns when pcm is complete.  Does not modify spectra. */
+int aacfb_process(aacfb_ctx *ctx, const float *spectra,
+                  const aacfb_frame_info *info,
+                  const uint8_t *tns_blob, const uint32_t *tns_offsets,
+                  float *pcm, int n_frames);
+
+/* Same contract with DEVICE pointers, enqueued on `stream` (a cudaStream_t
+ * passed as void*; NULL = the legacy default stream).  Asynchronous.
+ * tns_blob_bytes is the size of the device blob (0 if none). */
+int aacfb_process_device(aacfb_ctx *ctx, const float *d_spectra,
+                         const aacfb_frame_info *d_info,
+                         const uint8_t *d_tns_blob, const uint32_t *d_tns_offsets,
+                         size_t tns_blob_bytes,
+                         float *d_pcm, int n_frames, void *stream);
+
+/* The inner seam, one channel-frame at a time, HOST buffers:
+ *     filterBank.process(info, input, output, channel)  filter_bank.js:88
+ * `output` is the 1024 un-scaled, un-interleaved samples of this.data[channel]
+ * (decoder.js:269,318-319).  Stream index selects the decoder instance. */
+int aacfb_filterbank_process(aacfb_ctx *ctx, int stream, int channel,
+                             const aacfb_frame_info *info,
+                             const float *input, float *output);
+
+/* The inner seam  tns.process(ics, data, decode)  tns.js:105: filters `data`
+ * (1024 floats, HOST) in place.  `mode` is one of AACFB_TNS_*; `tns_block`
+ * is one block of the blob format above (`block_bytes` long). */
+int aacfb_tns_process(aacfb_ctx *ctx, const aacfb_frame_info *info,
+                      const uint8_t *tns_block, size_t block_bytes,
+                      float *data, uint32_t mode);
+
+/* Overlap state hand-off, HOST buffers [S][C][1024] (FilterBank.overlaps). */
+int aacfb_get_overlap(aacfb_ctx *ctx, float *overlap);
+int aacfb_set_overlap(aacfb_ctx *ctx, const float *overlap);
+
+/* Introspection */
+const char *aacfb_last_error(const aacfb_ctx *ctx); /* ctx may be NULL: global */
+int aacfb_version(void);
+/* number of kernels this context has launched since creation */
+uint64_t aacfb_launch_count(const aacfb_ctx *ctx);
+/* Copy one of the constant tables the kernels use to a HOST buffer (for
+ * table-parity tests against the oracle).  which: 0 FFT roots 512 (re,im)
+ * [1024 f32], 1 FFT roots 64 [128], 2 MDCT twiddles 2048 (c,s) [1024],
+ * 3 MDCT twiddles 256 [128], 4 sine1024, 5 kbd1024, 6 sine128, 7 kbd128.
+ * Returns the number of floats written or a negative error. */
+int aacfb_get_table(int which, float *dst, int capacity);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AACFB_H_ */

@@ -1,0 +1,141 @@
+"""ctypes binding of the CPU oracle (oracle/aacfb_oracle.c).
+
+TEST INFRASTRUCTURE ONLY -- see the header of aacfb_oracle.c.  Importable
+from tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+``--impl reference`` legs; never from the product package.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "libaacfb_oracle.so")
+
+INFO_DTYPE = np.dtype(
+    [("window_sequence", "u1"), ("shape_prev", "u1"), ("shape_cur", "u1"),
+     ("max_sfb", "u1"), ("tns_present", "u1"), ("reserved", "u1", (3,))])
+assert INFO_DTYPE.itemsize == 8
+
+TNS_AS_SHIPPED, TNS_FIXED_AR, TNS_FIXED_MA = 0, 1, 2
+
+
+def build(force: bool = False) -> str:
+    """Compile the oracle with the committed recipe (oracle/Makefile)."""
+    src = os.path.join(_HERE, "aacfb_oracle.c")
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+        subprocess.run(["make", "-C", _HERE, "-s"], check=True)
+    return _SO
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(_SO)
+        L.aacfb_oracle_init.restype = None
+        L.aacfb_oracle_table.argtypes = [C.c_int, C.c_void_p, C.c_int]
+        L.aacfb_oracle_table_f64.argtypes = [C.c_int, C.c_void_p, C.c_int]
+        L.aacfb_oracle_fft.argtypes = [C.c_int, C.c_void_p]
+        L.aacfb_oracle_fft.restype = None
+        L.aacfb_oracle_mdct.argtypes = [C.c_int, C.c_void_p, C.c_void_p]
+        L.aacfb_oracle_mdct.restype = None
+        L.aacfb_oracle_filterbank.argtypes = [C.c_void_p] * 4
+        L.aacfb_oracle_filterbank.restype = None
+        L.aacfb_oracle_tns.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_uint32, C.c_void_p]
+        L.aacfb_oracle_tns.restype = None
+        L.aacfb_oracle_process.argtypes = [C.c_void_p] * 6 + [C.c_int] * 4 + [C.c_uint32, C.c_int]
+        L.aacfb_oracle_process.restype = C.c_int
+        L.aacfb_oracle_init()
+        _lib = L
+    return _lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def table(which: int) -> np.ndarray:
+    out = np.empty(1024, np.float32)
+    n = lib().aacfb_oracle_table(which, _p(out), out.size)
+    assert n > 0
+    return out[:n].copy()
+
+
+def table_f64(which: int) -> np.ndarray:
+    out = np.empty(1024, np.float64)
+    n = lib().aacfb_oracle_table_f64(which, _p(out), out.size)
+    assert n > 0
+    return out[:n].copy()
+
+
+def fft_inverse(z: np.ndarray) -> np.ndarray:
+    """fft.js:105-192 with forward=false on an [L][2] float32 AoS array."""
+    a = np.ascontiguousarray(z, np.float32).copy()
+    lib().aacfb_oracle_fft(a.shape[0], _p(a))
+    return a
+
+
+def imdct(N: int, x: np.ndarray) -> np.ndarray:
+    """mdct.js:62-115: N/2 coefficients -> N samples."""
+    x = np.ascontiguousarray(x, np.float32)
+    assert x.size == N // 2
+    y = np.empty(N, np.float32)
+    lib().aacfb_oracle_mdct(N, _p(x), _p(y))
+    return y
+
+
+def make_info(window_sequence=0, shape_prev=0, shape_cur=0, max_sfb=0, tns_present=0) -> np.ndarray:
+    r = np.zeros((), INFO_DTYPE)
+    r["window_sequence"], r["shape_prev"], r["shape_cur"] = window_sequence, shape_prev, shape_cur
+    r["max_sfb"], r["tns_present"] = max_sfb, tns_present
+    return r
+
+
+def filterbank(info: np.ndarray, x: np.ndarray, overlap: np.ndarray) -> np.ndarray:
+    """filter_bank.js:88-204 for one channel-frame; `overlap` is updated in place."""
+    x = np.ascontiguousarray(x, np.float32)
+    assert overlap.dtype == np.float32 and overlap.flags.c_contiguous and overlap.size == 1024
+    info = np.ascontiguousarray(info)
+    out = np.empty(1024, np.float32)
+    lib().aacfb_oracle_filterbank(_p(info), _p(x), _p(out), _p(overlap))
+    return out
+
+
+def tns(info: np.ndarray, block: bytes, sample_index: int, mode: int, data: np.ndarray) -> np.ndarray:
+    """tns.js:105-177 on a copy of `data`."""
+    d = np.ascontiguousarray(data, np.float32).copy()
+    info = np.ascontiguousarray(info)
+    b = np.frombuffer(block, np.uint8).copy() if len(block) else np.zeros(8, np.uint8)
+    lib().aacfb_oracle_tns(_p(info), _p(b), len(block), sample_index, mode, _p(d))
+    return d
+
+
+def process(spectra, info, tns_blob=None, tns_offsets=None, overlap=None, *, sample_index=4,
+            flags=TNS_AS_SHIPPED, n_threads=1):
+    """Whole path for a batch (same contract as aacfb_process).
+
+    spectra [S][T][C][1024] f32, info [S][T][C] INFO_DTYPE, overlap [S][C][1024]
+    (updated in place; zeros if None).  Returns (pcm [S][T][1024][C], overlap)."""
+    spectra = np.ascontiguousarray(spectra, np.float32)
+    S, T, Cn, n = spectra.shape
+    assert n == 1024
+    info = np.ascontiguousarray(info, INFO_DTYPE).reshape(S, T, Cn)
+    if overlap is None:
+        overlap = np.zeros((S, Cn, 1024), np.float32)
+    assert overlap.shape == (S, Cn, 1024) and overlap.dtype == np.float32 and overlap.flags.c_contiguous
+    pcm = np.empty((S, T, 1024, Cn), np.float32)
+    if tns_blob is not None:
+        tns_blob = np.ascontiguousarray(tns_blob, np.uint8)
+        tns_offsets = np.ascontiguousarray(tns_offsets, np.uint32)
+        assert tns_offsets.size == S * T * Cn + 1
+    rc = lib().aacfb_oracle_process(_p(spectra), _p(info), _p(tns_blob), _p(tns_offsets), _p(overlap), _p(pcm),
+                                    S, T, Cn, sample_index, flags, n_threads)
+    assert rc == 0
+    return pcm, overlap
