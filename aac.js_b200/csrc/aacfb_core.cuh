@@ -1,0 +1,521 @@
+// aacfb_core.cuh -- per-thread compute phases of the synthesis kernel.
+//
+// A *worker* is 64 threads that carry two (stream, channel) chains through
+// time.  Each thread keeps 8 complex points per chain in registers; a
+// 512-point inverse FFT is three register passes (radix-2 DIT stages 1-3,
+// 4-6, 7-9) with two swizzled shared-memory exchanges in between.  The
+// butterfly network, twiddle values and operation order are those of the
+// reference's FFT.process (src/fft.js:105-192) so rounding tracks it; only
+// the *placement* of butterflies on threads is new.
+//
+// Every phase is a pure function of (thread index, registers, staging
+// buffer, tables), written __host__ __device__ so that tests can run the
+// very same code on the CPU (csrc/aacfb_emul.cu) where no GPU exists.
+//
+// All arithmetic goes through f_mul/f_add/f_fma so that neither nvcc nor gcc
+// contracts or reassociates anything: host emulation and device agree bit
+// for bit.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#include "../../include/aacfb.h"
+#include "aacfb_tables.h"
+
+#if defined(__CUDACC__)
+#define AACFB_HD __host__ __device__ __forceinline__
+#else
+#define AACFB_HD inline
+#endif
+
+namespace aacfb {
+
+#if defined(__CUDA_ARCH__)
+AACFB_HD float f_mul(float a, float b) { return __fmul_rn(a, b); }
+AACFB_HD float f_add(float a, float b) { return __fadd_rn(a, b); }
+AACFB_HD float f_sub(float a, float b) { return __fsub_rn(a, b); }
+AACFB_HD float f_fma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+#else
+AACFB_HD float f_mul(float a, float b) { volatile float r = a * b; return r; }
+AACFB_HD float f_add(float a, float b) { volatile float r = a + b; return r; }
+AACFB_HD float f_sub(float a, float b) { volatile float r = a - b; return r; }
+AACFB_HD float f_fma(float a, float b, float c) { return fmaf(a, b, c); }
+#endif
+
+constexpr int kWorkerThreads = 64;
+constexpr int kRowFloats = 1024;        // one channel-frame of spectrum
+constexpr int kStageFloats = 2 * 1024;  // two chains per stage
+
+AACFB_HD constexpr int brev3(int q) { return ((q & 1) << 2) | (q & 2) | ((q >> 2) & 1); }
+AACFB_HD int brev6(int u) {
+    return ((u & 1) << 5) | ((u & 2) << 3) | ((u & 4) << 1) | ((u & 8) >> 1) | ((u & 16) >> 3) | ((u & 32) >> 5);
+}
+
+// Registers of one thread: 8 complex points for each of the worker's 2 chains.
+struct Pts {
+    float r[2][8], i[2][8];
+};
+// Overlap carried between frames: positions m(q) and 1023-m(q), q = 0..7.
+struct Ovl {
+    float a[2][8], b[2][8];
+};
+// PCM samples of the current frame at the same positions, before write-out.
+struct Out {
+    float a[2][8], b[2][8];
+};
+// Phases below are templated on <C0, NCH>: they act on chains C0 .. C0+NCH-1.
+
+// ---------------------------------------------------------------- butterflies
+// fft.js:180-188: t = x[hi]*w (kept in double there); x[hi] = x[lo]-t; x[lo] += t.
+AACFB_HD void bfly(float &ar, float &ai, float &br, float &bi, float wr, float wi) {
+    const float lr = f_fma(br, wr, f_fma(-bi, wi, ar));
+    const float li = f_fma(br, wi, f_fma(bi, wr, ai));
+    const float hr = f_fma(-br, wr, f_fma(bi, wi, ar));
+    const float hi = f_fma(-br, wi, f_fma(-bi, wr, ai));
+    ar = lr; ai = li; br = hr; bi = hi;
+}
+AACFB_HD void bfly1(float &ar, float &ai, float &br, float &bi) {  // w = (1, 0): exact in the reference too
+    const float lr = f_add(ar, br), li = f_add(ai, bi);
+    const float hr = f_sub(ar, br), hi = f_sub(ai, bi);
+    ar = lr; ai = li; br = hr; bi = hi;
+}
+// fft.js:140-170, inverse branch: the fused first two stages on 4 points.
+AACFB_HD void base4(float *r, float *i) {
+    const float a0 = f_add(r[0], r[1]), a1 = f_add(i[0], i[1]);
+    const float b0 = f_add(r[2], r[3]), b1 = f_add(i[2], i[3]);
+    const float c0 = f_sub(r[0], r[1]), c1 = f_sub(i[0], i[1]);
+    const float d0 = f_sub(r[2], r[3]), d1 = f_sub(i[2], i[3]);
+    r[0] = f_add(a0, b0); i[0] = f_add(a1, b1);
+    r[2] = f_sub(a0, b0); i[2] = f_sub(a1, b1);
+    r[1] = f_sub(c0, d1); i[1] = f_add(c1, d0);
+    r[3] = f_add(c0, d1); i[3] = f_sub(c1, d0);
+}
+
+// Stages 1-3 on 8 consecutive array positions (regs indexed by position&7).
+// wA = roots[k * L/8], k = 0..3 (fft.js:173-178 with i = 4).
+template <int C0, int NCH>
+AACFB_HD void pass_a(Pts &z, const float2 *wA) {
+#pragma unroll
+    for (int c = C0; c < C0 + NCH; ++c) {
+        base4(&z.r[c][0], &z.i[c][0]);
+        base4(&z.r[c][4], &z.i[c][4]);
+        bfly1(z.r[c][0], z.i[c][0], z.r[c][4], z.i[c][4]);
+#pragma unroll
+        for (int k = 1; k < 4; ++k) bfly(z.r[c][k], z.i[c][k], z.r[c][4 + k], z.i[c][4 + k], wA[k].x, wA[k].y);
+    }
+}
+
+// Three stages on 8 points whose array positions differ in three consecutive
+// bits (regs indexed by those bits).  tw[0] serves the first stage, tw[1..2]
+// the second, tw[3..6] the third (see SynthTables::twB/twC/twS).
+template <int C0, int NCH>
+AACFB_HD void pass_3stage(Pts &z, const float2 *tw) {
+#pragma unroll
+    for (int c = C0; c < C0 + NCH; ++c) {
+#pragma unroll
+        for (int q = 0; q < 8; q += 2) bfly(z.r[c][q], z.i[c][q], z.r[c][q + 1], z.i[c][q + 1], tw[0].x, tw[0].y);
+#pragma unroll
+        for (int q = 0; q < 8; q += 4) {
+            bfly(z.r[c][q], z.i[c][q], z.r[c][q + 2], z.i[c][q + 2], tw[1].x, tw[1].y);
+            bfly(z.r[c][q + 1], z.i[c][q + 1], z.r[c][q + 3], z.i[c][q + 3], tw[2].x, tw[2].y);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) bfly(z.r[c][q], z.i[c][q], z.r[c][q + 4], z.i[c][q + 4], tw[3 + q].x, tw[3 + q].y);
+    }
+}
+
+// ------------------------------------------------------------ long transform
+// Thread roles.  Pass A / pass C thread u: input indices n = u + 64*j and
+// output bins k = 64*q + u.  Pass B thread v holds array positions
+// p = 64*bhi + 8*q + blo with (b7 b6 b8 b2 b1 b0) = bits of v.
+AACFB_HD int passb_bhi(int v) { return (((v >> 3) & 1) << 2) | (((v >> 5) & 1) << 1) | ((v >> 4) & 1); }
+AACFB_HD int passb_blo(int v) { return v & 7; }
+
+// Pre-twiddle (mdct.js:73-76) straight from the staged spectrum row into the
+// bit-reversed register order pass A needs: reg q <- input n = u + 64*brev3(q).
+template <int C0, int NCH>
+AACFB_HD void long_load(int u, const float *const *row, const float2 *cs2048, Pts &z) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const int n = u + 64 * brev3(q);
+        const float2 cs = cs2048[n];
+#pragma unroll
+        for (int c = C0; c < C0 + NCH; ++c) {
+            const float x0 = row[c][2 * n], x1 = row[c][1023 - 2 * n];
+            z.i[c][q] = f_fma(x0, cs.x, f_mul(x1, cs.y));
+            z.r[c][q] = f_fma(x1, cs.x, -f_mul(x0, cs.y));
+        }
+    }
+}
+
+// Exchange 1 (pass A -> pass B).  Element index e = array position; stored at
+// e ^ (e >> 5) so that both the scatter below and the gather in ex1_read hit
+// 16 distinct 8-byte bank pairs per half-warp.
+template <int C0, int NCH>
+AACFB_HD void ex1_write(int u, const Pts &z, float2 *const *buf) {
+    const int a = brev6(u);
+    const int base = (8 * a) ^ (a >> 2);
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+#pragma unroll
+        for (int c = C0; c < C0 + NCH; ++c) {
+            float2 t; t.x = z.r[c][q]; t.y = z.i[c][q];
+            buf[c][base ^ q] = t;
+        }
+}
+template <int C0, int NCH>
+AACFB_HD void ex1_read(int v, float2 *const *buf, Pts &z) {
+    const int bhi = passb_bhi(v), blo = passb_blo(v);
+    const int base = ((64 * bhi) | blo) ^ (bhi << 1);
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+#pragma unroll
+        for (int c = C0; c < C0 + NCH; ++c) {
+            const float2 t = buf[c][base ^ ((8 * q) ^ (q >> 2))];
+            z.r[c][q] = t.x; z.i[c][q] = t.y;
+        }
+}
+// Exchange 2 (pass B -> pass C): stored at e ^ (bit8(e) << 3).
+template <int C0, int NCH>
+AACFB_HD void ex2_write(int v, const Pts &z, float2 *const *buf) {
+    const int bhi = passb_bhi(v), blo = passb_blo(v);
+    const int base = ((64 * bhi) | blo) ^ ((bhi >> 2) << 3);
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+#pragma unroll
+        for (int c = C0; c < C0 + NCH; ++c) {
+            float2 t; t.x = z.r[c][q]; t.y = z.i[c][q];
+            buf[c][base ^ (8 * q)] = t;
+        }
+}
+template <int C0, int NCH>
+AACFB_HD void ex2_read(int u, float2 *const *buf, Pts &z) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+#pragma unroll
+        for (int c = C0; c < C0 + NCH; ++c) {
+            const float2 t = buf[c][(64 * q + u) ^ ((q >> 2) << 3)];
+            z.r[c][q] = t.x; z.i[c][q] = t.y;
+        }
+}
+
+// Window tables of one channel-frame, resolved from (sequence, shapes).
+// first[k]  = (Wf[m], Wf[1023-m]) applied to the IMDCT's first half,
+// second[k] = (Ws[m], Ws[1023-m]) applied to y[1024+n]; m = long_pos_of_bin(k).
+// `second_swapped`: the table holds (W[m], W[1023-m]) and the reversed long
+// window W[1023-n] is wanted (filter_bank.js:115-116,198-200), so use (.y,.x).
+struct LongWin {
+    const float2 *first;
+    const float2 *second;
+    bool second_swapped;
+};
+AACFB_HD LongWin long_windows(const aacfb_frame_info &fi, const float2 (*wz)[512], const SynthTables *g) {
+    LongWin w;
+    const int sp = fi.shape_prev & 1, sc = fi.shape_cur & 1;
+    w.first = (fi.window_sequence == AACFB_LONG_STOP_SEQUENCE) ? g->fwz_stop[sp] : wz[sp];
+    if (fi.window_sequence == AACFB_LONG_START_SEQUENCE) { w.second = g->swz_start[sc]; w.second_swapped = false; }
+    else { w.second = wz[sc]; w.second_swapped = true; }
+    return w;
+}
+
+// Post-twiddle (mdct.js:82-87), reorder (mdct.js:90-114), window and
+// overlap-add (filter_bank.js:105-141,180-202), scale (decoder.js:210).
+// Thread u owns bins k = 64q+u, i.e. output positions m and 1023-m with
+// m = long_pos_of_bin(k); the same thread owned them in every earlier frame,
+// so the overlap lives in registers.
+// The frame's PCM goes to `o` (registers) and is written out by out_stage().
+template <int C0, int NCH>
+AACFB_HD void long_finish(int u, const Pts &z, Ovl &ov, const float2 *cs2048, const LongWin *win,
+                          bool emit, float scale, Out &o) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const int k = 64 * q + u;
+        const float2 cs = cs2048[k];
+#pragma unroll
+        for (int c = C0; c < C0 + NCH; ++c) {
+            const float re = z.r[c][q], im = z.i[c][q];
+            const float pr = f_fma(re, cs.x, -f_mul(im, cs.y));
+            const float pi = f_fma(im, cs.x, f_mul(re, cs.y));
+            // first-half sample at m is F, at 1023-m is -F; second-half sample is S at both
+            const float F = (q < 4) ? pr : pi;
+            const float S = (q < 4) ? -pi : pr;
+            if (emit) {
+                const float2 wf = win[c].first[k];
+                o.a[c][q] = f_mul(f_fma(F, wf.x, ov.a[c][q]), scale);
+                o.b[c][q] = f_mul(f_fma(-F, wf.y, ov.b[c][q]), scale);
+            }
+            const float2 ws = win[c].second[k];
+            ov.a[c][q] = f_mul(S, win[c].second_swapped ? ws.y : ws.x);
+            ov.b[c][q] = f_mul(S, win[c].second_swapped ? ws.x : ws.y);
+        }
+    }
+}
+
+// ----------------------------------------------------------- short transform
+// EIGHT_SHORT: thread u = 8*w + g works on window w.  Pass A' takes inputs
+// n = g + 8*j of that window, pass B' produces bins k = 8*q + g.
+template <int C0, int NCH>
+AACFB_HD void short_load(int u, const float *const *row, const float2 *cs256, Pts &z) {
+    const int w = u >> 3, g = u & 7;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const int n = g + 8 * brev3(q);
+        const float2 cs = cs256[n];
+#pragma unroll
+        for (int c = C0; c < C0 + NCH; ++c) {
+            const float x0 = row[c][128 * w + 2 * n], x1 = row[c][128 * w + 127 - 2 * n];
+            z.i[c][q] = f_fma(x0, cs.x, f_mul(x1, cs.y));
+            z.r[c][q] = f_fma(x1, cs.x, -f_mul(x0, cs.y));
+        }
+    }
+}
+// Exchange between the two passes of the 8 x 64-point FFTs.  Element
+// e = 64w + position; stored at e ^ (12*bit6(e)) ^ ((e>>4)&3).
+template <int C0, int NCH>
+AACFB_HD void exs_write(int u, const Pts &z, float2 *const *buf) {
+    const int w = u >> 3, a = brev3(u & 7);
+    const int base = ((64 * w) | (8 * a)) ^ (12 * (w & 1)) ^ (a >> 1);
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+#pragma unroll
+        for (int c = C0; c < C0 + NCH; ++c) {
+            float2 t; t.x = z.r[c][q]; t.y = z.i[c][q];
+            buf[c][base ^ q] = t;
+        }
+}
+template <int C0, int NCH>
+AACFB_HD void exs_read(int u, float2 *const *buf, Pts &z) {
+    const int w = u >> 3, g = u & 7;
+    const int base = ((64 * w) | g) ^ (12 * (w & 1));
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+#pragma unroll
+        for (int c = C0; c < C0 + NCH; ++c) {
+            const float2 t = buf[c][base ^ ((8 * q) ^ (q >> 1))];
+            z.r[c][q] = t.x; z.i[c][q] = t.y;
+        }
+}
+// Post-twiddle and reorder of the 8 short IMDCTs of ONE chain into
+// buf[256w + i] (filter_bank.js:144-146 -> mdct.js:82-114 with N = 256).
+template <int C>
+AACFB_HD void short_scatter(int u, const Pts &z, const float2 *cs256, float *buf) {
+    const int w = u >> 3, g = u & 7;
+    float *y = buf + 256 * w;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const int k = 8 * q + g;
+        const float2 cs = cs256[k];
+        const float re = z.r[C][q], im = z.i[C][q];
+        const float pr = f_fma(re, cs.x, -f_mul(im, cs.y));
+        const float pi = f_fma(im, cs.x, f_mul(re, cs.y));
+        if (q < 4) {  // k < 32
+            y[64 + 2 * k] = pr;  y[63 - 2 * k] = -pr;
+            y[192 + 2 * k] = -pi; y[191 - 2 * k] = -pi;
+        } else {
+            y[2 * (k - 32)] = pi; y[191 - 2 * k] = -pi;
+            y[128 + 2 * (k - 32)] = pr; y[319 - 2 * k] = pr;
+        }
+    }
+}
+// filter_bank.js:148-161: output sample n of an EIGHT_SHORT frame.
+AACFB_HD float short_first(int n, const float *buf, float ov, const float *wprev, const float *wcur) {
+    if (n < 448) return ov;
+    const int t = n - 448, j = t >> 7, i = t & 127;
+    if (j == 0) return f_fma(buf[i], wprev[i], ov);
+    return f_fma(buf[256 * j + i], wcur[i], f_fma(buf[256 * j - 128 + i], wcur[127 - i], ov));
+}
+// filter_bank.js:164-176: overlap sample n saved by an EIGHT_SHORT frame.
+AACFB_HD float short_second(int n, const float *buf, const float *wcur) {
+    if (n >= 576) return 0.f;
+    if (n >= 448) { const int i = n - 448; return f_mul(buf[1920 + i], wcur[127 - i]); }
+    const int t = n + 576, j = t >> 7, i = t & 127;
+    return f_fma(buf[256 * j + i], wcur[i], f_mul(buf[256 * j - 128 + i], wcur[127 - i]));
+}
+// Window + overlap-add of ONE chain of an EIGHT_SHORT frame from buf[2048].
+template <int C>
+AACFB_HD void short_finish(int u, const float *buf, Ovl &ov, const aacfb_frame_info &fi,
+                           const float (*wshort)[128], bool emit, float scale, Out &o) {
+    const float *wprev = wshort[fi.shape_prev & 1], *wcur = wshort[fi.shape_cur & 1];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const int m = long_pos_of_bin(64 * q + u), mm = 1023 - m;
+        if (emit) {
+            o.a[C][q] = f_mul(short_first(m, buf, ov.a[C][q], wprev, wcur), scale);
+            o.b[C][q] = f_mul(short_first(mm, buf, ov.b[C][q], wprev, wcur), scale);
+        }
+        ov.a[C][q] = short_second(m, buf, wcur);
+        ov.b[C][q] = short_second(mm, buf, wcur);
+    }
+}
+
+// ------------------------------------------------------------- PCM write-out
+// The frame's samples sit in registers at positions (m, 1023-m).  They are
+// transposed through the (by now free) staging buffer so that global memory
+// sees only full, contiguous 16-byte-per-lane stores:
+//   interleaved: the two chains are channels c, c+1 of one stereo stream ->
+//                stage holds [1024][2], one contiguous 8 KiB PCM row
+//                (decoder.js:204-213 interleave)
+//   planar:      stage holds [2][1024]; each chain's row is written with
+//                stride `ostride`
+template <int C0, int NCH>
+AACFB_HD void out_stage(int u, const Out &o, float *stage, bool interleaved) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const int m = long_pos_of_bin(64 * q + u), mm = 1023 - m;
+        if (interleaved && NCH == 2) {
+            float2 t; t.x = o.a[0][q]; t.y = o.a[1][q];
+            reinterpret_cast<float2 *>(stage)[m] = t;
+            t.x = o.b[0][q]; t.y = o.b[1][q];
+            reinterpret_cast<float2 *>(stage)[mm] = t;
+        } else {
+#pragma unroll
+            for (int c = C0; c < C0 + NCH; ++c) {
+                stage[1024 * c + m] = o.a[c][q];
+                stage[1024 * c + mm] = o.b[c][q];
+            }
+        }
+    }
+}
+AACFB_HD void out_copy(int u, const float *stage, float *const *out, int ostride, int c_lo, int c_hi, bool interleaved) {
+    if (interleaved) {
+        const float4 *s4 = reinterpret_cast<const float4 *>(stage);
+        float4 *d4 = reinterpret_cast<float4 *>(out[0]);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) d4[64 * i + u] = s4[64 * i + u];
+        return;
+    }
+    for (int c = c_lo; c < c_hi; ++c) {
+        if (ostride == 1) {
+            const float4 *s4 = reinterpret_cast<const float4 *>(stage + 1024 * c);
+            float4 *d4 = reinterpret_cast<float4 *>(out[c]);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) d4[64 * i + u] = s4[64 * i + u];
+        } else {
+#pragma unroll 4
+            for (int i = 0; i < 16; ++i) out[c][(size_t)(64 * i + u) * ostride] = stage[1024 * c + 64 * i + u];
+        }
+    }
+}
+
+// ---------------------------------------------------------------- overlap I/O
+template <int C>
+AACFB_HD void ovl_load(int u, const float *state, Ovl &ov) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const int m = long_pos_of_bin(64 * q + u);
+        ov.a[C][q] = state ? state[m] : 0.f;
+        ov.b[C][q] = state ? state[1023 - m] : 0.f;
+    }
+}
+template <int C>
+AACFB_HD void ovl_store(int u, const Ovl &ov, float *state) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const int m = long_pos_of_bin(64 * q + u);
+        state[m] = ov.a[C][q];
+        state[1023 - m] = ov.b[C][q];
+    }
+}
+
+// ------------------------------------------------------------------- TNS
+// tns.js:105-177 with `tmp` -> `top` at :122.  Strictly serial per chain:
+// each tap is a rounded f32 read-modify-write in the reference's order
+// (i = 1..min(m,order), tns.js:158-161), so one thread runs one chain with
+// the last ORD outputs (AR) / inputs (MA) in registers, and many chains run
+// side by side.  Taps beyond min(m,order) multiply a zero history / a zero
+// coefficient, which leaves the accumulator unchanged, so no per-tap
+// predicate is needed.  x = unfiltered row (read only), y = filtered row.
+template <int ORD, bool AR>
+AACFB_HD void tns_run(const float *x, float *y, int start, int size, int inc, const float *lpc, int order) {
+    float h[ORD], c[ORD];
+#pragma unroll
+    for (int i = 0; i < ORD; ++i) { h[i] = 0.f; c[i] = i < order ? lpc[i] : 0.f; }
+    // band edges are multiples of 4 (tables.js:34-124), so runs are whole float4s
+    for (int m = 0; m < size; m += 4) {
+        const int at = inc > 0 ? start + m : start - m - 3;
+        const float4 t = *reinterpret_cast<const float4 *>(x + at);
+        float v[4];
+        if (inc > 0) { v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
+        else         { v[0] = t.w; v[1] = t.z; v[2] = t.y; v[3] = t.x; }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float acc = v[j];
+#pragma unroll
+            for (int i = 0; i < ORD; ++i) acc = f_fma(AR ? -h[i] : h[i], c[i], acc);
+            // MA branch, order 20: the reference's tmp has 20 slots, tmp[20] reads
+            // undefined -> NaN once m >= 20 (tns.js:43,169)
+            if (!AR && order == AACFB_TNS_MAX_ORDER && m + j >= AACFB_TNS_MAX_ORDER) acc = NAN;
+            const float push = AR ? acc : v[j];
+#pragma unroll
+            for (int i = ORD - 1; i > 0; --i) h[i] = h[i - 1];
+            h[0] = push;
+            v[j] = acc;
+        }
+        float4 o;
+        if (inc > 0) { o.x = v[0]; o.y = v[1]; o.z = v[2]; o.w = v[3]; }
+        else         { o.x = v[3]; o.y = v[2]; o.z = v[1]; o.w = v[0]; }
+        *reinterpret_cast<float4 *>(y + at) = o;
+    }
+}
+
+template <bool AR>
+AACFB_HD void tns_dispatch(const float *x, float *y, int start, int size, int inc, const float *lpc, int order) {
+    if (order <= 4) tns_run<4, AR>(x, y, start, size, inc, lpc, order);
+    else if (order <= 8) tns_run<8, AR>(x, y, start, size, inc, lpc, order);
+    else if (order <= 12) tns_run<12, AR>(x, y, start, size, inc, lpc, order);
+    else if (order <= 16) tns_run<16, AR>(x, y, start, size, inc, lpc, order);
+    else tns_run<20, AR>(x, y, start, size, inc, lpc, order);
+}
+
+// One channel-frame: walk the TNS block (aacfb.h blob layout), build each
+// filter's direct-form coefficients (tns.js:128-140) and run it over its band
+// range (tns.js:142-154).  Filters of one window cover disjoint, downward
+// stacked band ranges, so every run reads unfiltered input from x.
+// The caller has already copied x to y.
+AACFB_HD void tns_apply(const aacfb_frame_info &fi, const uint8_t *block, uint32_t block_bytes, int sample_index,
+                        bool ar, const TnsBandTables &bt, const float *x, float *y) {
+    if (block_bytes < 8) return;
+    const bool is_short = fi.window_sequence == AACFB_EIGHT_SHORT_SEQUENCE;
+    const uint16_t *swb = is_short ? bt.swb_short[sample_index] : bt.swb_long[sample_index];
+    const int swb_count = is_short ? bt.swb_short_count[sample_index] : bt.swb_long_count[sample_index];
+    const int window_count = is_short ? 8 : 1;
+    const int max_bands = bt.tns_max_bands[sample_index];             // tns.js:23 (long table for short windows too)
+    const int mmm = max_bands < fi.max_sfb ? max_bands : fi.max_sfb;  // tns.js:106
+    float lpc[AACFB_TNS_MAX_ORDER];
+    uint32_t pos = 8;
+    for (int w = 0; w < 8; ++w) {
+        int bottom = swb_count;  // tns.js:113
+        for (int f = 0; f < block[w]; ++f) {
+            if (pos + 4 > block_bytes) return;
+            const int length = block[pos], order = block[pos + 1], direction = block[pos + 2];
+            const float *coef = reinterpret_cast<const float *>(block + pos + 4);
+            pos += 4 + 4 * order;
+            if (order > AACFB_TNS_MAX_ORDER || pos > block_bytes) return;
+            if (w >= window_count) continue;
+            const int top = bottom;  // tns.js:121
+            bottom = top - length;   // tns.js:122, `tmp` read as `top`
+            if (bottom < 0) bottom = 0;
+            if (order == 0) continue;  // tns.js:125
+            for (int i = 0; i < order; ++i) {
+                const float r = -coef[i];
+                lpc[i] = r;
+                for (int j = 0, len = (i + 1) >> 1; j < len; ++j) {
+                    const float fwd = lpc[j], bwd = lpc[i - 1 - j];
+                    lpc[j] = f_fma(r, bwd, fwd);
+                    lpc[i - 1 - j] = f_fma(r, fwd, bwd);
+                }
+            }
+            int start = swb[bottom < mmm ? bottom : mmm];
+            const int end = swb[top < mmm ? top : mmm];
+            const int size = end - start;
+            if (size <= 0) continue;  // tns.js:147
+            int inc = 1;
+            if (direction) { inc = -1; start = end - 1; }  // tns.js:149-152
+            start += w * 128;                              // tns.js:154
+            if (ar) tns_dispatch<true>(x, y, start, size, inc, lpc, order);
+            else tns_dispatch<false>(x, y, start, size, inc, lpc, order);
+        }
+    }
+}
+
+}  // namespace aacfb

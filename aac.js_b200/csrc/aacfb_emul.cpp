@@ -1,0 +1,122 @@
+// aacfb_emul.cpp -- CPU emulation of the synthesis kernel's worker schedule.
+//
+// TEST-ONLY.  Runs the very same __host__ __device__ phase code the CUDA
+// kernel runs (aacfb_core.cuh / aacfb_worker.cuh): 64 host threads play the
+// 64 threads of one worker, a std::barrier plays the named barrier, and a
+// plain memcpy plays the TMA load.  It lets the CPU-only test tier check the
+// kernel's index maps, swizzles, window-switching and chunk/halo logic against
+// the oracle bit patterns without a GPU.  It is never linked into
+// libaacfb.so and is not a fallback: the shipped library has no CPU path.
+#include <barrier>
+#include <cstring>
+#include <thread>
+#include <vector>
+
+#include <cuda_runtime.h>  // float2/float4 only
+
+#include "aacfb_tables.h"
+#include "aacfb_worker.cuh"
+
+using namespace aacfb;
+
+namespace {
+struct HostSync {
+    std::barrier<> *bar;
+    void barrier() { bar->arrive_and_wait(); }
+    void stage_free() { bar->arrive_and_wait(); }
+};
+}  // namespace
+
+extern "C" __attribute__((visibility("default"))) int aacfb_emul_process(
+    const float *spectra, const aacfb_frame_info *info, const uint8_t *tns_blob, const uint32_t *tns_offsets,
+    float *overlap /*[S][C][1024] in/out*/, float *pcm, int S, int T, int C, int sample_index, uint32_t flags,
+    int chunk_len) {
+    const HostTables &H = host_tables();
+    const SynthTables *tab = &H.synth;
+    const TnsBandTables &bt = tns_band_tables();
+    const uint32_t mode = flags & AACFB_TNS_MODE_MASK;
+
+    // TNS pre-pass (the kernel's tns_kernel): filtered copies of the rows that carry TNS
+    std::vector<float> scratch;
+    const bool tns_on = mode != AACFB_TNS_AS_SHIPPED && tns_blob && tns_offsets;
+    if (tns_on) {
+        scratch.assign(spectra, spectra + (size_t)S * T * C * 1024);
+        for (size_t cf = 0; cf < (size_t)S * T * C; ++cf) {
+            if (!info[cf].tns_present) continue;
+            const uint32_t o0 = tns_offsets[cf], o1 = tns_offsets[cf + 1];
+            if (o1 <= o0) continue;
+            tns_apply(info[cf], tns_blob + o0, o1 - o0, sample_index, mode == AACFB_TNS_FIXED_AR, bt,
+                      spectra + cf * 1024, scratch.data() + cf * 1024);
+        }
+    }
+    const float *rows = tns_on ? scratch.data() : spectra;
+
+    const Geometry g = make_geometry(S, T, C, C, 0, 0, chunk_len);
+    const int n_items = g.n_pairs * g.n_chunks;
+    alignas(16) static thread_local float dummy;
+    (void)dummy;
+
+    for (int item = 0; item < n_items; ++item) {
+        const Item it = make_item(g, item);
+        std::barrier<> bar(kWorkerThreads);
+        std::vector<float> stage_mem(kStageFloats + 4);
+        float *stage = stage_mem.data();
+        while (reinterpret_cast<uintptr_t>(stage) & 15) ++stage;
+        const int f_begin = it.t0 > 0 ? it.t0 - 1 : 0;
+
+        auto body = [&](int u) {
+            HostSync sync{&bar};
+            Pts z;
+            Ovl ov;
+            std::memset(&ov, 0, sizeof ov);
+            if (it.t0 == 0) {
+                ovl_load<0>(u, overlap + state_index(g, it.s[0], it.j[0]), ov);
+                if (it.nch == 2) ovl_load<1>(u, overlap + state_index(g, it.s[1], it.j[1]), ov);
+            }
+            for (int t = f_begin; t < it.t1; ++t) {
+                // "TMA": thread 0 fills the stage, everyone waits
+                if (u == 0)
+                    for (int c = 0; c < it.nch; ++c)
+                        std::memcpy(stage + 1024 * c, rows + cf_index(g, it.s[c], t, it.j[c]) * 1024, 4096);
+                bar.arrive_and_wait();
+                FrameIO io;
+                io.stage = stage;
+                io.nch = it.nch;
+                io.emit = t >= it.t0;
+                io.interleaved = it.interleaved;
+                io.scale = 1.0f / 32768.0f;
+                io.ostride = g.nc;
+                for (int c = 0; c < 2; ++c) {
+                    io.fi[c] = info[cf_index(g, it.s[c], t, it.j[c])];
+                    io.fi[c].window_sequence &= 3;
+                    io.out[c] = pcm + ((size_t)it.s[c] * g.T + t) * 1024 * g.nc + it.j[c];
+                }
+                worker_frame(u, sync, io, tab, tab, z, ov);
+            }
+            if (it.t1 == g.T) {
+                ovl_store<0>(u, ov, overlap + state_index(g, it.s[0], it.j[0]));
+                if (it.nch == 2) ovl_store<1>(u, ov, overlap + state_index(g, it.s[1], it.j[1]));
+            }
+        };
+        std::vector<std::thread> th;
+        for (int u = 0; u < kWorkerThreads; ++u) th.emplace_back(body, u);
+        for (auto &t : th) t.join();
+    }
+    return 0;
+}
+
+extern "C" __attribute__((visibility("default"))) int aacfb_emul_table(int which, float *dst, int cap) {
+    const HostTables &H = host_tables();
+    auto put = [&](const float *src, int n) { if (cap < n) return -1; std::memcpy(dst, src, sizeof(float) * n); return n; };
+    switch (which) {
+    case 0: return put(&H.roots512[0][0], 1024);
+    case 1: return put(&H.roots64[0][0], 128);
+    case 2: return put(&H.synth.cs2048[0].x, 1024);
+    case 3: return put(&H.synth.cs256[0].x, 128);
+    case 4: return put(H.sine1024, 1024);
+    case 5: return put(H.kbd1024, 1024);
+    case 6: return put(H.sine128, 128);
+    case 7: return put(H.kbd128, 128);
+    }
+    return -1;
+}

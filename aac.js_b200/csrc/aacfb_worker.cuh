@@ -1,0 +1,171 @@
+// aacfb_worker.cuh -- the per-frame schedule of one worker thread.
+//
+// A worker (64 threads) owns one staging buffer per frame: two spectrum rows
+// of 1024 floats (one per chain), filled by TMA in the kernel.  Once a row
+// has been consumed into registers the same 4 KiB serve as that chain's FFT
+// exchange buffer; for EIGHT_SHORT frames the whole 8 KiB serve as the
+// 2048-sample IMDCT buffer `buf` of filter_bank.js:43; at the end of the
+// frame they serve as the transpose buffer of the PCM write-out.
+//
+// `Sync` provides the two synchronisation points the schedule needs:
+//   sync.barrier()     all 64 threads of the worker
+//   sync.stage_free()  barrier + "this frame's staging buffer may be refilled"
+// The kernel implements them with a named barrier and a TMA issue, the CPU
+// emulation (tests) with a std::barrier.
+#pragma once
+#include "aacfb_core.cuh"
+
+namespace aacfb {
+
+struct FrameIO {
+    float *stage;                 // 2048 floats: row of chain 0, row of chain 1
+    aacfb_frame_info fi[2];
+    int nch;                      // 1 or 2 live chains
+    bool emit;                    // false for the halo frame of a chunk
+    bool interleaved;             // chains are channels c, c+1 of one stereo stream
+    float scale;                  // 2^-15 (decoder.js:210) or 1 for the inner seam
+    float *out[2];                // sample 0 of this frame for each chain
+    int ostride;
+};
+
+// ONLY_LONG / LONG_START / LONG_STOP for chains C0..C0+NCH-1.  Leaves the
+// frame's PCM in `o`; the staging buffer is no longer read when it returns
+// (callers still need a barrier before overwriting it).
+template <int C0, int NCH, class Sync>
+AACFB_HD void frame_long(int u, Sync &sync, const FrameIO &io, const SynthTables *ts, const SynthTables *tg,
+                         Pts &z, Ovl &ov, Out &o) {
+    const float *row[2] = {io.stage, io.stage + kRowFloats};
+    float2 *buf[2] = {reinterpret_cast<float2 *>(io.stage), reinterpret_cast<float2 *>(io.stage + kRowFloats)};
+    long_load<C0, NCH>(u, row, ts->cs2048, z);
+    pass_a<C0, NCH>(z, ts->rootsA);
+    sync.barrier();  // every thread has consumed the rows
+    ex1_write<C0, NCH>(u, z, buf);
+    sync.barrier();
+    ex1_read<C0, NCH>(u, buf, z);
+    pass_3stage<C0, NCH>(z, ts->twB + 7 * passb_blo(u));
+    sync.barrier();
+    ex2_write<C0, NCH>(u, z, buf);
+    sync.barrier();
+    ex2_read<C0, NCH>(u, buf, z);
+    float2 twc[7];
+#pragma unroll
+    for (int j = 0; j < 7; ++j) twc[j] = ts->twC[j][u];
+    pass_3stage<C0, NCH>(z, twc);
+    LongWin win[2];
+#pragma unroll
+    for (int c = C0; c < C0 + NCH; ++c) win[c] = long_windows(io.fi[c], ts->wz, tg);
+    long_finish<C0, NCH>(u, z, ov, ts->cs2048, win, io.emit, io.scale, o);
+}
+
+// The 8 x 64-point FFTs of EIGHT_SHORT for chains C0..C0+NCH-1; leaves the
+// un-twiddled bins in z.
+template <int C0, int NCH, class Sync>
+AACFB_HD void frame_short_fft(int u, Sync &sync, const FrameIO &io, const SynthTables *ts, Pts &z) {
+    const float *row[2] = {io.stage, io.stage + kRowFloats};
+    float2 *buf[2] = {reinterpret_cast<float2 *>(io.stage), reinterpret_cast<float2 *>(io.stage + kRowFloats)};
+    short_load<C0, NCH>(u, row, ts->cs256, z);
+    pass_a<C0, NCH>(z, ts->roots64A);
+    sync.barrier();
+    exs_write<C0, NCH>(u, z, buf);
+    sync.barrier();
+    exs_read<C0, NCH>(u, buf, z);
+    pass_3stage<C0, NCH>(z, ts->twS + 7 * (u & 7));
+}
+
+// Window + overlap-add of chain C of an EIGHT_SHORT frame.  Needs the whole
+// staging buffer: barrier first, since other threads may still be reading
+// exchange data out of it.
+template <int C, class Sync>
+AACFB_HD void frame_short_ola(int u, Sync &sync, const FrameIO &io, const SynthTables *ts, const Pts &z, Ovl &ov,
+                              Out &o) {
+    sync.barrier();
+    short_scatter<C>(u, z, ts->cs256, io.stage);
+    sync.barrier();
+    short_finish<C>(u, io.stage, ov, io.fi[C], ts->wshort, io.emit, io.scale, o);
+}
+
+AACFB_HD bool is_short(const aacfb_frame_info &fi) { return fi.window_sequence == AACFB_EIGHT_SHORT_SEQUENCE; }
+
+// One frame of the worker's (up to) two chains.
+template <class Sync>
+AACFB_HD void worker_frame(int u, Sync &sync, const FrameIO &io, const SynthTables *ts, const SynthTables *tg, Pts &z,
+                           Ovl &ov) {
+    Out o;
+    const bool s0 = is_short(io.fi[0]);
+    const bool s1 = io.nch == 2 && is_short(io.fi[1]);
+    if (io.nch == 1) {
+        if (!s0) frame_long<0, 1>(u, sync, io, ts, tg, z, ov, o);
+        else { frame_short_fft<0, 1>(u, sync, io, ts, z); frame_short_ola<0>(u, sync, io, ts, z, ov, o); }
+    } else if (!s0 && !s1) {
+        frame_long<0, 2>(u, sync, io, ts, tg, z, ov, o);
+    } else if (s0 && s1) {
+        frame_short_fft<0, 2>(u, sync, io, ts, z);
+        frame_short_ola<0>(u, sync, io, ts, z, ov, o);
+        frame_short_ola<1>(u, sync, io, ts, z, ov, o);
+    } else if (s0) {  // chain 1 long first (touches only its own row), then chain 0 short
+        frame_long<1, 1>(u, sync, io, ts, tg, z, ov, o);
+        frame_short_fft<0, 1>(u, sync, io, ts, z);
+        frame_short_ola<0>(u, sync, io, ts, z, ov, o);
+    } else {
+        frame_long<0, 1>(u, sync, io, ts, tg, z, ov, o);
+        frame_short_fft<1, 1>(u, sync, io, ts, z);
+        frame_short_ola<1>(u, sync, io, ts, z, ov, o);
+    }
+    if (io.emit) {
+        sync.barrier();  // nobody reads exchange / IMDCT data out of the stage any more
+        if (io.nch == 2) out_stage<0, 2>(u, o, io.stage, io.interleaved);
+        else out_stage<0, 1>(u, o, io.stage, false);
+        sync.barrier();
+        out_copy(u, io.stage, io.out, io.ostride, 0, io.nch, io.interleaved && io.nch == 2);
+    }
+    sync.stage_free();
+}
+
+// ------------------------------------------------------------ work geometry
+// The batch is S streams x T frames x nc channels.  Chain h = s*nc + j is one
+// (stream, channel) sequence through time; chains are paired (2i, 2i+1) and
+// time is cut into chunks of L frames.  One work item = (pair, chunk).  A
+// chunk that does not start at t = 0 first runs frame t0-1 as a *halo* (no
+// output) to rebuild the overlap that frame t0 needs: overlap[t] depends on
+// frame t alone (filter_bank.js:114-116), so no state crosses items.
+struct Geometry {
+    int S, T, nc;        // batch shape: spectra [S][T][nc][1024], pcm [S][T][1024][nc]
+    int c_state, c0;     // overlap state is [*][c_state][1024]; chain j is state channel c0+j
+    int s_base;          // first stream of this batch in the overlap state
+    int L, n_chunks, n_pairs;
+};
+AACFB_HD Geometry make_geometry(int S, int T, int nc, int c_state, int c0, int s_base, int L) {
+    Geometry g;
+    g.S = S; g.T = T; g.nc = nc; g.c_state = c_state; g.c0 = c0; g.s_base = s_base;
+    g.L = L < 1 ? 1 : L;
+    g.n_chunks = (T + g.L - 1) / g.L;
+    g.n_pairs = (S * nc + 1) / 2;
+    return g;
+}
+struct Item {
+    int nch;             // live chains
+    int s[2], j[2];      // stream / channel-in-batch of each chain
+    int t0, t1;          // frames [t0, t1) are emitted
+    bool interleaved;
+};
+AACFB_HD Item make_item(const Geometry &g, int item) {
+    Item it;
+    const int pair = item / g.n_chunks, chunk = item % g.n_chunks;
+    const int h0 = 2 * pair, total = g.S * g.nc;
+    it.nch = (h0 + 1 < total) ? 2 : 1;
+    for (int c = 0; c < 2; ++c) {
+        const int h = (h0 + c < total) ? h0 + c : h0;
+        it.s[c] = h / g.nc;
+        it.j[c] = h % g.nc;
+    }
+    it.t0 = chunk * g.L;
+    it.t1 = it.t0 + g.L < g.T ? it.t0 + g.L : g.T;
+    it.interleaved = it.nch == 2 && g.nc == 2 && it.s[0] == it.s[1] && it.j[0] == 0;
+    return it;
+}
+AACFB_HD size_t cf_index(const Geometry &g, int s, int t, int j) { return ((size_t)s * g.T + t) * g.nc + j; }
+AACFB_HD size_t state_index(const Geometry &g, int s, int j) {
+    return ((size_t)(g.s_base + s) * g.c_state + g.c0 + j) * 1024;
+}
+
+}  // namespace aacfb
