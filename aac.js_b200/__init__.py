@@ -1,0 +1,282 @@
+"""aac.js_b200 -- host-side mirror of the aac.js filterbank seam over the B200 C-ABI.
+
+The reference is JavaScript; no JS runtime exists in this image, so the host
+side that tests and benchmarks drive is this Python mirror of the reference's
+own interface for the path (same class names, argument meaning and error
+behaviour):
+
+    FilterBank(smallFrames, channels).process(info, input, output, channel)
+        reference src/filter_bank.js:24-44, 88-204
+    TNS(config).process(ics, data, decode)
+        reference src/tns.js:22-44, 105-177
+    AACDecoder.process(elements) + the interleave of readChunk
+        reference src/decoder.js:204-213, 218-334
+
+Everything is a thin ctypes call into ``libaacfb.so`` (include/aacfb.h) -- the
+same C entry points the N-API addon in ``js/`` binds.  There is NO CPU
+implementation here: if the CUDA library is missing or no sm_100 device is
+usable, construction raises.  (Because the directory name contains a dot the
+package is imported through the ``aacjs_b200`` shim at the repo root.)
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libaacfb.so")
+
+ONLY_LONG_SEQUENCE, LONG_START_SEQUENCE, EIGHT_SHORT_SEQUENCE, LONG_STOP_SEQUENCE = 0, 1, 2, 3  # ics.js:44-47
+TNS_AS_SHIPPED, TNS_FIXED_AR, TNS_FIXED_MA = 0, 1, 2
+TNS_MAX_ORDER = 20  # tns.js:46
+
+INFO_DTYPE = np.dtype(
+    [("window_sequence", "u1"), ("shape_prev", "u1"), ("shape_cur", "u1"),
+     ("max_sfb", "u1"), ("tns_present", "u1"), ("reserved", "u1", (3,))])
+
+ERRORS = {-1: "AACFB_ERR_ARG", -2: "AACFB_ERR_SMALL", -3: "AACFB_ERR_SEQUENCE", -4: "AACFB_ERR_TNS",
+          -5: "AACFB_ERR_CUDA", -6: "AACFB_ERR_NOMEM"}
+
+# every symbol include/aacfb.h declares
+ABI_SYMBOLS = ["aacfb_create", "aacfb_destroy", "aacfb_reset", "aacfb_process", "aacfb_process_device",
+               "aacfb_filterbank_process", "aacfb_tns_process", "aacfb_get_overlap", "aacfb_set_overlap",
+               "aacfb_last_error", "aacfb_version", "aacfb_launch_count", "aacfb_get_table"]
+
+
+class AacfbError(RuntimeError):
+    """The JS shim rethrows library errors as ``Error(msg)``; this is its Python twin."""
+
+    def __init__(self, code, msg):
+        super().__init__(f"{ERRORS.get(code, code)}: {msg}")
+        self.code = code
+
+
+_lib = None
+
+
+def lib():
+    """Load libaacfb.so; raises (never falls back) when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                              "(there is no CPU implementation of this path)")
+        L = C.CDLL(LIB_PATH)
+        vp, ci, u32 = C.c_void_p, C.c_int, C.c_uint32
+        L.aacfb_create.argtypes = [C.POINTER(vp), ci, ci, ci, ci, ci, u32]
+        L.aacfb_destroy.argtypes = [vp]
+        L.aacfb_reset.argtypes = [vp]
+        L.aacfb_process.argtypes = [vp, vp, vp, vp, vp, vp, ci]
+        L.aacfb_process_device.argtypes = [vp, vp, vp, vp, vp, C.c_size_t, vp, ci, vp]
+        L.aacfb_filterbank_process.argtypes = [vp, ci, ci, vp, vp, vp]
+        L.aacfb_tns_process.argtypes = [vp, vp, vp, C.c_size_t, vp, u32]
+        L.aacfb_get_overlap.argtypes = [vp, vp]
+        L.aacfb_set_overlap.argtypes = [vp, vp]
+        L.aacfb_last_error.argtypes = [vp]
+        L.aacfb_last_error.restype = C.c_char_p
+        L.aacfb_launch_count.argtypes = [vp]
+        L.aacfb_launch_count.restype = C.c_uint64
+        L.aacfb_get_table.argtypes = [ci, vp, ci]
+        _lib = L
+    return _lib
+
+
+def _ptr(a):
+    return None if a is None else C.c_void_p(a.ctypes.data)
+
+
+def get_table(which: int) -> np.ndarray:
+    out = np.empty(1024, np.float32)
+    n = lib().aacfb_get_table(which, _ptr(out), out.size)
+    if n < 0:
+        raise AacfbError(n, "bad table index")
+    return out[:n].copy()
+
+
+class Context:
+    """One aacfb_ctx: S decoder instances of `channels` channels on one GPU."""
+
+    def __init__(self, n_streams=1, channels=2, sample_index=4, flags=TNS_AS_SHIPPED, device=0, small_frames=False):
+        self._h = C.c_void_p()
+        self.n_streams, self.channels, self.sample_index, self.flags = n_streams, channels, sample_index, flags
+        rc = lib().aacfb_create(C.byref(self._h), device, n_streams, channels, sample_index, int(bool(small_frames)),
+                                flags)
+        if rc != 0:
+            raise AacfbError(rc, lib().aacfb_last_error(None).decode())
+
+    def _check(self, rc):
+        if rc != 0:
+            raise AacfbError(rc, lib().aacfb_last_error(self._h).decode())
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            lib().aacfb_destroy(self._h)
+            self._h = C.c_void_p()
+
+    __del__ = close
+
+    def reset(self):
+        self._check(lib().aacfb_reset(self._h))
+
+    @property
+    def launches(self) -> int:
+        return int(lib().aacfb_launch_count(self._h))
+
+    def get_overlap(self) -> np.ndarray:
+        out = np.empty((self.n_streams, self.channels, 1024), np.float32)
+        self._check(lib().aacfb_get_overlap(self._h, _ptr(out)))
+        return out
+
+    def set_overlap(self, ov):
+        ov = np.ascontiguousarray(ov, np.float32)
+        assert ov.shape == (self.n_streams, self.channels, 1024)
+        self._check(lib().aacfb_set_overlap(self._h, _ptr(ov)))
+
+    def process(self, spectra, info, tns_blob=None, tns_offsets=None, out=None) -> np.ndarray:
+        """Batched hot path with host arrays: spectra [S][T][C][1024] -> pcm [S][T][1024][C]."""
+        spectra = np.ascontiguousarray(spectra, np.float32)
+        S, T, Cn, n = spectra.shape
+        assert (S, Cn, n) == (self.n_streams, self.channels, 1024), spectra.shape
+        info = np.ascontiguousarray(info, INFO_DTYPE)
+        assert info.size == S * T * Cn
+        if tns_blob is not None:
+            tns_blob = np.ascontiguousarray(tns_blob, np.uint8)
+            tns_offsets = np.ascontiguousarray(tns_offsets, np.uint32)
+            assert tns_offsets.size == S * T * Cn + 1
+        pcm = out if out is not None else np.empty((S, T, 1024, Cn), np.float32)
+        assert pcm.dtype == np.float32 and pcm.flags.c_contiguous and pcm.size == spectra.size
+        self._check(lib().aacfb_process(self._h, _ptr(spectra), _ptr(info), _ptr(tns_blob), _ptr(tns_offsets),
+                                        _ptr(pcm), T))
+        return pcm
+
+    def process_device(self, d_spectra: int, d_info: int, d_pcm: int, n_frames: int, stream: int = 0,
+                       d_tns_blob: int = 0, d_tns_offsets: int = 0, tns_blob_bytes: int = 0):
+        """Same with raw device addresses (e.g. torch.Tensor.data_ptr()), enqueued on `stream`."""
+        self._check(lib().aacfb_process_device(self._h, C.c_void_p(d_spectra), C.c_void_p(d_info),
+                                               C.c_void_p(d_tns_blob or None), C.c_void_p(d_tns_offsets or None),
+                                               tns_blob_bytes, C.c_void_p(d_pcm), n_frames, C.c_void_p(stream or None)))
+
+
+# ---------------------------------------------------------------------------
+# Mirrors of the reference's JS classes for this path
+# ---------------------------------------------------------------------------
+def _info_record(info) -> np.ndarray:
+    """Accept a JS-like ICSInfo (attributes or dict: windowSequence, windowShape[2], maxSFB)."""
+    get = (lambda k, d=0: info.get(k, d)) if isinstance(info, dict) else (lambda k, d=0: getattr(info, k, d))
+    r = np.zeros((), INFO_DTYPE)
+    shape = get("windowShape", (0, 0))
+    r["window_sequence"] = get("windowSequence")
+    r["shape_prev"], r["shape_cur"] = shape[0], shape[1]
+    r["max_sfb"] = get("maxSFB", 0)
+    return r
+
+
+class FilterBank:
+    """`new FilterBank(smallFrames, channels)` -- filter_bank.js:24-44."""
+
+    def __init__(self, smallFrames, channels, *, device=0, sample_index=4, ctx: Context | None = None, stream=0):
+        if smallFrames:
+            raise AacfbError(-2, "WHA?? No small frames allowed.")  # filter_bank.js:26
+        self.ctx = ctx or Context(1, channels, sample_index, TNS_AS_SHIPPED, device)
+        self.stream = stream
+        self.length, self.shortLength = 1024, 128
+
+    @property
+    def overlaps(self):
+        return self.ctx.get_overlap()[self.stream]
+
+    def process(self, info, input, output, channel):
+        """filterBank.process(info, input, output, channel) -- filter_bank.js:88-204.
+
+        Reads `input` (1024 floats), fully overwrites `output`, updates overlaps[channel]."""
+        rec = _info_record(info)
+        x = np.ascontiguousarray(input, np.float32)
+        assert x.size == 1024 and output.dtype == np.float32 and output.size == 1024 and output.flags.c_contiguous
+        self.ctx._check(lib().aacfb_filterbank_process(self.ctx._h, self.stream, channel, _ptr(rec), _ptr(x),
+                                                       _ptr(output)))
+
+
+class TNS:
+    """`new TNS(config)` -- tns.js:22-44.  decode() (the bit parse) stays in the JS host."""
+
+    def __init__(self, config=None, *, ctx: Context | None = None, mode=None):
+        cfg = config or {}
+        self.sampleIndex = cfg.get("sampleIndex", 4) if isinstance(cfg, dict) else getattr(cfg, "sampleIndex", 4)
+        self.nFilt = np.zeros(8, np.int32)
+        self.length = np.zeros((8, 4), np.int32)
+        self.direction = np.zeros((8, 4), bool)
+        self.order = np.zeros((8, 4), np.int32)
+        self.coef = np.zeros((8, 4, TNS_MAX_ORDER), np.float32)
+        self._ctx = ctx
+        self.mode = mode  # None: "tmp -> top" fixed, branch chosen by `decode`
+
+    def block(self) -> bytes:
+        """Serialise to one block of the aacfb.h TNS blob."""
+        out = bytearray(int(v) for v in self.nFilt)
+        for w in range(8):
+            for f in range(int(self.nFilt[w])):
+                order = int(self.order[w][f])
+                if order > TNS_MAX_ORDER:
+                    raise AacfbError(-4, f"TNS filter out of range: {order}")  # tns.js:85
+                out += bytes([int(self.length[w][f]), order, int(bool(self.direction[w][f])), 0])
+                out += np.asarray(self.coef[w][f][:order], np.float32).tobytes()
+        return bytes(out)
+
+    def process(self, ics, data, decode):
+        """tns.process(ics, data, decode) -- tns.js:105-177, in place on `data` (Float32, 1024).
+
+        mode=TNS_AS_SHIPPED reproduces the reference as it stands (identity, tns.js:122);
+        otherwise `decode` selects the AR (:156-162) or MA (:163-174) branch."""
+        mode = self.mode if self.mode is not None else (TNS_FIXED_AR if decode else TNS_FIXED_MA)
+        info = ics["info"] if isinstance(ics, dict) else ics.info
+        rec = _info_record(info)
+        rec["max_sfb"] = ics["maxSFB"] if isinstance(ics, dict) else ics.maxSFB  # tns.js:106 reads ics.maxSFB
+        ctx = self._ctx or Context(1, 1, self.sampleIndex, TNS_AS_SHIPPED, 0)
+        assert data.dtype == np.float32 and data.size == 1024 and data.flags.c_contiguous
+        blk = np.frombuffer(self.block(), np.uint8)
+        ctx._check(lib().aacfb_tns_process(ctx._h, _ptr(rec), _ptr(blk), blk.size, _ptr(data), mode))
+
+
+def pack_tns(blocks):
+    """[bytes|None per channel-frame] -> (blob u8, offsets u32[n+1]) in the aacfb.h layout."""
+    offs, blob = [0], bytearray()
+    for b in blocks:
+        if b:
+            blob += b
+            blob += b"\0" * (-len(blob) % 4)
+        offs.append(len(blob))
+    return (np.frombuffer(bytes(blob), np.uint8).copy() if blob else np.zeros(4, np.uint8)), np.asarray(offs, np.uint32)
+
+
+class AACDecoder:
+    """The slice of AACDecoder this path replaces: `process(elements)` + the
+    interleave of `readChunk` (decoder.js:204-213, 218-334), batched over K frames.
+
+    `frames` is a list of frames, each a list of per-channel dicts
+    {"info": ICSInfo-like, "data": Float32[1024], "tnsPresent": bool, "tns": TNS, "maxSFB": int}
+    -- what ICStream.decode leaves behind (ics.js:56-81) after M/S and IS."""
+
+    def __init__(self, channels, sample_index=4, *, device=0, tns_mode=TNS_AS_SHIPPED):
+        self.config = {"chanConfig": channels, "sampleIndex": sample_index, "frameLength": 1024}
+        self.ctx = Context(1, channels, sample_index, tns_mode, device)
+        self.filter_bank = self.ctx  # decoder.js:112
+
+    def readChunks(self, frames) -> np.ndarray:
+        T, Cn = len(frames), self.config["chanConfig"]
+        spectra = np.empty((1, T, Cn, 1024), np.float32)
+        info = np.zeros((1, T, Cn), INFO_DTYPE)
+        blocks = []
+        for t, fr in enumerate(frames):
+            assert len(fr) == Cn
+            for c, ch in enumerate(fr):
+                spectra[0, t, c] = ch["data"]
+                rec = _info_record(ch["info"])
+                rec["max_sfb"] = ch.get("maxSFB", 0)
+                rec["tns_present"] = 1 if ch.get("tnsPresent") else 0
+                info[0, t, c] = rec
+                blocks.append(ch["tns"].block() if ch.get("tnsPresent") else None)
+        blob, offs = pack_tns(blocks)
+        pcm = self.ctx.process(spectra, info, blob, offs)
+        return pcm.reshape(T * 1024 * Cn)  # K frames of readChunk output back to back

@@ -1,0 +1,447 @@
+// aacfb_api.cu -- the C ABI of include/aacfb.h on top of the sm_100a kernels.
+//
+// No CPU fallback lives here: every compute entry point needs a CUDA device
+// that can run the sm_100a image and fails with AACFB_ERR_CUDA otherwise.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <vector>
+
+#include "../../include/aacfb.h"
+#include "aacfb_kernels.h"
+#include "aacfb_tables.h"
+
+using namespace aacfb;
+
+namespace {
+
+constexpr int kLanes = 2;        // host-path pipeline depth (H2D | kernel | D2H overlap)
+constexpr int kCounters = 64;
+
+thread_local char g_err[256] = "";
+
+struct Lane {                    // device staging of one in-flight sub-batch of the host path
+    cudaStream_t stream = nullptr;
+    float *d_spectra = nullptr, *d_pcm = nullptr, *d_scratch = nullptr;
+    aacfb_frame_info *d_info = nullptr;
+    uint32_t *d_offsets = nullptr;
+    size_t cap_cf = 0;           // capacity in channel-frames
+    size_t cap_scratch = 0;
+};
+
+}  // namespace
+
+struct aacfb_ctx {
+    int device = 0, S = 0, C = 0, sample_index = 0, num_sms = 0;
+    uint32_t flags = 0;
+    float *d_ovl[2] = {nullptr, nullptr};
+    int cur = 0;
+    SynthTables *d_tab = nullptr;
+    TnsBandTables *d_bands = nullptr;
+    unsigned *d_counters = nullptr;
+    unsigned counter_next = 0;
+    Lane lane[kLanes];
+    uint8_t *d_blob = nullptr;
+    size_t cap_blob = 0;
+    float *d_dev_scratch = nullptr;  // scratch of the device-pointer path
+    size_t cap_dev_scratch = 0;
+    uint64_t launches = 0;
+    char err[256] = "";
+};
+
+namespace {
+
+int fail(aacfb_ctx *ctx, int code, const char *fmt, ...) {
+    char buf[256];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    std::snprintf(g_err, sizeof g_err, "%s", buf);
+    if (ctx) std::snprintf(ctx->err, sizeof ctx->err, "%s", buf);
+    return code;
+}
+
+#define CU(ctx, call)                                                                                   \
+    do {                                                                                                \
+        cudaError_t e__ = (call);                                                                       \
+        if (e__ != cudaSuccess)                                                                         \
+            return fail(ctx, AACFB_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__),   \
+                        __FILE__, __LINE__);                                                            \
+    } while (0)
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+        else prev = -1;
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+// Chunk length: minimise (waves of items over the worker pool) x (frames per
+// item incl. the halo frame), preferring longer chunks on ties.
+int pick_chunk(int n_pairs, int T, int workers) {
+    long best_cost = -1;
+    int best_L = T;
+    for (int L = T; L >= 1; --L) {
+        const int chunks = (T + L - 1) / L;
+        const long items = (long)n_pairs * chunks;
+        const long waves = (items + workers - 1) / workers;
+        const long cost = waves * (L + (chunks > 1 ? 1 : 0));
+        if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_L = L; }
+    }
+    return best_L;
+}
+
+// Enqueue TNS pre-pass (if the context's mode asks for it) and the synthesis
+// kernel for S_sub streams starting at stream s_base, all on `stream`.
+int enqueue(aacfb_ctx *ctx, const float *d_spectra, const aacfb_frame_info *d_info, const uint8_t *d_blob,
+            const uint32_t *d_offsets, size_t blob_bytes, float *d_scratch, float *d_pcm, int S_sub, int s_base,
+            int T, int nc, int c0, float scale, bool in_place_state, cudaStream_t stream) {
+    const uint32_t mode = ctx->flags & AACFB_TNS_MODE_MASK;
+    const size_t n_cf = (size_t)S_sub * T * nc;
+    const bool tns_on = mode != AACFB_TNS_AS_SHIPPED && d_blob && d_offsets && blob_bytes > 0 && d_scratch;
+    if (tns_on) {
+        TnsParams tp{};
+        tp.spectra = d_spectra; tp.scratch = d_scratch; tp.info = d_info; tp.blob = d_blob; tp.offsets = d_offsets;
+        tp.blob_bytes = blob_bytes; tp.n_cf = n_cf; tp.sample_index = ctx->sample_index;
+        tp.ar = mode == AACFB_TNS_FIXED_AR; tp.bands = ctx->d_bands;
+        CU(ctx, launch_tns(tp, stream));
+        ctx->launches++;
+    }
+    SynthParams sp{};
+    sp.spectra = d_spectra; sp.scratch = tns_on ? d_scratch : nullptr; sp.info = d_info; sp.pcm = d_pcm;
+    sp.ovl_in = ctx->d_ovl[ctx->cur];
+    sp.ovl_out = in_place_state ? ctx->d_ovl[ctx->cur] : ctx->d_ovl[ctx->cur ^ 1];
+    sp.tab = ctx->d_tab;
+    const int n_pairs = (S_sub * nc + 1) / 2;
+    const int L = in_place_state ? T : pick_chunk(n_pairs, T, ctx->num_sms * kWorkers);
+    sp.g = make_geometry(S_sub, T, nc, ctx->C, c0, s_base, L);
+    sp.n_items = sp.g.n_pairs * sp.g.n_chunks;
+    sp.scale = scale;
+    sp.counter = ctx->d_counters + (ctx->counter_next++ % kCounters);
+    CU(ctx, cudaMemsetAsync(sp.counter, 0, sizeof(unsigned), stream));
+    const int grid = std::max(1, std::min(ctx->num_sms, (sp.n_items + kWorkers - 1) / kWorkers));
+    CU(ctx, launch_synth(sp, grid, stream));
+    ctx->launches++;
+    return AACFB_OK;
+}
+
+int grow_lane(aacfb_ctx *ctx, Lane &ln, size_t n_cf, bool need_scratch) {
+    if (n_cf > ln.cap_cf) {
+        cudaFree(ln.d_spectra); cudaFree(ln.d_pcm); cudaFree(ln.d_info); cudaFree(ln.d_offsets);
+        ln.d_spectra = ln.d_pcm = nullptr; ln.d_info = nullptr; ln.d_offsets = nullptr; ln.cap_cf = 0;
+        CU(ctx, cudaMalloc(&ln.d_spectra, n_cf * 4096));
+        CU(ctx, cudaMalloc(&ln.d_pcm, n_cf * 4096));
+        CU(ctx, cudaMalloc(&ln.d_info, n_cf * sizeof(aacfb_frame_info)));
+        CU(ctx, cudaMalloc(&ln.d_offsets, (n_cf + 1) * sizeof(uint32_t)));
+        ln.cap_cf = n_cf;
+    }
+    if (need_scratch && n_cf > ln.cap_scratch) {
+        cudaFree(ln.d_scratch); ln.d_scratch = nullptr; ln.cap_scratch = 0;
+        CU(ctx, cudaMalloc(&ln.d_scratch, n_cf * 4096));
+        ln.cap_scratch = n_cf;
+    }
+    return AACFB_OK;
+}
+
+// Host-side validation of the side info (the reference throws on these:
+// tns.js:84-85; unknown window sequences cannot occur there, ics.js:282).
+int validate(aacfb_ctx *ctx, const aacfb_frame_info *info, const uint8_t *blob, const uint32_t *offsets, size_t n_cf) {
+    for (size_t i = 0; i < n_cf; ++i) {
+        if (info[i].window_sequence > 3)
+            return fail(ctx, AACFB_ERR_SEQUENCE, "channel-frame %zu: window_sequence %u out of range", i,
+                        (unsigned)info[i].window_sequence);
+        if (!info[i].tns_present || !blob || !offsets) continue;
+        const uint32_t o0 = offsets[i], o1 = offsets[i + 1];
+        if (o1 < o0 || (o0 & 3)) return fail(ctx, AACFB_ERR_TNS, "channel-frame %zu: bad TNS offsets", i);
+        if (o1 == o0) continue;
+        if (o1 - o0 < 8) return fail(ctx, AACFB_ERR_TNS, "channel-frame %zu: TNS block too short", i);
+        const uint8_t *b = blob + o0;
+        uint32_t pos = 8;
+        for (int w = 0; w < 8; ++w)
+            for (int f = 0; f < b[w]; ++f) {
+                if (pos + 4 > o1 - o0) return fail(ctx, AACFB_ERR_TNS, "channel-frame %zu: truncated TNS block", i);
+                const unsigned order = b[pos + 1];
+                if (order > AACFB_TNS_MAX_ORDER)
+                    return fail(ctx, AACFB_ERR_TNS, "TNS filter out of range: %u", order);  // tns.js:85
+                pos += 4 + 4 * order;
+                if (pos > o1 - o0) return fail(ctx, AACFB_ERR_TNS, "channel-frame %zu: truncated TNS block", i);
+            }
+    }
+    return AACFB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+#define API __attribute__((visibility("default")))
+
+API int aacfb_version(void) { return 100; }
+
+API const char *aacfb_last_error(const aacfb_ctx *ctx) { return ctx ? ctx->err : g_err; }
+
+API uint64_t aacfb_launch_count(const aacfb_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+API int aacfb_get_table(int which, float *dst, int capacity) {
+    if (!dst) return AACFB_ERR_ARG;
+    const HostTables &H = host_tables();
+    const float *src = nullptr;
+    int n = 0;
+    switch (which) {
+    case 0: src = &H.roots512[0][0]; n = 1024; break;
+    case 1: src = &H.roots64[0][0]; n = 128; break;
+    case 2: src = &H.synth.cs2048[0].x; n = 1024; break;
+    case 3: src = &H.synth.cs256[0].x; n = 128; break;
+    case 4: src = H.sine1024; n = 1024; break;
+    case 5: src = H.kbd1024; n = 1024; break;
+    case 6: src = H.sine128; n = 128; break;
+    case 7: src = H.kbd128; n = 128; break;
+    default: return AACFB_ERR_ARG;
+    }
+    if (capacity < n) return AACFB_ERR_ARG;
+    std::memcpy(dst, src, sizeof(float) * n);
+    return n;
+}
+
+API int aacfb_create(aacfb_ctx **out, int device, int n_streams, int channels, int sample_index, int small_frames,
+                     uint32_t flags) {
+    if (!out) return fail(nullptr, AACFB_ERR_ARG, "null out pointer");
+    *out = nullptr;
+    if (small_frames) return fail(nullptr, AACFB_ERR_SMALL, "WHA?? No small frames allowed.");  // filter_bank.js:26
+    if (n_streams < 1 || channels < 1 || channels > AACFB_MAX_CHANNELS)
+        return fail(nullptr, AACFB_ERR_ARG, "n_streams/channels out of range");
+    if (sample_index < 0 || sample_index > 11) return fail(nullptr, AACFB_ERR_ARG, "sample_index must be 0..11");
+    if ((flags & AACFB_TNS_MODE_MASK) == 3u || (flags & ~AACFB_TNS_MODE_MASK))
+        return fail(nullptr, AACFB_ERR_ARG, "unknown flags");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, AACFB_ERR_CUDA, "no CUDA device: %s (this library has no CPU path)", cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return fail(nullptr, AACFB_ERR_ARG, "device %d out of range", device);
+    aacfb_ctx *ctx = new (std::nothrow) aacfb_ctx;
+    if (!ctx) return fail(nullptr, AACFB_ERR_NOMEM, "out of memory");
+    ctx->device = device; ctx->S = n_streams; ctx->C = channels; ctx->sample_index = sample_index; ctx->flags = flags;
+    DeviceGuard guard(device);
+    cudaDeviceProp prop;
+    auto bail = [&](cudaError_t err, const char *what) {
+        const int rc = fail(nullptr, AACFB_ERR_CUDA, "%s: %s", what, cudaGetErrorString(err));
+        aacfb_destroy(ctx);
+        return rc;
+    };
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return bail(e, "cudaGetDeviceProperties");
+    if (prop.major != 10) {
+        aacfb_destroy(ctx);
+        return fail(nullptr, AACFB_ERR_CUDA, "device %d is sm_%d%d; this library ships sm_100a code only", device,
+                    prop.major, prop.minor);
+    }
+    ctx->num_sms = prop.multiProcessorCount;
+    const size_t ovl_bytes = (size_t)n_streams * channels * 4096;
+    for (int i = 0; i < 2; ++i) {
+        if ((e = cudaMalloc(&ctx->d_ovl[i], ovl_bytes)) != cudaSuccess) return bail(e, "cudaMalloc overlap");
+        if ((e = cudaMemset(ctx->d_ovl[i], 0, ovl_bytes)) != cudaSuccess) return bail(e, "cudaMemset overlap");
+    }
+    if ((e = cudaMalloc(&ctx->d_tab, sizeof(SynthTables))) != cudaSuccess) return bail(e, "cudaMalloc tables");
+    if ((e = cudaMemcpy(ctx->d_tab, &host_tables().synth, sizeof(SynthTables), cudaMemcpyHostToDevice)) != cudaSuccess)
+        return bail(e, "cudaMemcpy tables");
+    if ((e = cudaMalloc(&ctx->d_bands, sizeof(TnsBandTables))) != cudaSuccess) return bail(e, "cudaMalloc bands");
+    if ((e = cudaMemcpy(ctx->d_bands, &tns_band_tables(), sizeof(TnsBandTables), cudaMemcpyHostToDevice)) != cudaSuccess)
+        return bail(e, "cudaMemcpy bands");
+    if ((e = cudaMalloc(&ctx->d_counters, kCounters * sizeof(unsigned))) != cudaSuccess) return bail(e, "cudaMalloc");
+    for (int i = 0; i < kLanes; ++i)
+        if ((e = cudaStreamCreateWithFlags(&ctx->lane[i].stream, cudaStreamNonBlocking)) != cudaSuccess)
+            return bail(e, "cudaStreamCreate");
+    *out = ctx;
+    return AACFB_OK;
+}
+
+API int aacfb_destroy(aacfb_ctx *ctx) {
+    if (!ctx) return AACFB_OK;
+    DeviceGuard guard(ctx->device);
+    cudaDeviceSynchronize();
+    for (int i = 0; i < kLanes; ++i) {
+        Lane &ln = ctx->lane[i];
+        if (ln.stream) cudaStreamDestroy(ln.stream);
+        cudaFree(ln.d_spectra); cudaFree(ln.d_pcm); cudaFree(ln.d_scratch); cudaFree(ln.d_info); cudaFree(ln.d_offsets);
+    }
+    cudaFree(ctx->d_ovl[0]); cudaFree(ctx->d_ovl[1]); cudaFree(ctx->d_tab); cudaFree(ctx->d_bands);
+    cudaFree(ctx->d_counters); cudaFree(ctx->d_blob); cudaFree(ctx->d_dev_scratch);
+    delete ctx;
+    return AACFB_OK;
+}
+
+API int aacfb_reset(aacfb_ctx *ctx) {
+    if (!ctx) return fail(nullptr, AACFB_ERR_ARG, "null context");
+    DeviceGuard guard(ctx->device);
+    CU(ctx, cudaDeviceSynchronize());
+    CU(ctx, cudaMemset(ctx->d_ovl[ctx->cur], 0, (size_t)ctx->S * ctx->C * 4096));
+    return AACFB_OK;
+}
+
+API int aacfb_get_overlap(aacfb_ctx *ctx, float *overlap) {
+    if (!ctx || !overlap) return fail(ctx, AACFB_ERR_ARG, "null argument");
+    DeviceGuard guard(ctx->device);
+    CU(ctx, cudaDeviceSynchronize());
+    CU(ctx, cudaMemcpy(overlap, ctx->d_ovl[ctx->cur], (size_t)ctx->S * ctx->C * 4096, cudaMemcpyDeviceToHost));
+    return AACFB_OK;
+}
+
+API int aacfb_set_overlap(aacfb_ctx *ctx, const float *overlap) {
+    if (!ctx || !overlap) return fail(ctx, AACFB_ERR_ARG, "null argument");
+    DeviceGuard guard(ctx->device);
+    CU(ctx, cudaDeviceSynchronize());
+    CU(ctx, cudaMemcpy(ctx->d_ovl[ctx->cur], overlap, (size_t)ctx->S * ctx->C * 4096, cudaMemcpyHostToDevice));
+    return AACFB_OK;
+}
+
+API int aacfb_process_device(aacfb_ctx *ctx, const float *d_spectra, const aacfb_frame_info *d_info,
+                             const uint8_t *d_tns_blob, const uint32_t *d_tns_offsets, size_t tns_blob_bytes,
+                             float *d_pcm, int n_frames, void *stream) {
+    if (!ctx) return fail(nullptr, AACFB_ERR_ARG, "null context");
+    if (n_frames < 0) return fail(ctx, AACFB_ERR_ARG, "negative frame count");
+    if (n_frames == 0) return AACFB_OK;
+    if (!d_spectra || !d_info || !d_pcm) return fail(ctx, AACFB_ERR_ARG, "null buffer");
+    if ((reinterpret_cast<uintptr_t>(d_spectra) | reinterpret_cast<uintptr_t>(d_pcm)) & 15)
+        return fail(ctx, AACFB_ERR_ARG, "spectra/pcm must be 16-byte aligned");
+    DeviceGuard guard(ctx->device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const uint32_t mode = ctx->flags & AACFB_TNS_MODE_MASK;
+    float *scratch = nullptr;
+    if (mode != AACFB_TNS_AS_SHIPPED && d_tns_blob && d_tns_offsets && tns_blob_bytes) {
+        const size_t n_cf = (size_t)ctx->S * n_frames * ctx->C;
+        if (n_cf > ctx->cap_dev_scratch) {
+            CU(ctx, cudaDeviceSynchronize());
+            cudaFree(ctx->d_dev_scratch); ctx->d_dev_scratch = nullptr; ctx->cap_dev_scratch = 0;
+            CU(ctx, cudaMalloc(&ctx->d_dev_scratch, n_cf * 4096));
+            ctx->cap_dev_scratch = n_cf;
+        }
+        scratch = ctx->d_dev_scratch;
+    }
+    const int rc = enqueue(ctx, d_spectra, d_info, d_tns_blob, d_tns_offsets, tns_blob_bytes, scratch, d_pcm, ctx->S, 0,
+                           n_frames, ctx->C, 0, 1.0f / 32768.0f, false, st);
+    if (rc != AACFB_OK) return rc;
+    ctx->cur ^= 1;
+    return AACFB_OK;
+}
+
+API int aacfb_process(aacfb_ctx *ctx, const float *spectra, const aacfb_frame_info *info, const uint8_t *tns_blob,
+                      const uint32_t *tns_offsets, float *pcm, int n_frames) {
+    if (!ctx) return fail(nullptr, AACFB_ERR_ARG, "null context");
+    if (n_frames < 0) return fail(ctx, AACFB_ERR_ARG, "negative frame count");
+    if (n_frames == 0) return AACFB_OK;
+    if (!spectra || !info || !pcm) return fail(ctx, AACFB_ERR_ARG, "null buffer");
+    const int S = ctx->S, C = ctx->C, T = n_frames;
+    const size_t per_stream = (size_t)T * C;
+    int rc = validate(ctx, info, tns_blob, tns_offsets, (size_t)S * per_stream);
+    if (rc != AACFB_OK) return rc;
+    DeviceGuard guard(ctx->device);
+    const uint32_t mode = ctx->flags & AACFB_TNS_MODE_MASK;
+    const bool tns_on = mode != AACFB_TNS_AS_SHIPPED && tns_blob && tns_offsets;
+    size_t blob_bytes = 0;
+    if (tns_on) {
+        blob_bytes = tns_offsets[(size_t)S * per_stream];
+        if (blob_bytes > ctx->cap_blob) {
+            CU(ctx, cudaDeviceSynchronize());
+            cudaFree(ctx->d_blob); ctx->d_blob = nullptr; ctx->cap_blob = 0;
+            CU(ctx, cudaMalloc(&ctx->d_blob, blob_bytes + 16));
+            ctx->cap_blob = blob_bytes;
+        }
+        if (blob_bytes) CU(ctx, cudaMemcpyAsync(ctx->d_blob, tns_blob, blob_bytes, cudaMemcpyHostToDevice, ctx->lane[0].stream));
+        CU(ctx, cudaStreamSynchronize(ctx->lane[0].stream));
+    }
+    // Sub-batches of whole streams, two in flight: the copy-in of one overlaps
+    // the kernel and copy-out of the other (PCIe is the bottleneck end to end).
+    int n_sub = std::min(S, 8);
+    if ((size_t)S * per_stream * 4096 < (size_t)(8u << 20)) n_sub = 1;
+    const int s_per = (S + n_sub - 1) / n_sub;
+    for (int i = 0; i < kLanes; ++i)
+        if ((rc = grow_lane(ctx, ctx->lane[i], (size_t)s_per * per_stream, tns_on && blob_bytes)) != AACFB_OK) return rc;
+    int li = 0;
+    for (int s0 = 0; s0 < S; s0 += s_per, li ^= 1) {
+        Lane &ln = ctx->lane[li];
+        const int sn = std::min(s_per, S - s0);
+        const size_t n_cf = (size_t)sn * per_stream, off = (size_t)s0 * per_stream;
+        // stream order makes reuse of this lane's buffers safe
+        CU(ctx, cudaMemcpyAsync(ln.d_spectra, spectra + off * 1024, n_cf * 4096, cudaMemcpyHostToDevice, ln.stream));
+        CU(ctx, cudaMemcpyAsync(ln.d_info, info + off, n_cf * sizeof(aacfb_frame_info), cudaMemcpyHostToDevice, ln.stream));
+        if (tns_on && blob_bytes)
+            CU(ctx, cudaMemcpyAsync(ln.d_offsets, tns_offsets + off, (n_cf + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, ln.stream));
+        rc = enqueue(ctx, ln.d_spectra, ln.d_info, (tns_on && blob_bytes) ? ctx->d_blob : nullptr, ln.d_offsets, blob_bytes,
+                     ln.d_scratch, ln.d_pcm, sn, s0, T, C, 0, 1.0f / 32768.0f, false, ln.stream);
+        if (rc != AACFB_OK) return rc;
+        CU(ctx, cudaMemcpyAsync(pcm + off * 1024, ln.d_pcm, n_cf * 4096, cudaMemcpyDeviceToHost, ln.stream));
+    }
+    for (int i = 0; i < kLanes; ++i) CU(ctx, cudaStreamSynchronize(ctx->lane[i].stream));
+    ctx->cur ^= 1;
+    return AACFB_OK;
+}
+
+API int aacfb_filterbank_process(aacfb_ctx *ctx, int stream, int channel, const aacfb_frame_info *info,
+                                 const float *input, float *output) {
+    if (!ctx || !info || !input || !output) return fail(ctx, AACFB_ERR_ARG, "null argument");
+    if (stream < 0 || stream >= ctx->S || channel < 0 || channel >= ctx->C)
+        return fail(ctx, AACFB_ERR_ARG, "stream/channel out of range");
+    if (info->window_sequence > 3) {  // filter_bank.js:104 has no default case: zero output, state untouched
+        std::memset(output, 0, 4096);
+        return AACFB_OK;
+    }
+    DeviceGuard guard(ctx->device);
+    Lane &ln = ctx->lane[0];
+    int rc = grow_lane(ctx, ln, 1, false);
+    if (rc != AACFB_OK) return rc;
+    aacfb_frame_info fi = *info;
+    fi.tns_present = 0;  // the inner seam is the filterbank alone
+    CU(ctx, cudaMemcpyAsync(ln.d_spectra, input, 4096, cudaMemcpyHostToDevice, ln.stream));
+    CU(ctx, cudaMemcpyAsync(ln.d_info, &fi, sizeof fi, cudaMemcpyHostToDevice, ln.stream));
+    rc = enqueue(ctx, ln.d_spectra, ln.d_info, nullptr, nullptr, 0, nullptr, ln.d_pcm, 1, stream, 1, 1, channel, 1.0f,
+                 true, ln.stream);
+    if (rc != AACFB_OK) return rc;
+    CU(ctx, cudaMemcpyAsync(output, ln.d_pcm, 4096, cudaMemcpyDeviceToHost, ln.stream));
+    CU(ctx, cudaStreamSynchronize(ln.stream));
+    return AACFB_OK;
+}
+
+API int aacfb_tns_process(aacfb_ctx *ctx, const aacfb_frame_info *info, const uint8_t *tns_block, size_t block_bytes,
+                          float *data, uint32_t mode) {
+    if (!ctx || !info || !data) return fail(ctx, AACFB_ERR_ARG, "null argument");
+    mode &= AACFB_TNS_MODE_MASK;
+    if (mode == 3u) return fail(ctx, AACFB_ERR_ARG, "unknown TNS mode");
+    if (mode == AACFB_TNS_AS_SHIPPED || !tns_block || block_bytes == 0) return AACFB_OK;  // identity, tns.js:122
+    aacfb_frame_info fi = *info;
+    fi.tns_present = 1;
+    const uint32_t offs[2] = {0, (uint32_t)block_bytes};
+    int rc = validate(ctx, &fi, tns_block, offs, 1);
+    if (rc != AACFB_OK) return rc;
+    DeviceGuard guard(ctx->device);
+    Lane &ln = ctx->lane[0];
+    if ((rc = grow_lane(ctx, ln, 1, true)) != AACFB_OK) return rc;
+    if (block_bytes > ctx->cap_blob) {
+        CU(ctx, cudaDeviceSynchronize());
+        cudaFree(ctx->d_blob); ctx->d_blob = nullptr; ctx->cap_blob = 0;
+        CU(ctx, cudaMalloc(&ctx->d_blob, block_bytes + 16));
+        ctx->cap_blob = block_bytes;
+    }
+    CU(ctx, cudaMemcpyAsync(ln.d_spectra, data, 4096, cudaMemcpyHostToDevice, ln.stream));
+    CU(ctx, cudaMemcpyAsync(ln.d_info, &fi, sizeof fi, cudaMemcpyHostToDevice, ln.stream));
+    CU(ctx, cudaMemcpyAsync(ln.d_offsets, offs, sizeof offs, cudaMemcpyHostToDevice, ln.stream));
+    CU(ctx, cudaMemcpyAsync(ctx->d_blob, tns_block, block_bytes, cudaMemcpyHostToDevice, ln.stream));
+    TnsParams tp{};
+    tp.spectra = ln.d_spectra; tp.scratch = ln.d_scratch; tp.info = ln.d_info; tp.blob = ctx->d_blob;
+    tp.offsets = ln.d_offsets; tp.blob_bytes = block_bytes; tp.n_cf = 1; tp.sample_index = ctx->sample_index;
+    tp.ar = mode == AACFB_TNS_FIXED_AR; tp.bands = ctx->d_bands;
+    CU(ctx, launch_tns(tp, ln.stream));
+    ctx->launches++;
+    CU(ctx, cudaMemcpyAsync(data, ln.d_scratch, 4096, cudaMemcpyDeviceToHost, ln.stream));
+    CU(ctx, cudaStreamSynchronize(ln.stream));
+    return AACFB_OK;
+}
+
+}  // extern "C"

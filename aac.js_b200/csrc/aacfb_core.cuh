@@ -22,11 +22,7 @@
 #include "../../include/aacfb.h"
 #include "aacfb_tables.h"
 
-#if defined(__CUDACC__)
-#define AACFB_HD __host__ __device__ __forceinline__
-#else
-#define AACFB_HD inline
-#endif
+#include "aacfb_geometry.h"
 
 namespace aacfb {
 

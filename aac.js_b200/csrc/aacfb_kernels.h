@@ -1,0 +1,49 @@
+// aacfb_kernels.h -- launch interface between the C-ABI layer and the kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#include "../../include/aacfb.h"
+#include "aacfb_geometry.h"
+#include "aacfb_tables.h"
+
+namespace aacfb {
+
+constexpr int kWorkers = 8;                 // workers per CTA
+constexpr int kStages = 3;                  // TMA ring depth per worker
+constexpr int kCtaThreads = kWorkers * 64;
+constexpr int kTnsThreads = 64;
+
+struct SynthParams {
+    const float *spectra;           // [S][T][nc][1024]
+    const float *scratch;           // TNS-filtered rows (same layout) or nullptr
+    const aacfb_frame_info *info;   // [S][T][nc]
+    float *pcm;                     // [S][T][1024][nc]
+    const float *ovl_in;            // overlap state read by chunks starting at t = 0
+    float *ovl_out;                 // overlap state written by chunks ending at t = T
+    const SynthTables *tab;         // device copy of the tables
+    Geometry g;
+    int n_items;
+    unsigned *counter;              // zeroed before launch
+    float scale;
+};
+
+struct TnsParams {
+    const float *spectra;
+    float *scratch;
+    const aacfb_frame_info *info;
+    const uint8_t *blob;
+    const uint32_t *offsets;
+    size_t blob_bytes;
+    size_t n_cf;
+    int sample_index;
+    int ar;                         // 1: all-pole branch (decode=true), 0: MA branch
+    const TnsBandTables *bands;
+};
+
+cudaError_t launch_synth(const SynthParams &P, int grid, cudaStream_t stream);
+cudaError_t launch_tns(const TnsParams &P, cudaStream_t stream);
+int synth_smem_bytes();
+
+}  // namespace aacfb
