@@ -26,7 +26,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libaacfb.so")
+LIB_PATH = os.environ.get("AACFB_LIB") or os.path.join(_HERE, "libaacfb.so")  # AACFB_LIB: tuning variants
 
 ONLY_LONG_SEQUENCE, LONG_START_SEQUENCE, EIGHT_SHORT_SEQUENCE, LONG_STOP_SEQUENCE = 0, 1, 2, 3  # ics.js:44-47
 TNS_AS_SHIPPED, TNS_FIXED_AR, TNS_FIXED_MA = 0, 1, 2

@@ -7,8 +7,12 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <map>
 #include <mutex>
+#include <queue>
+#include <tuple>
 #include <new>
 #include <vector>
 
@@ -85,18 +89,53 @@ struct DeviceGuard {
     ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
 };
 
-// Chunk length: minimise (waves of items over the worker pool) x (frames per
-// item incl. the halo frame), preferring longer chunks on ties.
+// Chunk length.  Workers are latency-bound and take items one after another
+// (static first round, then a shared counter), so the launch lasts as long as
+// the busiest worker: simulate that hand-out for every candidate L and keep
+// the L with the smallest makespan, in frames incl. the halo frame of every
+// chunk that does not start at t = 0.  AACFB_CHUNK_LEN overrides (tuning aid).
+long simulate_makespan(int n_pairs, int T, int L, int workers) {
+    const int chunks = (T + L - 1) / L;
+    const long items = (long)n_pairs * chunks;
+    if (items <= workers) return L + (chunks > 1 ? 1 : 0);
+    std::priority_queue<long, std::vector<long>, std::greater<long>> heap;
+    for (int i = 0; i < workers; ++i) heap.push(0);
+    long makespan = 0;
+    for (int c = 0; c < chunks; ++c) {
+        const int len = std::min(L, T - c * L) + (c > 0 ? 1 : 0);
+        for (int p = 0; p < n_pairs; ++p) {
+            const long t = heap.top() + len;
+            heap.pop();
+            heap.push(t);
+            makespan = std::max(makespan, t);
+        }
+    }
+    return makespan;
+}
+
 int pick_chunk(int n_pairs, int T, int workers) {
+    if (const char *env = std::getenv("AACFB_CHUNK_LEN")) {
+        const int v = std::atoi(env);
+        if (v >= 1) return std::min(v, T);
+    }
+    static std::mutex mu;
+    static std::map<std::tuple<int, int, int>, int> cache;
+    std::lock_guard<std::mutex> lock(mu);
+    const auto key = std::make_tuple(n_pairs, T, workers);
+    const auto hit = cache.find(key);
+    if (hit != cache.end()) return hit->second;
     long best_cost = -1;
-    int best_L = T;
+    int best_L = T, last_chunks = 0;
     for (int L = T; L >= 1; --L) {
         const int chunks = (T + L - 1) / L;
-        const long items = (long)n_pairs * chunks;
-        const long waves = (items + workers - 1) / workers;
-        const long cost = waves * (L + (chunks > 1 ? 1 : 0));
-        if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_L = L; }
+        if (chunks == last_chunks) continue;  // the largest L of each chunk count comes first... keep the most even split
+        last_chunks = chunks;
+        const int Le = (T + chunks - 1) / chunks;  // most even split into `chunks` pieces
+        if ((long)n_pairs * chunks > 64L * workers && best_cost >= 0) break;
+        const long cost = simulate_makespan(n_pairs, T, Le, workers);
+        if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_L = Le; }
     }
+    cache[key] = best_L;
     return best_L;
 }
 

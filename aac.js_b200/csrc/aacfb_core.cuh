@@ -47,16 +47,23 @@ AACFB_HD int brev6(int u) {
     return ((u & 1) << 5) | ((u & 2) << 3) | ((u & 4) << 1) | ((u & 8) >> 1) | ((u & 16) >> 3) | ((u & 32) >> 5);
 }
 
+// aacfb_frame_info packed into one 32-bit word (one 8-byte load per channel-frame):
+// window_sequence | shape_prev << 8 | shape_cur << 16 | max_sfb << 24.
+typedef uint32_t FrameBits;
+AACFB_HD int fb_seq(FrameBits b) { return b & 3; }
+AACFB_HD int fb_shape_prev(FrameBits b) { return (b >> 8) & 1; }
+AACFB_HD int fb_shape_cur(FrameBits b) { return (b >> 16) & 1; }
+AACFB_HD FrameBits fb_pack(const aacfb_frame_info &fi) {
+    return (uint32_t)fi.window_sequence | ((uint32_t)fi.shape_prev << 8) | ((uint32_t)fi.shape_cur << 16) |
+           ((uint32_t)fi.max_sfb << 24);
+}
+
 // Registers of one thread: 8 complex points for each of the worker's 2 chains.
 struct Pts {
     float r[2][8], i[2][8];
 };
 // Overlap carried between frames: positions m(q) and 1023-m(q), q = 0..7.
 struct Ovl {
-    float a[2][8], b[2][8];
-};
-// PCM samples of the current frame at the same positions, before write-out.
-struct Out {
     float a[2][8], b[2][8];
 };
 // Phases below are templated on <C0, NCH>: they act on chains C0 .. C0+NCH-1.
@@ -195,23 +202,32 @@ AACFB_HD void ex2_read(int u, float2 *const *buf, Pts &z) {
         }
 }
 
-// Window tables of one channel-frame, resolved from (sequence, shapes).
-// first[k]  = (Wf[m], Wf[1023-m]) applied to the IMDCT's first half,
-// second[k] = (Ws[m], Ws[1023-m]) applied to y[1024+n]; m = long_pos_of_bin(k).
-// `second_swapped`: the table holds (W[m], W[1023-m]) and the reversed long
-// window W[1023-n] is wanted (filter_bank.js:115-116,198-200), so use (.y,.x).
-struct LongWin {
-    const float2 *first;
-    const float2 *second;
-    bool second_swapped;
+// Position of sample n inside the staging buffer during write-out.  The
+// XOR keeps the scattered stores below (lane stride = 2 samples) and the
+// linear vector loads of out_copy() free of bank conflicts.
+AACFB_HD int stage_pos_interleaved(int n) { return n ^ ((n >> 4) & 1); }  // float2 units: [1024][2]
+AACFB_HD int stage_pos_planar(int n) { return n ^ ((n >> 5) & 1); }       // float units:  [2][1024]
+
+// Where a finished sample goes: the staging buffer (long frames: it is free
+// by then) or registers (frames with an EIGHT_SHORT chain, whose OLA still
+// needs the buffer).
+struct Out {
+    float a[2][8], b[2][8];
 };
-AACFB_HD LongWin long_windows(const aacfb_frame_info &fi, const float2 (*wz)[512], const SynthTables *g) {
-    LongWin w;
-    const int sp = fi.shape_prev & 1, sc = fi.shape_cur & 1;
-    w.first = (fi.window_sequence == AACFB_LONG_STOP_SEQUENCE) ? g->fwz_stop[sp] : wz[sp];
-    if (fi.window_sequence == AACFB_LONG_START_SEQUENCE) { w.second = g->swz_start[sc]; w.second_swapped = false; }
-    else { w.second = wz[sc]; w.second_swapped = true; }
-    return w;
+
+// Effective windows of a long-transform frame as (value at m, value at 1023-m):
+//   first half : ONLY_LONG/LONG_START -> long window of shape_prev (filter_bank.js:109-111,124-126)
+//                LONG_STOP            -> 0 | short asc | 1            (filter_bank.js:184-194)
+//   second half: ONLY_LONG/LONG_STOP  -> reversed long window of shape_cur (filter_bank.js:114-116,198-200)
+//                LONG_START           -> 1 | short desc | 0           (filter_bank.js:129-139)
+AACFB_HD float2 win_first(FrameBits fi, int k, const float2 (*wz)[512], const SynthTables *g) {
+    return fb_seq(fi) == AACFB_LONG_STOP_SEQUENCE ? g->fwz_stop[fb_shape_prev(fi)][k] : wz[fb_shape_prev(fi)][k];
+}
+AACFB_HD float2 win_second(FrameBits fi, int k, const float2 (*wz)[512], const SynthTables *g) {
+    if (fb_seq(fi) == AACFB_LONG_START_SEQUENCE) return g->swz_start[fb_shape_cur(fi)][k];
+    const float2 w = wz[fb_shape_cur(fi)][k];
+    float2 r; r.x = w.y; r.y = w.x;
+    return r;
 }
 
 // Post-twiddle (mdct.js:82-87), reorder (mdct.js:90-114), window and
@@ -219,14 +235,24 @@ AACFB_HD LongWin long_windows(const aacfb_frame_info &fi, const float2 (*wz)[512
 // Thread u owns bins k = 64q+u, i.e. output positions m and 1023-m with
 // m = long_pos_of_bin(k); the same thread owned them in every earlier frame,
 // so the overlap lives in registers.
-// The frame's PCM goes to `o` (registers) and is written out by out_stage().
-template <int C0, int NCH>
-AACFB_HD void long_finish(int u, const Pts &z, Ovl &ov, const float2 *cs2048, const LongWin *win,
-                          bool emit, float scale, Out &o) {
+//   UNIFORM : all chains are ONLY_LONG with the same shapes (the common case):
+//             one shared-memory window load serves every chain and both halves.
+//   TO_STAGE: write the PCM into the staging buffer (else into `o`).
+template <int C0, int NCH, bool UNIFORM, bool TO_STAGE>
+AACFB_HD void long_finish(int u, const Pts &z, Ovl &ov, const SynthTables *ts, const SynthTables *tg,
+                          const FrameBits *fi, bool emit, float scale, float *stage, bool interleaved, Out &o) {
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
         const int k = 64 * q + u;
-        const float2 cs = cs2048[k];
+        const float2 cs = ts->cs2048[k];
+        const int m = long_pos_of_bin(k), mm = 1023 - m;
+        float2 wf_u, ws_u;
+        if (UNIFORM) {
+            wf_u = ts->wz[fb_shape_prev(fi[C0])][k];
+            const float2 wc = fb_shape_prev(fi[C0]) == fb_shape_cur(fi[C0]) ? wf_u : ts->wz[fb_shape_cur(fi[C0])][k];
+            ws_u.x = wc.y; ws_u.y = wc.x;
+        }
+        float om[2], omm[2];
 #pragma unroll
         for (int c = C0; c < C0 + NCH; ++c) {
             const float re = z.r[c][q], im = z.i[c][q];
@@ -236,13 +262,30 @@ AACFB_HD void long_finish(int u, const Pts &z, Ovl &ov, const float2 *cs2048, co
             const float F = (q < 4) ? pr : pi;
             const float S = (q < 4) ? -pi : pr;
             if (emit) {
-                const float2 wf = win[c].first[k];
-                o.a[c][q] = f_mul(f_fma(F, wf.x, ov.a[c][q]), scale);
-                o.b[c][q] = f_mul(f_fma(-F, wf.y, ov.b[c][q]), scale);
+                const float2 wf = UNIFORM ? wf_u : win_first(fi[c], k, ts->wz, tg);
+                om[c] = f_mul(f_fma(F, wf.x, ov.a[c][q]), scale);
+                omm[c] = f_mul(f_fma(-F, wf.y, ov.b[c][q]), scale);
             }
-            const float2 ws = win[c].second[k];
-            ov.a[c][q] = f_mul(S, win[c].second_swapped ? ws.y : ws.x);
-            ov.b[c][q] = f_mul(S, win[c].second_swapped ? ws.x : ws.y);
+            const float2 ws = UNIFORM ? ws_u : win_second(fi[c], k, ts->wz, tg);
+            ov.a[c][q] = f_mul(S, ws.x);
+            ov.b[c][q] = f_mul(S, ws.y);
+        }
+        if (emit) {
+            if (!TO_STAGE) {
+#pragma unroll
+                for (int c = C0; c < C0 + NCH; ++c) { o.a[c][q] = om[c]; o.b[c][q] = omm[c]; }
+            } else if (NCH == 2 && interleaved) {
+                float2 t; t.x = om[0]; t.y = om[1];
+                reinterpret_cast<float2 *>(stage)[stage_pos_interleaved(m)] = t;
+                t.x = omm[0]; t.y = omm[1];
+                reinterpret_cast<float2 *>(stage)[stage_pos_interleaved(mm)] = t;
+            } else {
+#pragma unroll
+                for (int c = C0; c < C0 + NCH; ++c) {
+                    stage[1024 * c + stage_pos_planar(m)] = om[c];
+                    stage[1024 * c + stage_pos_planar(mm)] = omm[c];
+                }
+            }
         }
     }
 }
@@ -329,9 +372,9 @@ AACFB_HD float short_second(int n, const float *buf, const float *wcur) {
 }
 // Window + overlap-add of ONE chain of an EIGHT_SHORT frame from buf[2048].
 template <int C>
-AACFB_HD void short_finish(int u, const float *buf, Ovl &ov, const aacfb_frame_info &fi,
+AACFB_HD void short_finish(int u, const float *buf, Ovl &ov, FrameBits fi,
                            const float (*wshort)[128], bool emit, float scale, Out &o) {
-    const float *wprev = wshort[fi.shape_prev & 1], *wcur = wshort[fi.shape_cur & 1];
+    const float *wprev = wshort[fb_shape_prev(fi)], *wcur = wshort[fb_shape_cur(fi)];
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
         const int m = long_pos_of_bin(64 * q + u), mm = 1023 - m;
@@ -345,14 +388,16 @@ AACFB_HD void short_finish(int u, const float *buf, Ovl &ov, const aacfb_frame_i
 }
 
 // ------------------------------------------------------------- PCM write-out
-// The frame's samples sit in registers at positions (m, 1023-m).  They are
-// transposed through the (by now free) staging buffer so that global memory
-// sees only full, contiguous 16-byte-per-lane stores:
-//   interleaved: the two chains are channels c, c+1 of one stereo stream ->
+// The frame's samples are transposed through the (by now free) staging
+// buffer so that global memory sees only full, contiguous 16-byte-per-lane
+// stores:
+//   interleaved: the two chains are channels 0,1 of one stereo stream ->
 //                stage holds [1024][2], one contiguous 8 KiB PCM row
 //                (decoder.js:204-213 interleave)
 //   planar:      stage holds [2][1024]; each chain's row is written with
 //                stride `ostride`
+// Long frames store into the stage straight from long_finish(); frames with
+// a short chain come through registers (`Out`) and out_stage().
 template <int C0, int NCH>
 AACFB_HD void out_stage(int u, const Out &o, float *stage, bool interleaved) {
 #pragma unroll
@@ -360,35 +405,45 @@ AACFB_HD void out_stage(int u, const Out &o, float *stage, bool interleaved) {
         const int m = long_pos_of_bin(64 * q + u), mm = 1023 - m;
         if (interleaved && NCH == 2) {
             float2 t; t.x = o.a[0][q]; t.y = o.a[1][q];
-            reinterpret_cast<float2 *>(stage)[m] = t;
+            reinterpret_cast<float2 *>(stage)[stage_pos_interleaved(m)] = t;
             t.x = o.b[0][q]; t.y = o.b[1][q];
-            reinterpret_cast<float2 *>(stage)[mm] = t;
+            reinterpret_cast<float2 *>(stage)[stage_pos_interleaved(mm)] = t;
         } else {
 #pragma unroll
             for (int c = C0; c < C0 + NCH; ++c) {
-                stage[1024 * c + m] = o.a[c][q];
-                stage[1024 * c + mm] = o.b[c][q];
+                stage[1024 * c + stage_pos_planar(m)] = o.a[c][q];
+                stage[1024 * c + stage_pos_planar(mm)] = o.b[c][q];
             }
         }
     }
 }
-AACFB_HD void out_copy(int u, const float *stage, float *const *out, int ostride, int c_lo, int c_hi, bool interleaved) {
-    if (interleaved) {
-        const float4 *s4 = reinterpret_cast<const float4 *>(stage);
-        float4 *d4 = reinterpret_cast<float4 *>(out[0]);
+AACFB_HD void out_copy_interleaved(int u, const float *src, float *out) {
+    const float4 *s4 = reinterpret_cast<const float4 *>(src);
+    float4 *d4 = reinterpret_cast<float4 *>(out);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) d4[64 * i + u] = s4[64 * i + u];
-        return;
+    for (int i = 0; i < 8; ++i) {
+        const int j = 64 * i + u;  // samples 2j, 2j+1; stored swapped where bit 4 of the sample index is set
+        float4 v = s4[j];
+        if (j & 8) { float4 t; t.x = v.z; t.y = v.w; t.z = v.x; t.w = v.y; v = t; }
+        d4[j] = v;
     }
-    for (int c = c_lo; c < c_hi; ++c) {
-        if (ostride == 1) {
-            const float4 *s4 = reinterpret_cast<const float4 *>(stage + 1024 * c);
-            float4 *d4 = reinterpret_cast<float4 *>(out[c]);
+}
+AACFB_HD void out_copy_planar(int u, const float *src, float *out, int ostride) {
+    if (ostride == 1) {
+        const float4 *s4 = reinterpret_cast<const float4 *>(src);
+        float4 *d4 = reinterpret_cast<float4 *>(out);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) d4[64 * i + u] = s4[64 * i + u];
-        } else {
+        for (int i = 0; i < 4; ++i) {
+            const int j = 64 * i + u;  // samples 4j..4j+3; neighbours swapped where bit 5 is set
+            float4 v = s4[j];
+            if (j & 8) { float4 t; t.x = v.y; t.y = v.x; t.z = v.w; t.w = v.z; v = t; }
+            d4[j] = v;
+        }
+    } else {
 #pragma unroll 4
-            for (int i = 0; i < 16; ++i) out[c][(size_t)(64 * i + u) * ostride] = stage[1024 * c + 64 * i + u];
+        for (int i = 0; i < 16; ++i) {
+            const int n = 64 * i + u;
+            out[(size_t)n * ostride] = src[stage_pos_planar(n)];
         }
     }
 }

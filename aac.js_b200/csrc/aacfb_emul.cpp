@@ -59,9 +59,10 @@ extern "C" __attribute__((visibility("default"))) int aacfb_emul_process(
     for (int item = 0; item < n_items; ++item) {
         const Item it = make_item(g, item);
         std::barrier<> bar(kWorkerThreads);
-        std::vector<float> stage_mem(kStageFloats + 4);
+        std::vector<float> stage_mem(3 * kStageFloats + 4);
         float *stage = stage_mem.data();
         while (reinterpret_cast<uintptr_t>(stage) & 15) ++stage;
+        float *scratch2[2] = {stage + kStageFloats, stage + 2 * kStageFloats};
         const int f_begin = it.t0 > 0 ? it.t0 - 1 : 0;
 
         auto body = [&](int u) {
@@ -81,16 +82,15 @@ extern "C" __attribute__((visibility("default"))) int aacfb_emul_process(
                 bar.arrive_and_wait();
                 FrameIO io;
                 io.stage = stage;
+                io.scratch = scratch2[(t - f_begin) & 1];
                 io.nch = it.nch;
                 io.emit = t >= it.t0;
                 io.interleaved = it.interleaved;
                 io.scale = 1.0f / 32768.0f;
                 io.ostride = g.nc;
-                for (int c = 0; c < 2; ++c) {
-                    io.fi[c] = info[cf_index(g, it.s[c], t, it.j[c])];
-                    io.fi[c].window_sequence &= 3;
-                    io.out[c] = pcm + ((size_t)it.s[c] * g.T + t) * 1024 * g.nc + it.j[c];
-                }
+                for (int c = 0; c < 2; ++c) io.fi[c] = fb_pack(info[cf_index(g, it.s[c], t, it.j[c])]);
+                io.out0 = pcm + ((size_t)it.s[0] * g.T + t) * 1024 * g.nc + it.j[0];
+                io.out1 = pcm + ((size_t)it.s[1] * g.T + t) * 1024 * g.nc + it.j[1];
                 worker_frame(u, sync, io, tab, tab, z, ov);
             }
             if (it.t1 == g.T) {

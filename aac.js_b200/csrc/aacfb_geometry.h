@@ -39,7 +39,8 @@ struct Item {
 };
 AACFB_HD Item make_item(const Geometry &g, int item) {
     Item it;
-    const int pair = item / g.n_chunks, chunk = item % g.n_chunks;
+    // chunk-major order: the (shorter) last chunks of all pairs are handed out last
+    const int chunk = item / g.n_pairs, pair = item % g.n_pairs;
     const int h0 = 2 * pair, total = g.S * g.nc;
     it.nch = (h0 + 1 < total) ? 2 : 1;
     for (int c = 0; c < 2; ++c) {

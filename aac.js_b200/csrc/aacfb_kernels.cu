@@ -5,14 +5,15 @@
 //                  mdct.js:62-115, fft.js:105-192, decoder.js:204-213)
 //   tns_kernel   : TNS.process               (reference tns.js:105-177)
 //
-// synth_kernel is persistent: one CTA per SM, 8 workers of 64 threads per
-// CTA.  A worker pulls (chain pair, time chunk) items from a global counter
+// synth_kernel is persistent: one CTA per SM, kWorkers workers of 64 threads
+// per CTA.  A worker pulls (chain pair, time chunk) items from a global counter
 // and streams through the chunk's frames.  Spectrum rows are brought from
-// HBM by 1-D TMA bulk copies (cp.async.bulk, SASS UBLKCP) into a 3-deep ring
-// of 8 KiB staging buffers per worker, completion signalled on mbarriers, so
-// ~16 KiB per worker (128 KiB per SM) are always in flight.  All FFT data
-// movement stays in registers and the staging buffer; the only global stores
-// are fully coalesced float4 rows of finished PCM.  See aacfb_worker.cuh for
+// HBM by 1-D TMA bulk copies (cp.async.bulk, SASS UBLKCP) into a ring of
+// 8 KiB staging buffers per worker, completion signalled on mbarriers, so
+// the next frame's rows are always in flight while the current one is
+// transformed.  All FFT data movement stays in registers, the staging buffer
+// and a scratch buffer; the only global stores are fully coalesced float4
+// rows of finished PCM.  See aacfb_worker.cuh for
 // the per-frame schedule and aacfb_core.cuh for the arithmetic.
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -27,7 +28,8 @@ namespace {
 constexpr int kStageBytes = kStageFloats * 4;
 constexpr int kTabBytes = (kSmemTableBytes + 127) & ~127;
 constexpr int kOffStages = kTabBytes;
-constexpr int kOffBars = kOffStages + kWorkers * kStages * kStageBytes;
+constexpr int kBufsPerWorker = kStages + 2;  // TMA ring + two alternating scratch buffers
+constexpr int kOffBars = kOffStages + kWorkers * kBufsPerWorker * kStageBytes;
 constexpr int kOffSlots = kOffBars + kWorkers * kStages * 8;
 constexpr int kSmemTotal = kOffSlots + kWorkers * 4;
 static_assert(kSmemTotal <= 227 * 1024, "shared memory budget");
@@ -86,10 +88,14 @@ struct DevSync {
     }
 };
 
+// aacfb_frame_info is 8 bytes: one 64-bit load, low word = FrameBits, byte 4 = tns_present
+__device__ __forceinline__ uint2 info_raw(const SynthParams &P, size_t cf) {
+    return __ldg(reinterpret_cast<const uint2 *>(P.info) + cf);
+}
+__device__ __forceinline__ FrameBits info_lo(const SynthParams &P, size_t cf) { return info_raw(P, cf).x; }
 __device__ __forceinline__ const float *row_ptr(const SynthParams &P, size_t cf) {
-    const aacfb_frame_info fi = P.info[cf];
-    const float *base = (P.scratch != nullptr && fi.tns_present) ? P.scratch : P.spectra;
-    return base + cf * 1024;
+    const bool tns = P.scratch != nullptr && (info_raw(P, cf).y & 0xffu) != 0;
+    return (tns ? P.scratch : P.spectra) + cf * 1024;
 }
 
 }  // namespace
@@ -106,7 +112,8 @@ __global__ void __launch_bounds__(kCtaThreads, 1) synth_kernel(const __grid_cons
         for (int i = tid; i < kSmemTableBytes / 16; i += kCtaThreads) dst[i] = src[i];
     }
     const SynthTables *ts = reinterpret_cast<const SynthTables *>(smem);
-    float *stages = reinterpret_cast<float *>(smem + kOffStages) + (size_t)w * kStages * kStageFloats;
+    float *stages = reinterpret_cast<float *>(smem + kOffStages) + (size_t)w * kBufsPerWorker * kStageFloats;
+    float *scratch = stages + kStages * kStageFloats;
     const uint32_t bars = smem_u32(smem + kOffBars) + w * kStages * 8;
     volatile int *slot = reinterpret_cast<volatile int *>(smem + kOffSlots) + w;
     if (leader) {
@@ -123,8 +130,14 @@ __global__ void __launch_bounds__(kCtaThreads, 1) synth_kernel(const __grid_cons
     Pts z;
     Ovl ov;
 
+    // First item of every worker is assigned statically, interleaved over the CTAs, so that a
+    // batch with few items still spreads over all SMs; further items come from the counter.
+    bool first = true;
     for (;;) {
-        if (leader) *slot = (int)atomicAdd(P.counter, 1u);
+        if (leader)
+            *slot = first ? w * (int)gridDim.x + (int)blockIdx.x
+                          : kWorkers * (int)gridDim.x + (int)atomicAdd(P.counter, 1u);
+        first = false;
         sync.barrier();
         const int item = *slot;
         if (item >= P.n_items) break;
@@ -153,17 +166,16 @@ __global__ void __launch_bounds__(kCtaThreads, 1) synth_kernel(const __grid_cons
             const uint32_t st = fc % kStages;
             FrameIO io;
             io.stage = stages + st * kStageFloats;
+            io.scratch = scratch + (fc & 1u) * kStageFloats;
             io.nch = it.nch;
             io.emit = t >= it.t0;
             io.interleaved = it.interleaved;
             io.scale = P.scale;
             io.ostride = g.nc;
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                io.fi[c] = P.info[cf_index(g, it.s[c], t, it.j[c])];
-                io.fi[c].window_sequence &= 3;
-                io.out[c] = P.pcm + ((size_t)it.s[c] * g.T + t) * 1024 * g.nc + it.j[c];
-            }
+            io.fi[0] = info_lo(P, cf_index(g, it.s[0], t, it.j[0]));
+            io.fi[1] = info_lo(P, cf_index(g, it.s[1], t, it.j[1]));
+            io.out0 = P.pcm + ((size_t)it.s[0] * g.T + t) * 1024 * g.nc + it.j[0];
+            io.out1 = P.pcm + ((size_t)it.s[1] * g.T + t) * 1024 * g.nc + it.j[1];
             sync.next_valid = f + kStages < nf;
             if (leader && sync.next_valid) {
                 sync.dst = smem_u32(io.stage);

@@ -10,8 +10,14 @@
 
 namespace aacfb {
 
-constexpr int kWorkers = 8;                 // workers per CTA
-constexpr int kStages = 3;                  // TMA ring depth per worker
+#ifndef AACFB_WORKERS
+#define AACFB_WORKERS 6
+#endif
+#ifndef AACFB_STAGES
+#define AACFB_STAGES 2
+#endif
+constexpr int kWorkers = AACFB_WORKERS;     // workers per CTA (6 x 64 threads -> 168 registers/thread, no spills)
+constexpr int kStages = AACFB_STAGES;       // TMA ring depth per worker
 constexpr int kCtaThreads = kWorkers * 64;
 constexpr int kTnsThreads = 64;
 

@@ -3,9 +3,10 @@
 // A worker (64 threads) owns one staging buffer per frame: two spectrum rows
 // of 1024 floats (one per chain), filled by TMA in the kernel.  Once a row
 // has been consumed into registers the same 4 KiB serve as that chain's FFT
-// exchange buffer; for EIGHT_SHORT frames the whole 8 KiB serve as the
-// 2048-sample IMDCT buffer `buf` of filter_bank.js:43; at the end of the
-// frame they serve as the transpose buffer of the PCM write-out.
+// second exchange buffer (the first exchange goes through a per-worker scratch
+// buffer); for EIGHT_SHORT frames stage and scratch serve as the 2048-sample
+// IMDCT buffers `buf` of filter_bank.js:43; the PCM write-out is transposed
+// through whichever of the two is free.
 //
 // `Sync` provides the two synchronisation points the schedule needs:
 //   sync.barrier()     all 64 threads of the worker
@@ -19,107 +20,144 @@
 namespace aacfb {
 
 struct FrameIO {
-    float *stage;                 // 2048 floats: row of chain 0, row of chain 1
-    aacfb_frame_info fi[2];
+    float *stage;                 // 2048 floats filled by TMA: row of chain 0, row of chain 1
+    float *scratch;               // 2048 floats, alternates between two buffers from frame to frame
+    FrameBits fi[2];              // packed aacfb_frame_info of each chain
     int nch;                      // 1 or 2 live chains
     bool emit;                    // false for the halo frame of a chunk
-    bool interleaved;             // chains are channels c, c+1 of one stereo stream
+    bool interleaved;             // chains are channels 0, 1 of one stereo stream
     float scale;                  // 2^-15 (decoder.js:210) or 1 for the inner seam
-    float *out[2];                // sample 0 of this frame for each chain
+    float *out0, *out1;           // sample 0 of this frame for each chain
     int ostride;
 };
 
-// ONLY_LONG / LONG_START / LONG_STOP for chains C0..C0+NCH-1.  Leaves the
-// frame's PCM in `o`; the staging buffer is no longer read when it returns
-// (callers still need a barrier before overwriting it).
+AACFB_HD bool is_short(FrameBits fi) { return fb_seq(fi) == AACFB_EIGHT_SHORT_SEQUENCE; }
+
+// Buffer plan of a frame (S = stage, X = scratch).  Every arrow that crosses
+// threads is separated by exactly one worker barrier; because the scratch
+// buffer alternates between frames, nothing of frame f+1 can collide with the
+// write-out of frame f.
+//
+//   long:   rows S -> regs -> X (exchange 1) -> regs -> S (exchange 2) -> regs -> PCM X -> global
+//   short:  rows S -> regs -> X (exchange)   -> regs -> IMDCT buffers S / X -> regs -> PCM -> global
+
+// 512-point inverse FFT of chains C0..C0+NCH-1 (fft.js:105-192 on the
+// pre-twiddled rows, mdct.js:73-79): two barriers.
 template <int C0, int NCH, class Sync>
-AACFB_HD void frame_long(int u, Sync &sync, const FrameIO &io, const SynthTables *ts, const SynthTables *tg,
-                         Pts &z, Ovl &ov, Out &o) {
+AACFB_HD void long_fft(int u, Sync &sync, const FrameIO &io, const SynthTables *ts, Pts &z) {
     const float *row[2] = {io.stage, io.stage + kRowFloats};
-    float2 *buf[2] = {reinterpret_cast<float2 *>(io.stage), reinterpret_cast<float2 *>(io.stage + kRowFloats)};
+    float2 *bufx[2] = {reinterpret_cast<float2 *>(io.scratch), reinterpret_cast<float2 *>(io.scratch + kRowFloats)};
+    float2 *bufs[2] = {reinterpret_cast<float2 *>(io.stage), reinterpret_cast<float2 *>(io.stage + kRowFloats)};
     long_load<C0, NCH>(u, row, ts->cs2048, z);
     pass_a<C0, NCH>(z, ts->rootsA);
-    sync.barrier();  // every thread has consumed the rows
-    ex1_write<C0, NCH>(u, z, buf);
-    sync.barrier();
-    ex1_read<C0, NCH>(u, buf, z);
+    ex1_write<C0, NCH>(u, z, bufx);
+    sync.barrier();  // exchange 1 complete; every thread has consumed its part of the rows
+    ex1_read<C0, NCH>(u, bufx, z);
     pass_3stage<C0, NCH>(z, ts->twB + 7 * passb_blo(u));
-    sync.barrier();
-    ex2_write<C0, NCH>(u, z, buf);
-    sync.barrier();
-    ex2_read<C0, NCH>(u, buf, z);
+    ex2_write<C0, NCH>(u, z, bufs);
+    sync.barrier();  // exchange 2 complete; exchange-1 data is dead
+    ex2_read<C0, NCH>(u, bufs, z);
     float2 twc[7];
 #pragma unroll
     for (int j = 0; j < 7; ++j) twc[j] = ts->twC[j][u];
     pass_3stage<C0, NCH>(z, twc);
-    LongWin win[2];
-#pragma unroll
-    for (int c = C0; c < C0 + NCH; ++c) win[c] = long_windows(io.fi[c], ts->wz, tg);
-    long_finish<C0, NCH>(u, z, ov, ts->cs2048, win, io.emit, io.scale, o);
 }
 
-// The 8 x 64-point FFTs of EIGHT_SHORT for chains C0..C0+NCH-1; leaves the
-// un-twiddled bins in z.
+// The 8 x 64-point FFTs of EIGHT_SHORT for chains C0..C0+NCH-1: one barrier.
 template <int C0, int NCH, class Sync>
-AACFB_HD void frame_short_fft(int u, Sync &sync, const FrameIO &io, const SynthTables *ts, Pts &z) {
+AACFB_HD void short_fft(int u, Sync &sync, const FrameIO &io, const SynthTables *ts, Pts &z) {
     const float *row[2] = {io.stage, io.stage + kRowFloats};
-    float2 *buf[2] = {reinterpret_cast<float2 *>(io.stage), reinterpret_cast<float2 *>(io.stage + kRowFloats)};
+    float2 *bufx[2] = {reinterpret_cast<float2 *>(io.scratch), reinterpret_cast<float2 *>(io.scratch + kRowFloats)};
     short_load<C0, NCH>(u, row, ts->cs256, z);
     pass_a<C0, NCH>(z, ts->roots64A);
+    exs_write<C0, NCH>(u, z, bufx);
     sync.barrier();
-    exs_write<C0, NCH>(u, z, buf);
-    sync.barrier();
-    exs_read<C0, NCH>(u, buf, z);
+    exs_read<C0, NCH>(u, bufx, z);
     pass_3stage<C0, NCH>(z, ts->twS + 7 * (u & 7));
 }
 
-// Window + overlap-add of chain C of an EIGHT_SHORT frame.  Needs the whole
-// staging buffer: barrier first, since other threads may still be reading
-// exchange data out of it.
-template <int C, class Sync>
-AACFB_HD void frame_short_ola(int u, Sync &sync, const FrameIO &io, const SynthTables *ts, const Pts &z, Ovl &ov,
-                              Out &o) {
-    sync.barrier();
-    short_scatter<C>(u, z, ts->cs256, io.stage);
-    sync.barrier();
-    short_finish<C>(u, io.stage, ov, io.fi[C], ts->wshort, io.emit, io.scale, o);
+// Write-out of a finished frame from buffer `src`, after which the stage may
+// be refilled.  `src_is_stage`: the PCM sits in the stage itself, so the copy
+// has to finish before the refill.
+template <class Sync>
+AACFB_HD void frame_tail(int u, Sync &sync, const FrameIO &io, const float *src, bool src_is_stage) {
+    if (!io.emit) { sync.stage_free(); return; }
+    if (src_is_stage) sync.barrier(); else sync.stage_free();
+    if (io.nch == 2 && io.interleaved) out_copy_interleaved(u, src, io.out0);
+    else {
+        out_copy_planar(u, src, io.out0, io.ostride);
+        if (io.nch == 2) out_copy_planar(u, src + 1024, io.out1, io.ostride);
+    }
+    if (src_is_stage) sync.stage_free();
 }
 
-AACFB_HD bool is_short(const aacfb_frame_info &fi) { return fi.window_sequence == AACFB_EIGHT_SHORT_SEQUENCE; }
+// A frame whose chains are all long transforms: 3 barriers.
+template <int NCH, class Sync>
+AACFB_HD void frame_all_long(int u, Sync &sync, const FrameIO &io, const SynthTables *ts, const SynthTables *tg,
+                             Pts &z, Ovl &ov) {
+    long_fft<0, NCH>(u, sync, io, ts, z);
+    Out none;
+    const bool uniform = fb_seq(io.fi[0]) == AACFB_ONLY_LONG_SEQUENCE &&
+                         (NCH == 1 || ((io.fi[0] ^ io.fi[1]) & 0x00ffffffu) == 0);
+    // exchange-1 data in the scratch buffer is dead since the second barrier: the PCM goes there
+    if (uniform) long_finish<0, NCH, true, true>(u, z, ov, ts, tg, io.fi, io.emit, io.scale, io.scratch, io.interleaved, none);
+    else long_finish<0, NCH, false, true>(u, z, ov, ts, tg, io.fi, io.emit, io.scale, io.scratch, io.interleaved, none);
+    frame_tail(u, sync, io, io.scratch, false);
+}
+
+// A frame with at least one EIGHT_SHORT chain: results pass through registers.
+template <class Sync>
+AACFB_HD void frame_with_short(int u, Sync &sync, const FrameIO &io, const SynthTables *ts, const SynthTables *tg,
+                               Pts &z, Ovl &ov) {
+    Out o;
+    const bool s0 = is_short(io.fi[0]);
+    const bool s1 = io.nch == 2 && is_short(io.fi[1]);
+    if (io.nch == 2 && s0 && s1) {
+        short_fft<0, 2>(u, sync, io, ts, z);
+        short_scatter<0>(u, z, ts->cs256, io.stage);        // rows are dead since the exchange barrier
+        sync.barrier();
+        short_finish<0>(u, io.stage, ov, io.fi[0], ts->wshort, io.emit, io.scale, o);
+        short_scatter<1>(u, z, ts->cs256, io.scratch);      // exchange data dead since the last barrier
+        sync.barrier();
+        short_finish<1>(u, io.scratch, ov, io.fi[1], ts->wshort, io.emit, io.scale, o);
+        if (io.emit) out_stage<0, 2>(u, o, io.stage, io.interleaved);  // chain 0's buffer: dead since the last barrier
+        frame_tail(u, sync, io, io.stage, true);
+        return;
+    }
+    if (io.nch == 1) {
+        short_fft<0, 1>(u, sync, io, ts, z);
+        short_scatter<0>(u, z, ts->cs256, io.stage);
+        sync.barrier();
+        short_finish<0>(u, io.stage, ov, io.fi[0], ts->wshort, io.emit, io.scale, o);
+        if (io.emit) out_stage<0, 1>(u, o, io.scratch, false);
+    } else if (s0) {  // chain 1 long first (it only touches its own halves), then chain 0 short
+        long_fft<1, 1>(u, sync, io, ts, z);
+        long_finish<1, 1, false, false>(u, z, ov, ts, tg, io.fi, io.emit, io.scale, io.stage, false, o);
+        short_fft<0, 1>(u, sync, io, ts, z);
+        short_scatter<0>(u, z, ts->cs256, io.stage);
+        sync.barrier();
+        short_finish<0>(u, io.stage, ov, io.fi[0], ts->wshort, io.emit, io.scale, o);
+        if (io.emit) out_stage<0, 2>(u, o, io.scratch, io.interleaved);
+    } else {
+        long_fft<0, 1>(u, sync, io, ts, z);
+        long_finish<0, 1, false, false>(u, z, ov, ts, tg, io.fi, io.emit, io.scale, io.stage, false, o);
+        short_fft<1, 1>(u, sync, io, ts, z);
+        short_scatter<1>(u, z, ts->cs256, io.stage);
+        sync.barrier();
+        short_finish<1>(u, io.stage, ov, io.fi[1], ts->wshort, io.emit, io.scale, o);
+        if (io.emit) out_stage<0, 2>(u, o, io.scratch, io.interleaved);
+    }
+    frame_tail(u, sync, io, io.scratch, false);
+}
 
 // One frame of the worker's (up to) two chains.
 template <class Sync>
 AACFB_HD void worker_frame(int u, Sync &sync, const FrameIO &io, const SynthTables *ts, const SynthTables *tg, Pts &z,
                            Ovl &ov) {
-    Out o;
-    const bool s0 = is_short(io.fi[0]);
-    const bool s1 = io.nch == 2 && is_short(io.fi[1]);
-    if (io.nch == 1) {
-        if (!s0) frame_long<0, 1>(u, sync, io, ts, tg, z, ov, o);
-        else { frame_short_fft<0, 1>(u, sync, io, ts, z); frame_short_ola<0>(u, sync, io, ts, z, ov, o); }
-    } else if (!s0 && !s1) {
-        frame_long<0, 2>(u, sync, io, ts, tg, z, ov, o);
-    } else if (s0 && s1) {
-        frame_short_fft<0, 2>(u, sync, io, ts, z);
-        frame_short_ola<0>(u, sync, io, ts, z, ov, o);
-        frame_short_ola<1>(u, sync, io, ts, z, ov, o);
-    } else if (s0) {  // chain 1 long first (touches only its own row), then chain 0 short
-        frame_long<1, 1>(u, sync, io, ts, tg, z, ov, o);
-        frame_short_fft<0, 1>(u, sync, io, ts, z);
-        frame_short_ola<0>(u, sync, io, ts, z, ov, o);
-    } else {
-        frame_long<0, 1>(u, sync, io, ts, tg, z, ov, o);
-        frame_short_fft<1, 1>(u, sync, io, ts, z);
-        frame_short_ola<1>(u, sync, io, ts, z, ov, o);
-    }
-    if (io.emit) {
-        sync.barrier();  // nobody reads exchange / IMDCT data out of the stage any more
-        if (io.nch == 2) out_stage<0, 2>(u, o, io.stage, io.interleaved);
-        else out_stage<0, 1>(u, o, io.stage, false);
-        sync.barrier();
-        out_copy(u, io.stage, io.out, io.ostride, 0, io.nch, io.interleaved && io.nch == 2);
-    }
-    sync.stage_free();
+    const bool any_short = is_short(io.fi[0]) || (io.nch == 2 && is_short(io.fi[1]));
+    if (any_short) frame_with_short(u, sync, io, ts, tg, z, ov);
+    else if (io.nch == 2) frame_all_long<2>(u, sync, io, ts, tg, z, ov);
+    else frame_all_long<1>(u, sync, io, ts, tg, z, ov);
 }
 
 }  // namespace aacfb

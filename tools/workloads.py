@@ -65,7 +65,8 @@ def legal_random_sequence(T, rng):
     return seq
 
 
-def make(config: int, S: int, T: int, C: int = 2, seed: int = 0, shape_prev_mode: str = "as_shipped"):
+def make(config: int, S: int, T: int, C: int = 2, seed: int = 0, shape_prev_mode: str = "as_shipped",
+         side_only: bool = False):
     """Returns dict(spectra, info, tns_blob, tns_offsets, flags, sample_index).
 
     config 1/2: ONLY_LONG, TNS off.  3: EIGHT_SHORT.  4: ONLY_LONG + TNS (order 12, one filter of
@@ -74,7 +75,7 @@ def make(config: int, S: int, T: int, C: int = 2, seed: int = 0, shape_prev_mode
     reference defect C5) or the previous frame's shape_cur ("carried")."""
     rng = np.random.default_rng(seed)
     sigma = {1: 3.0e5, 2: 3.0e5, 3: 1.0e5, 4: 0.75e5, 5: 1.0e5}[config]
-    spectra = rng.standard_normal((S, T, C, 1024), dtype=np.float32) * np.float32(sigma)
+    spectra = None if side_only else rng.standard_normal((S, T, C, 1024), dtype=np.float32) * np.float32(sigma)
     info = np.zeros((S, T, C), INFO_DTYPE)
     info["shape_cur"] = (np.arange(S) & 1).astype(np.uint8)[:, None, None]
     if shape_prev_mode == "carried":
