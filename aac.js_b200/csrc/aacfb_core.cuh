@@ -47,6 +47,12 @@ AACFB_HD int brev6(int u) {
     return ((u & 1) << 5) | ((u & 2) << 3) | ((u & 4) << 1) | ((u & 8) >> 1) | ((u & 16) >> 3) | ((u & 32) >> 5);
 }
 
+// Logical thread index u of (warp-in-worker w, lane l): chosen so that the
+// mirror partner 63-u of every thread is lane l^31 of the same warp, while
+// each half-warp still covers 16 consecutive u (all bank-conflict analyses
+// below are per half-warp).  warp 0 = {0..15, 48..63}, warp 1 = {16..47}.
+AACFB_HD int worker_thread_index(int w, int l) { return w == 0 ? (l < 16 ? l : 32 + l) : 16 + l; }
+
 // aacfb_frame_info packed into one 32-bit word (one 8-byte load per channel-frame):
 // window_sequence | shape_prev << 8 | shape_cur << 16 | max_sfb << 24.
 typedef uint32_t FrameBits;
@@ -202,17 +208,19 @@ AACFB_HD void ex2_read(int u, float2 *const *buf, Pts &z) {
         }
 }
 
-// Position of sample n inside the staging buffer during write-out.  The
-// XOR keeps the scattered stores below (lane stride = 2 samples) and the
-// linear vector loads of out_copy() free of bank conflicts.
-AACFB_HD int stage_pos_interleaved(int n) { return n ^ ((n >> 4) & 1); }  // float2 units: [1024][2]
-AACFB_HD int stage_pos_planar(int n) { return n ^ ((n >> 5) & 1); }       // float units:  [2][1024]
-
-// Where a finished sample goes: the staging buffer (long frames: it is free
-// by then) or registers (frames with an EIGHT_SHORT chain, whose OLA still
-// needs the buffer).
+// Finished samples that cannot leave yet (frames with an EIGHT_SHORT chain
+// finish chain by chain) wait in registers.
 struct Out {
     float a[2][8], b[2][8];
+};
+
+// Where the PCM of the current frame goes.
+struct OutDst {
+    bool emit;          // false for the halo frame of a chunk
+    bool interleaved;   // chains are channels 0, 1 of one stereo stream: pcm[n][2]
+    float scale;        // 2^-15 (decoder.js:210) or 1 for the inner seam
+    float *out0, *out1; // sample 0 of this frame for each chain
+    int ostride;        // distance between successive samples of one chain
 };
 
 // Effective windows of a long-transform frame as (value at m, value at 1023-m):
@@ -230,60 +238,116 @@ AACFB_HD float2 win_second(FrameBits fi, int k, const float2 (*wz)[512], const S
     return r;
 }
 
+// ------------------------------------------------------------- PCM write-out
+// Thread u holds, for q = 0..7, the samples at m = long_pos_of_bin(64q+u)
+// (even) and at 1023-m (odd).  The odd neighbour m+1 of its own q is the
+// mirrored sample of q' = 7-q of thread 63-u.  Threads are numbered so that
+// 63-u sits in the same warp at lane ^ 31 (see worker_thread_index), hence one
+// shuffle per sample turns the scattered ownership into contiguous runs
+//   interleaved stereo: (L[m], R[m], L[m+1], R[m+1]) -> one 16-byte store
+//   planar / mono:      (x[m], x[m+1])               -> one  8-byte store
+// and every warp-level store covers whole 32-byte sectors of the PCM row
+// (decoder.js:204-213 interleave).  a[h][c] / b[h][c]: samples of chain c at
+// m and 1023-m for q = qq (h = 0) and q = 7-qq (h = 1).
+template <int C0, int NCH, class Sync>
+AACFB_HD void emit_pair(int u, Sync &sync, int qq, const float (*a)[2], const float (*b)[2], const OutDst &d) {
+    float r_lo[2], r_hi[2];
+#pragma unroll
+    for (int c = C0; c < C0 + NCH; ++c) {
+        r_lo[c] = sync.partner(u, b[1][c]);  // partner's 1023-m' of q' = 7-qq  == my m(qq) + 1
+        r_hi[c] = sync.partner(u, b[0][c]);  // partner's 1023-m' of q' = qq    == my m(7-qq) + 1
+    }
+    const int m_lo = long_pos_of_bin(64 * qq + u), m_hi = long_pos_of_bin(64 * (7 - qq) + u);
+    if (NCH == 2 && d.interleaved) {
+        float4 v;
+        v.x = a[0][0]; v.y = a[0][1]; v.z = r_lo[0]; v.w = r_lo[1];
+        *reinterpret_cast<float4 *>(d.out0 + 2 * m_lo) = v;
+        v.x = a[1][0]; v.y = a[1][1]; v.z = r_hi[0]; v.w = r_hi[1];
+        *reinterpret_cast<float4 *>(d.out0 + 2 * m_hi) = v;
+    } else {
+#pragma unroll
+        for (int c = C0; c < C0 + NCH; ++c) {
+            float *o = c == 0 ? d.out0 : d.out1;
+            if (d.ostride == 1) {
+                float2 v;
+                v.x = a[0][c]; v.y = r_lo[c];
+                *reinterpret_cast<float2 *>(o + m_lo) = v;
+                v.x = a[1][c]; v.y = r_hi[c];
+                *reinterpret_cast<float2 *>(o + m_hi) = v;
+            } else {
+                o[(size_t)m_lo * d.ostride] = a[0][c];
+                o[(size_t)(m_lo + 1) * d.ostride] = r_lo[c];
+                o[(size_t)m_hi * d.ostride] = a[1][c];
+                o[(size_t)(m_hi + 1) * d.ostride] = r_hi[c];
+            }
+        }
+    }
+}
+// Write-out of samples parked in registers (frames with a short chain).
+template <int C0, int NCH, class Sync>
+AACFB_HD void out_store(int u, Sync &sync, const Out &o, const OutDst &d) {
+#pragma unroll
+    for (int qq = 0; qq < 4; ++qq) {
+        float a[2][2], b[2][2];
+#pragma unroll
+        for (int c = C0; c < C0 + NCH; ++c) {
+            a[0][c] = o.a[c][qq]; b[0][c] = o.b[c][qq];
+            a[1][c] = o.a[c][7 - qq]; b[1][c] = o.b[c][7 - qq];
+        }
+        emit_pair<C0, NCH>(u, sync, qq, a, b, d);
+    }
+}
+
 // Post-twiddle (mdct.js:82-87), reorder (mdct.js:90-114), window and
 // overlap-add (filter_bank.js:105-141,180-202), scale (decoder.js:210).
 // Thread u owns bins k = 64q+u, i.e. output positions m and 1023-m with
 // m = long_pos_of_bin(k); the same thread owned them in every earlier frame,
 // so the overlap lives in registers.
-//   UNIFORM : all chains are ONLY_LONG with the same shapes (the common case):
-//             one shared-memory window load serves every chain and both halves.
-//   TO_STAGE: write the PCM into the staging buffer (else into `o`).
-template <int C0, int NCH, bool UNIFORM, bool TO_STAGE>
-AACFB_HD void long_finish(int u, const Pts &z, Ovl &ov, const SynthTables *ts, const SynthTables *tg,
-                          const FrameBits *fi, bool emit, float scale, float *stage, bool interleaved, Out &o) {
+//   UNIFORM  : all chains are ONLY_LONG with the same shapes (the common case):
+//              one shared-memory window load serves every chain and both halves.
+//   TO_GLOBAL: store the PCM right away (else park it in `o`).
+template <int C0, int NCH, bool UNIFORM, bool TO_GLOBAL, class Sync>
+AACFB_HD void long_finish(int u, Sync &sync, const Pts &z, Ovl &ov, const SynthTables *ts, const SynthTables *tg,
+                          const FrameBits *fi, const OutDst &d, Out &o) {
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
-        const int k = 64 * q + u;
-        const float2 cs = ts->cs2048[k];
-        const int m = long_pos_of_bin(k), mm = 1023 - m;
-        float2 wf_u, ws_u;
-        if (UNIFORM) {
-            wf_u = ts->wz[fb_shape_prev(fi[C0])][k];
-            const float2 wc = fb_shape_prev(fi[C0]) == fb_shape_cur(fi[C0]) ? wf_u : ts->wz[fb_shape_cur(fi[C0])][k];
-            ws_u.x = wc.y; ws_u.y = wc.x;
-        }
-        float om[2], omm[2];
+    for (int qq = 0; qq < 4; ++qq) {
+        float a[2][2], b[2][2];
 #pragma unroll
-        for (int c = C0; c < C0 + NCH; ++c) {
-            const float re = z.r[c][q], im = z.i[c][q];
-            const float pr = f_fma(re, cs.x, -f_mul(im, cs.y));
-            const float pi = f_fma(im, cs.x, f_mul(re, cs.y));
-            // first-half sample at m is F, at 1023-m is -F; second-half sample is S at both
-            const float F = (q < 4) ? pr : pi;
-            const float S = (q < 4) ? -pi : pr;
-            if (emit) {
-                const float2 wf = UNIFORM ? wf_u : win_first(fi[c], k, ts->wz, tg);
-                om[c] = f_mul(f_fma(F, wf.x, ov.a[c][q]), scale);
-                omm[c] = f_mul(f_fma(-F, wf.y, ov.b[c][q]), scale);
+        for (int h = 0; h < 2; ++h) {
+            const int q = h ? 7 - qq : qq;
+            const int k = 64 * q + u;
+            const float2 cs = ts->cs2048[k];
+            float2 wf_u, ws_u;
+            if (UNIFORM) {
+                wf_u = ts->wz[fb_shape_prev(fi[C0])][k];
+                const float2 wc = fb_shape_prev(fi[C0]) == fb_shape_cur(fi[C0]) ? wf_u : ts->wz[fb_shape_cur(fi[C0])][k];
+                ws_u.x = wc.y; ws_u.y = wc.x;
             }
-            const float2 ws = UNIFORM ? ws_u : win_second(fi[c], k, ts->wz, tg);
-            ov.a[c][q] = f_mul(S, ws.x);
-            ov.b[c][q] = f_mul(S, ws.y);
-        }
-        if (emit) {
-            if (!TO_STAGE) {
 #pragma unroll
-                for (int c = C0; c < C0 + NCH; ++c) { o.a[c][q] = om[c]; o.b[c][q] = omm[c]; }
-            } else if (NCH == 2 && interleaved) {
-                float2 t; t.x = om[0]; t.y = om[1];
-                reinterpret_cast<float2 *>(stage)[stage_pos_interleaved(m)] = t;
-                t.x = omm[0]; t.y = omm[1];
-                reinterpret_cast<float2 *>(stage)[stage_pos_interleaved(mm)] = t;
-            } else {
+            for (int c = C0; c < C0 + NCH; ++c) {
+                const float re = z.r[c][q], im = z.i[c][q];
+                const float pr = f_fma(re, cs.x, -f_mul(im, cs.y));
+                const float pi = f_fma(im, cs.x, f_mul(re, cs.y));
+                // first-half sample at m is F, at 1023-m is -F; second-half sample is S at both
+                const float F = (q < 4) ? pr : pi;
+                const float S = (q < 4) ? -pi : pr;
+                if (d.emit) {
+                    const float2 wf = UNIFORM ? wf_u : win_first(fi[c], k, ts->wz, tg);
+                    a[h][c] = f_mul(f_fma(F, wf.x, ov.a[c][q]), d.scale);
+                    b[h][c] = f_mul(f_fma(-F, wf.y, ov.b[c][q]), d.scale);
+                }
+                const float2 ws = UNIFORM ? ws_u : win_second(fi[c], k, ts->wz, tg);
+                ov.a[c][q] = f_mul(S, ws.x);
+                ov.b[c][q] = f_mul(S, ws.y);
+            }
+        }
+        if (d.emit) {
+            if (TO_GLOBAL) emit_pair<C0, NCH>(u, sync, qq, a, b, d);
+            else {
 #pragma unroll
                 for (int c = C0; c < C0 + NCH; ++c) {
-                    stage[1024 * c + stage_pos_planar(m)] = om[c];
-                    stage[1024 * c + stage_pos_planar(mm)] = omm[c];
+                    o.a[c][qq] = a[0][c]; o.b[c][qq] = b[0][c];
+                    o.a[c][7 - qq] = a[1][c]; o.b[c][7 - qq] = b[1][c];
                 }
             }
         }
@@ -384,67 +448,6 @@ AACFB_HD void short_finish(int u, const float *buf, Ovl &ov, FrameBits fi,
         }
         ov.a[C][q] = short_second(m, buf, wcur);
         ov.b[C][q] = short_second(mm, buf, wcur);
-    }
-}
-
-// ------------------------------------------------------------- PCM write-out
-// The frame's samples are transposed through the (by now free) staging
-// buffer so that global memory sees only full, contiguous 16-byte-per-lane
-// stores:
-//   interleaved: the two chains are channels 0,1 of one stereo stream ->
-//                stage holds [1024][2], one contiguous 8 KiB PCM row
-//                (decoder.js:204-213 interleave)
-//   planar:      stage holds [2][1024]; each chain's row is written with
-//                stride `ostride`
-// Long frames store into the stage straight from long_finish(); frames with
-// a short chain come through registers (`Out`) and out_stage().
-template <int C0, int NCH>
-AACFB_HD void out_stage(int u, const Out &o, float *stage, bool interleaved) {
-#pragma unroll
-    for (int q = 0; q < 8; ++q) {
-        const int m = long_pos_of_bin(64 * q + u), mm = 1023 - m;
-        if (interleaved && NCH == 2) {
-            float2 t; t.x = o.a[0][q]; t.y = o.a[1][q];
-            reinterpret_cast<float2 *>(stage)[stage_pos_interleaved(m)] = t;
-            t.x = o.b[0][q]; t.y = o.b[1][q];
-            reinterpret_cast<float2 *>(stage)[stage_pos_interleaved(mm)] = t;
-        } else {
-#pragma unroll
-            for (int c = C0; c < C0 + NCH; ++c) {
-                stage[1024 * c + stage_pos_planar(m)] = o.a[c][q];
-                stage[1024 * c + stage_pos_planar(mm)] = o.b[c][q];
-            }
-        }
-    }
-}
-AACFB_HD void out_copy_interleaved(int u, const float *src, float *out) {
-    const float4 *s4 = reinterpret_cast<const float4 *>(src);
-    float4 *d4 = reinterpret_cast<float4 *>(out);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const int j = 64 * i + u;  // samples 2j, 2j+1; stored swapped where bit 4 of the sample index is set
-        float4 v = s4[j];
-        if (j & 8) { float4 t; t.x = v.z; t.y = v.w; t.z = v.x; t.w = v.y; v = t; }
-        d4[j] = v;
-    }
-}
-AACFB_HD void out_copy_planar(int u, const float *src, float *out, int ostride) {
-    if (ostride == 1) {
-        const float4 *s4 = reinterpret_cast<const float4 *>(src);
-        float4 *d4 = reinterpret_cast<float4 *>(out);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int j = 64 * i + u;  // samples 4j..4j+3; neighbours swapped where bit 5 is set
-            float4 v = s4[j];
-            if (j & 8) { float4 t; t.x = v.y; t.y = v.x; t.z = v.w; t.w = v.z; v = t; }
-            d4[j] = v;
-        }
-    } else {
-#pragma unroll 4
-        for (int i = 0; i < 16; ++i) {
-            const int n = 64 * i + u;
-            out[(size_t)n * ostride] = src[stage_pos_planar(n)];
-        }
     }
 }
 

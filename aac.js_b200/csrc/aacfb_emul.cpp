@@ -22,8 +22,16 @@ using namespace aacfb;
 namespace {
 struct HostSync {
     std::barrier<> *bar;
+    float *mailbox;  // 64 slots shared by the worker's threads
     void barrier() { bar->arrive_and_wait(); }
     void stage_free() { bar->arrive_and_wait(); }
+    float partner(int u, float v) {  // the kernel's __shfl_xor_sync(.., 31)
+        mailbox[u] = v;
+        bar->arrive_and_wait();
+        const float r = mailbox[63 - u];
+        bar->arrive_and_wait();
+        return r;
+    }
 };
 }  // namespace
 
@@ -63,10 +71,11 @@ extern "C" __attribute__((visibility("default"))) int aacfb_emul_process(
         float *stage = stage_mem.data();
         while (reinterpret_cast<uintptr_t>(stage) & 15) ++stage;
         float *scratch2[2] = {stage + kStageFloats, stage + 2 * kStageFloats};
+        float mailbox[kWorkerThreads];
         const int f_begin = it.t0 > 0 ? it.t0 - 1 : 0;
 
         auto body = [&](int u) {
-            HostSync sync{&bar};
+            HostSync sync{&bar, mailbox};
             Pts z;
             Ovl ov;
             std::memset(&ov, 0, sizeof ov);
@@ -84,13 +93,13 @@ extern "C" __attribute__((visibility("default"))) int aacfb_emul_process(
                 io.stage = stage;
                 io.scratch = scratch2[(t - f_begin) & 1];
                 io.nch = it.nch;
-                io.emit = t >= it.t0;
-                io.interleaved = it.interleaved;
-                io.scale = 1.0f / 32768.0f;
-                io.ostride = g.nc;
+                io.dst.emit = t >= it.t0;
+                io.dst.interleaved = it.interleaved;
+                io.dst.scale = 1.0f / 32768.0f;
+                io.dst.ostride = g.nc;
                 for (int c = 0; c < 2; ++c) io.fi[c] = fb_pack(info[cf_index(g, it.s[c], t, it.j[c])]);
-                io.out0 = pcm + ((size_t)it.s[0] * g.T + t) * 1024 * g.nc + it.j[0];
-                io.out1 = pcm + ((size_t)it.s[1] * g.T + t) * 1024 * g.nc + it.j[1];
+                io.dst.out0 = pcm + ((size_t)it.s[0] * g.T + t) * 1024 * g.nc + it.j[0];
+                io.dst.out1 = pcm + ((size_t)it.s[1] * g.T + t) * 1024 * g.nc + it.j[1];
                 worker_frame(u, sync, io, tab, tab, z, ov);
             }
             if (it.t1 == g.T) {

@@ -33,6 +33,7 @@ constexpr int kOffBars = kOffStages + kWorkers * kBufsPerWorker * kStageBytes;
 constexpr int kOffSlots = kOffBars + kWorkers * kStages * 8;
 constexpr int kSmemTotal = kOffSlots + kWorkers * 4;
 static_assert(kSmemTotal <= 227 * 1024, "shared memory budget");
+static_assert(2 * kWorkers + 1 <= 16, "named barriers");
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -67,8 +68,9 @@ struct RowSource {
 };
 
 struct DevSync {
-    uint32_t bar_id;
-    bool leader;
+    uint32_t bar_id;      // named barrier of this worker (all 64 threads block)
+    uint32_t free_id;     // named barrier "stage is free": followers arrive, the leader's warp waits
+    bool leader_warp, leader;
     // the refill this frame's stage_free() has to issue (leader only)
     bool next_valid;
     uint32_t dst, mbar;
@@ -83,9 +85,15 @@ struct DevSync {
     __device__ __forceinline__ void stage_free() {
         // order this thread's generic-proxy accesses to the stage before the async-proxy refill
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        barrier();
-        if (leader && next_valid) issue();
+        if (leader_warp) {
+            asm volatile("bar.sync %0, 64;" ::"r"(free_id) : "memory");
+            if (leader && next_valid) issue();
+        } else {
+            asm volatile("bar.arrive %0, 64;" ::"r"(free_id) : "memory");
+        }
     }
+    // value of thread 63-u: lane ^ 31 of the same warp (worker_thread_index)
+    __device__ __forceinline__ float partner(int, float v) { return __shfl_xor_sync(0xffffffffu, v, 31); }
 };
 
 // aacfb_frame_info is 8 bytes: one 64-bit load, low word = FrameBits, byte 4 = tns_present
@@ -102,7 +110,8 @@ __device__ __forceinline__ const float *row_ptr(const SynthParams &P, size_t cf)
 
 __global__ void __launch_bounds__(kCtaThreads, 1) synth_kernel(const __grid_constant__ SynthParams P) {
     extern __shared__ __align__(128) uint8_t smem[];
-    const int tid = threadIdx.x, w = tid >> 6, u = tid & 63;
+    const int tid = threadIdx.x, w = tid >> 6;
+    const int u = worker_thread_index((tid >> 5) & 1, tid & 31);
     const bool leader = u == 0;
 
     // constant tables -> shared memory (once per CTA)
@@ -124,6 +133,8 @@ __global__ void __launch_bounds__(kCtaThreads, 1) synth_kernel(const __grid_cons
 
     DevSync sync;
     sync.bar_id = 1 + w;
+    sync.free_id = 1 + kWorkers + w;
+    sync.leader_warp = ((tid >> 5) & 1) == 0;
     sync.leader = leader;
     const Geometry g = P.g;
     uint32_t fc = 0;  // frames this worker has staged so far: ring position and mbarrier phase
@@ -168,14 +179,14 @@ __global__ void __launch_bounds__(kCtaThreads, 1) synth_kernel(const __grid_cons
             io.stage = stages + st * kStageFloats;
             io.scratch = scratch + (fc & 1u) * kStageFloats;
             io.nch = it.nch;
-            io.emit = t >= it.t0;
-            io.interleaved = it.interleaved;
-            io.scale = P.scale;
-            io.ostride = g.nc;
+            io.dst.emit = t >= it.t0;
+            io.dst.interleaved = it.interleaved;
+            io.dst.scale = P.scale;
+            io.dst.ostride = g.nc;
             io.fi[0] = info_lo(P, cf_index(g, it.s[0], t, it.j[0]));
             io.fi[1] = info_lo(P, cf_index(g, it.s[1], t, it.j[1]));
-            io.out0 = P.pcm + ((size_t)it.s[0] * g.T + t) * 1024 * g.nc + it.j[0];
-            io.out1 = P.pcm + ((size_t)it.s[1] * g.T + t) * 1024 * g.nc + it.j[1];
+            io.dst.out0 = P.pcm + ((size_t)it.s[0] * g.T + t) * 1024 * g.nc + it.j[0];
+            io.dst.out1 = P.pcm + ((size_t)it.s[1] * g.T + t) * 1024 * g.nc + it.j[1];
             sync.next_valid = f + kStages < nf;
             if (leader && sync.next_valid) {
                 sync.dst = smem_u32(io.stage);
