@@ -82,3 +82,16 @@ def test_tns_block_serialisation_and_order_check():
     t.order[0][0] = 21
     with pytest.raises(A.AacfbError, match="TNS filter out of range"):  # tns.js:85
         t.block()
+
+
+def test_napi_addon_source_compiles_against_the_header():
+    """No Node on this image: syntax-check the addon against a stub node_api.h so that the
+    JS binding cannot drift from include/aacfb.h unnoticed."""
+    src = os.path.join(ROOT, "aac.js_b200", "js", "napi", "aacfb_napi.c")
+    r = subprocess.run(["gcc", "-fsyntax-only", "-Wall", "-Werror", "-I", os.path.join(ROOT, "tests", "stubs"), src],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    text = open(src).read()
+    for sym in ("aacfb_create", "aacfb_process", "aacfb_filterbank_process", "aacfb_tns_process", "aacfb_reset",
+                "aacfb_get_overlap", "aacfb_set_overlap", "aacfb_destroy", "aacfb_last_error"):
+        assert sym in text
