@@ -1,0 +1,62 @@
+"""Frame-batch sharding across the GPUs of one box.
+
+Channel-frames only couple along time inside one (stream, channel) chain, so a batch
+shards by *stream* with no data-path collective: rank r owns streams [lo_r, hi_r) and
+its own overlap state.  When the batch starts out on one rank (the decoder host feeds
+rank 0), the only communication is a scatter of spectra + side info and a gather of
+PCM -- grouped point-to-point sends/receives (NCCL has no scatter/gather primitive;
+`torch.distributed.batch_isend_irecv` maps to ncclGroupStart/ncclSend/ncclRecv/End).
+No reduction of any kind exists on this path.  Backend-agnostic: NCCL on GPUs, gloo
+in the CPU tests.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+
+def stream_range(n_streams: int, world: int, rank: int) -> tuple[int, int]:
+    """Contiguous, balanced split of streams: the first (n % world) ranks get one extra."""
+    base, extra = divmod(n_streams, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def scatter_streams(full: torch.Tensor | None, local: torch.Tensor, n_streams: int, root: int = 0) -> None:
+    """Send rows [lo_r, hi_r) of `full` (dim 0 = streams, on root) into `local` on every rank."""
+    rank, world = dist.get_rank(), dist.get_world_size()
+    ops = []
+    if rank == root:
+        for r in range(world):
+            lo, hi = stream_range(n_streams, world, r)
+            if r == root:
+                local.copy_(full[lo:hi])
+            elif hi > lo:
+                ops.append(dist.P2POp(dist.isend, full[lo:hi], r))
+    else:
+        lo, hi = stream_range(n_streams, world, rank)
+        if hi > lo:
+            ops.append(dist.P2POp(dist.irecv, local, root))
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+
+
+def gather_streams(local: torch.Tensor, full: torch.Tensor | None, n_streams: int, root: int = 0) -> None:
+    """Inverse of scatter_streams: collect every rank's rows into `full` on root."""
+    rank, world = dist.get_rank(), dist.get_world_size()
+    ops = []
+    if rank == root:
+        for r in range(world):
+            lo, hi = stream_range(n_streams, world, r)
+            if r == root:
+                full[lo:hi].copy_(local)
+            elif hi > lo:
+                ops.append(dist.P2POp(dist.irecv, full[lo:hi], r))
+    else:
+        lo, hi = stream_range(n_streams, world, rank)
+        if hi > lo:
+            ops.append(dist.P2POp(dist.isend, local, root))
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
