@@ -165,11 +165,14 @@ int enqueue(aacfb_ctx *ctx, const float *d_spectra, const aacfb_frame_info *d_in
     sp.g = make_geometry(S_sub, T, nc, ctx->C, c0, s_base, L);
     sp.n_items = sp.g.n_pairs * sp.g.n_chunks;
     sp.scale = scale;
-    sp.counter = ctx->d_counters + (ctx->counter_next++ % kCounters);
-    CU(ctx, cudaMemsetAsync(sp.counter, 0, sizeof(unsigned), stream));
-    const int grid = std::max(1, std::min(ctx->num_sms, (sp.n_items + kWorkers - 1) / kWorkers));
-    CU(ctx, launch_synth(sp, grid, stream));
-    ctx->launches++;
+    // Two instantiations walk the same item list: the long-only one takes the items without
+    // EIGHT_SHORT frames, the generic one the rest (each item is classified on the device).
+    for (int generic = 0; generic < 2; ++generic) {
+        sp.counter = ctx->d_counters + (ctx->counter_next++ % kCounters);
+        CU(ctx, cudaMemsetAsync(sp.counter, 0, sizeof(unsigned), stream));
+        CU(ctx, launch_synth(sp, ctx->num_sms, generic != 0, stream));
+        ctx->launches++;
+    }
     return AACFB_OK;
 }
 

@@ -412,11 +412,11 @@ AACFB_HD void short_scatter(int u, const Pts &z, const float2 *cs256, float *buf
         const float pr = f_fma(re, cs.x, -f_mul(im, cs.y));
         const float pi = f_fma(im, cs.x, f_mul(re, cs.y));
         if (q < 4) {  // k < 32
-            y[64 + 2 * k] = pr;  y[63 - 2 * k] = -pr;
-            y[192 + 2 * k] = -pi; y[191 - 2 * k] = -pi;
+            y[(64 + 2 * k)] = pr;  y[(63 - 2 * k)] = -pr;
+            y[(192 + 2 * k)] = -pi; y[(191 - 2 * k)] = -pi;
         } else {
-            y[2 * (k - 32)] = pi; y[191 - 2 * k] = -pi;
-            y[128 + 2 * (k - 32)] = pr; y[319 - 2 * k] = pr;
+            y[2 * (k - 32)] = pi; y[(191 - 2 * k)] = -pi;
+            y[(128 + 2 * (k - 32))] = pr; y[(319 - 2 * k)] = pr;
         }
     }
 }
@@ -479,36 +479,73 @@ AACFB_HD void ovl_store(int u, const Ovl &ov, float *state) {
 // side by side.  Taps beyond min(m,order) multiply a zero history / a zero
 // coefficient, which leaves the accumulator unchanged, so no per-tap
 // predicate is needed.  x = unfiltered row (read only), y = filtered row.
+constexpr int kTnsPrefetch = 8;  // float4s per block = one 128-byte line per thread, one block fetched ahead
+
+// Four samples through the serial chain (history h, coefficients c in registers).
 template <int ORD, bool AR>
-AACFB_HD void tns_run(const float *x, float *y, int start, int size, int inc, const float *lpc, int order) {
+AACFB_HD float4 tns_quad(float4 t, int inc, float (&h)[ORD], const float (&c)[ORD], bool nan_from, int m0) {
+    float v[4];
+    if (inc > 0) { v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
+    else         { v[0] = t.w; v[1] = t.z; v[2] = t.y; v[3] = t.x; }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        float acc = v[j];
+#pragma unroll
+        for (int i = 0; i < ORD; ++i) acc = f_fma(AR ? -h[i] : h[i], c[i], acc);
+        // MA branch, order 20: the reference's tmp has 20 slots, tmp[20] reads
+        // undefined -> NaN once m >= 20 (tns.js:43,169)
+        if (!AR && nan_from && m0 + j >= AACFB_TNS_MAX_ORDER) acc = NAN;
+        const float push = AR ? acc : v[j];
+#pragma unroll
+        for (int i = ORD - 1; i > 0; --i) h[i] = h[i - 1];
+        h[0] = push;
+        v[j] = acc;
+    }
+    float4 o;
+    if (inc > 0) { o.x = v[0]; o.y = v[1]; o.z = v[2]; o.w = v[3]; }
+    else         { o.x = v[3]; o.y = v[2]; o.z = v[1]; o.w = v[0]; }
+    return o;
+}
+
+// Not inlined on the device: each (ORD, AR) instantiation gets its own register allocation.
+template <int ORD, bool AR>
+AACFB_HD_NOINLINE void tns_run(const float *x, float *y, int start, int size, int inc, const float *lpc, int order) {
     float h[ORD], c[ORD];
 #pragma unroll
     for (int i = 0; i < ORD; ++i) { h[i] = 0.f; c[i] = i < order ? lpc[i] : 0.f; }
-    // band edges are multiples of 4 (tables.js:34-124), so runs are whole float4s
-    for (int m = 0; m < size; m += 4) {
-        const int at = inc > 0 ? start + m : start - m - 3;
-        const float4 t = *reinterpret_cast<const float4 *>(x + at);
-        float v[4];
-        if (inc > 0) { v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
-        else         { v[0] = t.w; v[1] = t.z; v[2] = t.y; v[3] = t.x; }
+    // Band edges are multiples of 4 (tables.js:34-124), so runs are whole float4s.  The chain
+    // is latency-bound and its loads are address-independent: whole blocks of kTnsPrefetch
+    // float4s (one 128-byte line) are fetched one block ahead of the arithmetic.
+    const int first = inc > 0 ? start : start - 3;
+    const int step = inc > 0 ? 4 : -4;
+    const int n4 = size >> 2, nblk = n4 / kTnsPrefetch;
+    const bool nan_from = order == AACFB_TNS_MAX_ORDER;
+    float4 cur[kTnsPrefetch];
+    if (nblk > 0) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            float acc = v[j];
+        for (int p = 0; p < kTnsPrefetch; ++p) cur[p] = *reinterpret_cast<const float4 *>(x + first + p * step);
+    }
+    for (int b = 0; b < nblk; ++b) {
+        const int base = first + b * kTnsPrefetch * step;
+        float4 nxt[kTnsPrefetch];
+        if (b + 1 < nblk) {
 #pragma unroll
-            for (int i = 0; i < ORD; ++i) acc = f_fma(AR ? -h[i] : h[i], c[i], acc);
-            // MA branch, order 20: the reference's tmp has 20 slots, tmp[20] reads
-            // undefined -> NaN once m >= 20 (tns.js:43,169)
-            if (!AR && order == AACFB_TNS_MAX_ORDER && m + j >= AACFB_TNS_MAX_ORDER) acc = NAN;
-            const float push = AR ? acc : v[j];
-#pragma unroll
-            for (int i = ORD - 1; i > 0; --i) h[i] = h[i - 1];
-            h[0] = push;
-            v[j] = acc;
+            for (int p = 0; p < kTnsPrefetch; ++p)
+                nxt[p] = *reinterpret_cast<const float4 *>(x + base + (kTnsPrefetch + p) * step);
         }
-        float4 o;
-        if (inc > 0) { o.x = v[0]; o.y = v[1]; o.z = v[2]; o.w = v[3]; }
-        else         { o.x = v[3]; o.y = v[2]; o.z = v[1]; o.w = v[0]; }
-        *reinterpret_cast<float4 *>(y + at) = o;
+#pragma unroll
+        for (int p = 0; p < kTnsPrefetch; ++p) {
+            const float4 o = tns_quad<ORD, AR>(cur[p], inc, h, c, nan_from, 4 * (b * kTnsPrefetch + p));
+            *reinterpret_cast<float4 *>(y + base + p * step) = o;
+        }
+        if (b + 1 < nblk) {
+#pragma unroll
+            for (int p = 0; p < kTnsPrefetch; ++p) cur[p] = nxt[p];
+        }
+    }
+    for (int q = nblk * kTnsPrefetch; q < n4; ++q) {  // tail shorter than a block
+        const float4 t = *reinterpret_cast<const float4 *>(x + first + q * step);
+        *reinterpret_cast<float4 *>(y + first + q * step) = tns_quad<ORD, AR>(t, inc, h, c, nan_from, 4 * q);
     }
 }
 
@@ -521,54 +558,102 @@ AACFB_HD void tns_dispatch(const float *x, float *y, int start, int size, int in
     else tns_run<20, AR>(x, y, start, size, inc, lpc, order);
 }
 
-// One channel-frame: walk the TNS block (aacfb.h blob layout), build each
-// filter's direct-form coefficients (tns.js:128-140) and run it over its band
-// range (tns.js:142-154).  Filters of one window cover disjoint, downward
-// stacked band ranges, so every run reads unfiltered input from x.
-// The caller has already copied x to y.
-AACFB_HD void tns_apply(const aacfb_frame_info &fi, const uint8_t *block, uint32_t block_bytes, int sample_index,
-                        bool ar, const TnsBandTables &bt, const float *x, float *y) {
-    if (block_bytes < 8) return;
-    const bool is_short = fi.window_sequence == AACFB_EIGHT_SHORT_SEQUENCE;
-    const uint16_t *swb = is_short ? bt.swb_short[sample_index] : bt.swb_long[sample_index];
-    const int swb_count = is_short ? bt.swb_short_count[sample_index] : bt.swb_long_count[sample_index];
-    const int window_count = is_short ? 8 : 1;
-    const int max_bands = bt.tns_max_bands[sample_index];             // tns.js:23 (long table for short windows too)
-    const int mmm = max_bands < fi.max_sfb ? max_bands : fi.max_sfb;  // tns.js:106
-    float lpc[AACFB_TNS_MAX_ORDER];
-    uint32_t pos = 8;
-    for (int w = 0; w < 8; ++w) {
-        int bottom = swb_count;  // tns.js:113
-        for (int f = 0; f < block[w]; ++f) {
-            if (pos + 4 > block_bytes) return;
-            const int length = block[pos], order = block[pos + 1], direction = block[pos + 2];
-            const float *coef = reinterpret_cast<const float *>(block + pos + 4);
-            pos += 4 + 4 * order;
-            if (order > AACFB_TNS_MAX_ORDER || pos > block_bytes) return;
-            if (w >= window_count) continue;
-            const int top = bottom;  // tns.js:121
-            bottom = top - length;   // tns.js:122, `tmp` read as `top`
-            if (bottom < 0) bottom = 0;
-            if (order == 0) continue;  // tns.js:125
-            for (int i = 0; i < order; ++i) {
-                const float r = -coef[i];
-                lpc[i] = r;
-                for (int j = 0, len = (i + 1) >> 1; j < len; ++j) {
-                    const float fwd = lpc[j], bwd = lpc[i - 1 - j];
-                    lpc[j] = f_fma(r, bwd, fwd);
-                    lpc[i - 1 - j] = f_fma(r, fwd, bwd);
-                }
-            }
-            int start = swb[bottom < mmm ? bottom : mmm];
-            const int end = swb[top < mmm ? top : mmm];
-            const int size = end - start;
-            if (size <= 0) continue;  // tns.js:147
-            int inc = 1;
-            if (direction) { inc = -1; start = end - 1; }  // tns.js:149-152
-            start += w * 128;                              // tns.js:154
-            if (ar) tns_dispatch<true>(x, y, start, size, inc, lpc, order);
-            else tns_dispatch<false>(x, y, start, size, inc, lpc, order);
+// One filter of the block, located in coefficient space.
+struct TnsFilter {
+    int start, size, inc, order;
+    const float *coef;
+    bool valid;   // false once the block is exhausted
+    bool active;  // has a non-empty run (tns.js:125,147)
+};
+// Iterates the filters of a block in (window, filter) order and maps each to
+// its coefficient run: top/bottom stacking tns.js:113,121-122 (`tmp` read as
+// `top`), band clamp :106,142-143, direction :149-152, window offset :154.
+struct TnsWalker {
+    const uint8_t *block;
+    uint32_t bytes, pos;
+    const uint16_t *swb;
+    int swb_count, window_count, mmm, w, f, bottom;
+    AACFB_HD TnsWalker(FrameBits fi, const uint8_t *b, uint32_t n, int sample_index, const TnsBandTables &bt)
+        : block(b), bytes(n), pos(8), w(0), f(0) {
+        const bool is_short = fb_seq(fi) == AACFB_EIGHT_SHORT_SEQUENCE;
+        swb = is_short ? bt.swb_short[sample_index] : bt.swb_long[sample_index];
+        swb_count = is_short ? bt.swb_short_count[sample_index] : bt.swb_long_count[sample_index];
+        window_count = is_short ? 8 : 1;
+        const int max_bands = bt.tns_max_bands[sample_index];  // tns.js:23 (the long table, for short windows too)
+        const int max_sfb = (int)(fi >> 24);
+        mmm = max_bands < max_sfb ? max_bands : max_sfb;
+        bottom = swb_count;
+    }
+    AACFB_HD TnsFilter next() {
+        TnsFilter r;
+        r.valid = false; r.active = false; r.start = r.size = r.order = 0; r.inc = 1; r.coef = nullptr;
+        if (bytes < 8) return r;
+        while (w < 8 && f >= block[w]) { ++w; f = 0; bottom = swb_count; }
+        if (w >= 8 || pos + 4 > bytes) return r;
+        const int length = block[pos], order = block[pos + 1], direction = block[pos + 2];
+        r.coef = reinterpret_cast<const float *>(block + pos + 4);
+        pos += 4 + 4 * order;
+        ++f;
+        if (order > AACFB_TNS_MAX_ORDER || pos > bytes) return r;
+        r.valid = true;
+        r.order = order;
+        if (w >= window_count) return r;  // tns.js:111 only visits w < windowCount
+        const int top = bottom;
+        bottom = top - length;
+        if (bottom < 0) bottom = 0;
+        if (order == 0) return r;
+        const int lo = swb[bottom < mmm ? bottom : mmm], hi = swb[top < mmm ? top : mmm];
+        if (hi - lo <= 0) return r;
+        r.size = hi - lo;
+        r.inc = direction ? -1 : 1;
+        r.start = (direction ? hi - 1 : lo) + w * 128;
+        r.active = true;
+        return r;
+    }
+};
+
+// One channel-frame: y = TNS(x).  Every float4 of the row is written exactly
+// once: first the coefficients no filter touches are copied, then each filter
+// (direct-form coefficients from the reflection coefficients, tns.js:128-140)
+// runs over its band range.  Filters of one window cover disjoint, downward
+// stacked ranges, so every run reads unfiltered input from x.
+AACFB_HD void tns_apply(FrameBits fi, const uint8_t *block, uint32_t block_bytes, int sample_index, bool ar,
+                        const TnsBandTables &bt, const float *x, float *y) {
+    uint32_t covered[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) covered[i] = 0u;
+    {
+        TnsWalker wk(fi, block, block_bytes, sample_index, bt);
+        for (TnsFilter ft = wk.next(); ft.valid; ft = wk.next()) {
+            if (!ft.active) continue;
+            const int lo = ft.inc > 0 ? ft.start : ft.start - ft.size + 1;
+            for (int q = lo >> 2; q < (lo + ft.size) >> 2; ++q) covered[q >> 5] |= 1u << (q & 31);
         }
+    }
+    const float4 *x4 = reinterpret_cast<const float4 *>(x);
+    float4 *y4 = reinterpret_cast<float4 *>(y);
+    for (int g = 0; g < 8; ++g) {
+        const uint32_t cv = covered[g];
+        if (cv == 0xffffffffu) continue;
+#pragma unroll 8
+        for (int b = 0; b < 32; ++b)
+            if (!((cv >> b) & 1u)) y4[32 * g + b] = x4[32 * g + b];
+    }
+    float lpc[AACFB_TNS_MAX_ORDER];
+    TnsWalker wk(fi, block, block_bytes, sample_index, bt);
+    for (TnsFilter ft = wk.next(); ft.valid; ft = wk.next()) {
+        if (!ft.active) continue;
+        for (int i = 0; i < ft.order; ++i) {
+            const float r = -ft.coef[i];
+            lpc[i] = r;
+            for (int j = 0, len = (i + 1) >> 1; j < len; ++j) {
+                const float fwd = lpc[j], bwd = lpc[i - 1 - j];
+                lpc[j] = f_fma(r, bwd, fwd);
+                lpc[i - 1 - j] = f_fma(r, fwd, bwd);
+            }
+        }
+        if (ar) tns_dispatch<true>(x, y, ft.start, ft.size, ft.inc, lpc, ft.order);
+        else tns_dispatch<false>(x, y, ft.start, ft.size, ft.inc, lpc, ft.order);
     }
 }
 

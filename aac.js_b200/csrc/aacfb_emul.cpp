@@ -7,6 +7,7 @@
 // kernel's index maps, swizzles, window-switching and chunk/halo logic against
 // the oracle bit patterns without a GPU.  It is never linked into
 // libaacfb.so and is not a fallback: the shipped library has no CPU path.
+#include <algorithm>
 #include <barrier>
 #include <cstring>
 #include <thread>
@@ -52,9 +53,9 @@ extern "C" __attribute__((visibility("default"))) int aacfb_emul_process(
         for (size_t cf = 0; cf < (size_t)S * T * C; ++cf) {
             if (!info[cf].tns_present) continue;
             const uint32_t o0 = tns_offsets[cf], o1 = tns_offsets[cf + 1];
-            if (o1 <= o0) continue;
-            tns_apply(info[cf], tns_blob + o0, o1 - o0, sample_index, mode == AACFB_TNS_FIXED_AR, bt,
-                      spectra + cf * 1024, scratch.data() + cf * 1024);
+            std::fill_n(scratch.begin() + cf * 1024, 1024, -1.0e30f);  // tns_apply must write every coefficient
+            tns_apply(fb_pack(info[cf]) & 0xffffff03u, tns_blob + o0, o1 > o0 ? o1 - o0 : 0, sample_index,
+                      mode == AACFB_TNS_FIXED_AR, bt, spectra + cf * 1024, scratch.data() + cf * 1024);
         }
     }
     const float *rows = tns_on ? scratch.data() : spectra;
@@ -73,6 +74,10 @@ extern "C" __attribute__((visibility("default"))) int aacfb_emul_process(
         float *scratch2[2] = {stage + kStageFloats, stage + 2 * kStageFloats};
         float mailbox[kWorkerThreads];
         const int f_begin = it.t0 > 0 ? it.t0 - 1 : 0;
+        bool item_has_short = false;  // the kernel's per-item classification
+        for (int t = f_begin; t < it.t1; ++t)
+            for (int c = 0; c < it.nch; ++c)
+                item_has_short |= info[cf_index(g, it.s[c], t, it.j[c])].window_sequence == AACFB_EIGHT_SHORT_SEQUENCE;
 
         auto body = [&](int u) {
             HostSync sync{&bar, mailbox};
@@ -100,7 +105,8 @@ extern "C" __attribute__((visibility("default"))) int aacfb_emul_process(
                 for (int c = 0; c < 2; ++c) io.fi[c] = fb_pack(info[cf_index(g, it.s[c], t, it.j[c])]);
                 io.dst.out0 = pcm + ((size_t)it.s[0] * g.T + t) * 1024 * g.nc + it.j[0];
                 io.dst.out1 = pcm + ((size_t)it.s[1] * g.T + t) * 1024 * g.nc + it.j[1];
-                worker_frame(u, sync, io, tab, tab, z, ov);
+                if (item_has_short) worker_frame<true>(u, sync, io, tab, tab, z, ov);
+                else worker_frame<false>(u, sync, io, tab, tab, z, ov);
             }
             if (it.t1 == g.T) {
                 ovl_store<0>(u, ov, overlap + state_index(g, it.s[0], it.j[0]));

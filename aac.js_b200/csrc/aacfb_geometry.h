@@ -4,8 +4,10 @@
 
 #if defined(__CUDACC__)
 #define AACFB_HD __host__ __device__ __forceinline__
+#define AACFB_HD_NOINLINE __host__ __device__ __noinline__
 #else
 #define AACFB_HD inline
+#define AACFB_HD_NOINLINE inline
 #endif
 
 namespace aacfb {

@@ -27,13 +27,18 @@ namespace {
 
 constexpr int kStageBytes = kStageFloats * 4;
 constexpr int kTabBytes = (kSmemTableBytes + 127) & ~127;
-constexpr int kOffStages = kTabBytes;
-constexpr int kBufsPerWorker = kStages + 2;  // TMA ring + two alternating scratch buffers
-constexpr int kOffBars = kOffStages + kWorkers * kBufsPerWorker * kStageBytes;
-constexpr int kOffSlots = kOffBars + kWorkers * kStages * 8;
-constexpr int kSmemTotal = kOffSlots + kWorkers * 4;
-static_assert(kSmemTotal <= 227 * 1024, "shared memory budget");
-static_assert(2 * kWorkers + 1 <= 16, "named barriers");
+
+// Shared-memory layout of a CTA with W workers and a TMA ring of ST stages per worker.
+template <int W, int ST>
+struct Layout {
+    static constexpr int kBufsPerWorker = ST + 2;  // TMA ring + two alternating scratch buffers
+    static constexpr int kOffStages = kTabBytes;
+    static constexpr int kOffBars = kOffStages + W * kBufsPerWorker * kStageBytes;
+    static constexpr int kOffSlots = kOffBars + W * ST * 8;
+    static constexpr int kTotal = kOffSlots + W * 8;
+    static_assert(kTotal <= 227 * 1024, "shared memory budget");
+    static_assert(2 * W + 1 <= 16, "named barriers");
+};
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -108,7 +113,14 @@ __device__ __forceinline__ const float *row_ptr(const SynthParams &P, size_t cf)
 
 }  // namespace
 
-__global__ void __launch_bounds__(kCtaThreads, 1) synth_kernel(const __grid_constant__ SynthParams P) {
+// GENERIC = false: takes only work items without EIGHT_SHORT frames (the long-transform code
+// alone, best register allocation); GENERIC = true: takes only the items that have one.
+// Both instantiations are launched back to back and walk the same item list.
+template <bool GENERIC, int W, int ST>
+__global__ void __launch_bounds__(W * 64, 1) synth_kernel(const __grid_constant__ SynthParams P) {
+    using L = Layout<W, ST>;
+    constexpr int kCtaThreads = W * 64, kWorkers = W, kStages = ST, kBufsPerWorker = L::kBufsPerWorker;
+    constexpr int kOffStages = L::kOffStages, kOffBars = L::kOffBars, kOffSlots = L::kOffSlots;
     extern __shared__ __align__(128) uint8_t smem[];
     const int tid = threadIdx.x, w = tid >> 6;
     const int u = worker_thread_index((tid >> 5) & 1, tid & 31);
@@ -124,7 +136,7 @@ __global__ void __launch_bounds__(kCtaThreads, 1) synth_kernel(const __grid_cons
     float *stages = reinterpret_cast<float *>(smem + kOffStages) + (size_t)w * kBufsPerWorker * kStageFloats;
     float *scratch = stages + kStages * kStageFloats;
     const uint32_t bars = smem_u32(smem + kOffBars) + w * kStages * 8;
-    volatile int *slot = reinterpret_cast<volatile int *>(smem + kOffSlots) + w;
+    volatile int *slot = reinterpret_cast<volatile int *>(smem + kOffSlots) + 2 * w;  // [0] item, [1] short flag
     if (leader) {
         for (int s = 0; s < kStages; ++s) mbar_init(bars + 8 * s, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -145,16 +157,30 @@ __global__ void __launch_bounds__(kCtaThreads, 1) synth_kernel(const __grid_cons
     // batch with few items still spreads over all SMs; further items come from the counter.
     bool first = true;
     for (;;) {
-        if (leader)
-            *slot = first ? w * (int)gridDim.x + (int)blockIdx.x
-                          : kWorkers * (int)gridDim.x + (int)atomicAdd(P.counter, 1u);
+        if (leader) {
+            slot[0] = first ? w * (int)gridDim.x + (int)blockIdx.x
+                            : kWorkers * (int)gridDim.x + (int)atomicAdd(P.counter, 1u);
+            slot[1] = 0;
+        }
         first = false;
         sync.barrier();
-        const int item = *slot;
+        const int item = slot[0];
         if (item >= P.n_items) break;
         const Item it = make_item(g, item);
         const int f_begin = it.t0 > 0 ? it.t0 - 1 : 0;
         const int nf = it.t1 - f_begin;
+        {   // does this item contain an EIGHT_SHORT frame?  (64 threads scan its side info)
+            bool mine = false;
+            for (int f = tid & 63; f < nf; f += 64) {
+                mine |= is_short(info_lo(P, cf_index(g, it.s[0], f_begin + f, it.j[0])));
+                if (it.nch == 2) mine |= is_short(info_lo(P, cf_index(g, it.s[1], f_begin + f, it.j[1])));
+            }
+            if (__any_sync(0xffffffffu, mine) && (tid & 31) == 0) slot[1] = 1;
+            sync.barrier();
+            const bool has_short = slot[1] != 0;
+            sync.barrier();  // slot is rewritten by the leader at the next item
+            if (has_short != GENERIC) continue;
+        }
 
         if (leader) {  // prologue: fill the ring
             for (int i = 0; i < kStages && i < nf; ++i) {
@@ -196,7 +222,7 @@ __global__ void __launch_bounds__(kCtaThreads, 1) synth_kernel(const __grid_cons
                 sync.src[1] = row_ptr(P, cf_index(g, it.s[1], t + kStages, it.j[1]));
             }
             mbar_wait(bars + 8 * st, (fc / kStages) & 1u);
-            worker_frame(u, sync, io, ts, P.tab, z, ov);
+            worker_frame<GENERIC>(u, sync, io, ts, P.tab, z, ov);
         }
         if (it.t1 == g.T) {
             ovl_store<0>(u, ov, P.ovl_out + state_index(g, it.s[0], it.j[0]));
@@ -205,43 +231,39 @@ __global__ void __launch_bounds__(kCtaThreads, 1) synth_kernel(const __grid_cons
     }
 }
 
-// One thread per channel-frame that carries TNS: copy the row to `scratch`
-// (cooperatively, coalesced) and run its filters there.  The chain is serial
-// by construction (see tns_run), parallelism is across channel-frames.
-__global__ void __launch_bounds__(kTnsThreads) tns_kernel(const __grid_constant__ TnsParams P) {
-    const size_t row0 = (size_t)blockIdx.x * kTnsThreads;
-    for (int r = 0; r < kTnsThreads; ++r) {
-        const size_t cf = row0 + r;
-        if (cf >= P.n_cf) break;
-        if (!P.info[cf].tns_present) continue;
-        const float4 *x4 = reinterpret_cast<const float4 *>(P.spectra + cf * 1024);
-        float4 *y4 = reinterpret_cast<float4 *>(P.scratch + cf * 1024);
-        for (int i = threadIdx.x; i < 256; i += kTnsThreads) y4[i] = x4[i];
-    }
-    __syncthreads();
-    const size_t cf = row0 + threadIdx.x;
+// One thread per channel-frame that carries TNS: write its filtered copy to
+// `scratch` (every float4 exactly once).  The chain is serial by construction
+// (see tns_run), parallelism is across channel-frames.
+__global__ void __launch_bounds__(kTnsThreads, 8) tns_kernel(const __grid_constant__ TnsParams P) {
+    const size_t cf = (size_t)blockIdx.x * kTnsThreads + threadIdx.x;
     if (cf >= P.n_cf) return;
-    const aacfb_frame_info fi = P.info[cf];
-    if (!fi.tns_present) return;
+    const uint2 raw = __ldg(reinterpret_cast<const uint2 *>(P.info) + cf);
+    if ((raw.y & 0xffu) == 0) return;
     const uint32_t o0 = P.offsets[cf], o1 = P.offsets[cf + 1];
-    if (o1 <= o0 || o1 > P.blob_bytes) return;
-    aacfb_frame_info f2 = fi;
-    f2.window_sequence &= 3;
-    tns_apply(f2, P.blob + o0, o1 - o0, P.sample_index, P.ar != 0, *P.bands, P.spectra + cf * 1024,
-              P.scratch + cf * 1024);
+    const bool has_block = o1 > o0 && o1 <= P.blob_bytes;
+    tns_apply((FrameBits)raw.x & 0xffffff03u, P.blob + (has_block ? o0 : 0), has_block ? o1 - o0 : 0, P.sample_index,
+              P.ar != 0, *P.bands, P.spectra + cf * 1024, P.scratch + cf * 1024);
 }
 
-cudaError_t launch_synth(const SynthParams &P, int grid, cudaStream_t stream) {
+template <bool GENERIC, int W, int ST>
+static cudaError_t launch_one(const SynthParams &P, int num_sms, cudaStream_t stream) {
     static bool attr_done[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 64 && !attr_done[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(synth_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal);
+        cudaError_t e = cudaFuncSetAttribute(synth_kernel<GENERIC, W, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             Layout<W, ST>::kTotal);
         if (e != cudaSuccess) return e;
         attr_done[dev] = true;
     }
-    synth_kernel<<<grid, kCtaThreads, kSmemTotal, stream>>>(P);
+    const int grid = num_sms < (P.n_items + W - 1) / W ? num_sms : (P.n_items + W - 1) / W;
+    synth_kernel<GENERIC, W, ST><<<grid < 1 ? 1 : grid, W * 64, Layout<W, ST>::kTotal, stream>>>(P);
     return cudaGetLastError();
+}
+
+cudaError_t launch_synth(const SynthParams &P, int num_sms, bool generic, cudaStream_t stream) {
+    return generic ? launch_one<true, kWorkersGeneric, kStagesGeneric>(P, num_sms, stream)
+                   : launch_one<false, kWorkers, kStages>(P, num_sms, stream);
 }
 
 cudaError_t launch_tns(const TnsParams &P, cudaStream_t stream) {
@@ -251,6 +273,6 @@ cudaError_t launch_tns(const TnsParams &P, cudaStream_t stream) {
     return cudaGetLastError();
 }
 
-int synth_smem_bytes() { return kSmemTotal; }
+int synth_smem_bytes() { return Layout<kWorkers, kStages>::kTotal; }
 
 }  // namespace aacfb

@@ -18,7 +18,8 @@ namespace aacfb {
 #endif
 constexpr int kWorkers = AACFB_WORKERS;     // workers per CTA (6 x 64 threads -> 168 registers/thread, no spills)
 constexpr int kStages = AACFB_STAGES;       // TMA ring depth per worker
-constexpr int kCtaThreads = kWorkers * 64;
+constexpr int kWorkersGeneric = 6;          // generic instantiation (items with EIGHT_SHORT frames)
+constexpr int kStagesGeneric = 2;
 constexpr int kTnsThreads = 64;
 
 struct SynthParams {
@@ -31,7 +32,7 @@ struct SynthParams {
     const SynthTables *tab;         // device copy of the tables
     Geometry g;
     int n_items;
-    unsigned *counter;              // zeroed before launch
+    unsigned *counter;              // zeroed before launch (one per kernel instantiation)
     float scale;
 };
 
@@ -48,7 +49,7 @@ struct TnsParams {
     const TnsBandTables *bands;
 };
 
-cudaError_t launch_synth(const SynthParams &P, int grid, cudaStream_t stream);
+cudaError_t launch_synth(const SynthParams &P, int num_sms, bool generic, cudaStream_t stream);
 cudaError_t launch_tns(const TnsParams &P, cudaStream_t stream);
 int synth_smem_bytes();
 

@@ -136,13 +136,18 @@ AACFB_HD void frame_with_short(int u, Sync &sync, const FrameIO &io, const Synth
     if (d.emit) out_store<0, 2>(u, sync, o, d);
 }
 
-// One frame of the worker's (up to) two chains.
-template <class Sync>
+// One frame of the worker's (up to) two chains.  GENERIC = false is the
+// instantiation for work items without any EIGHT_SHORT frame: it contains no
+// short-window code at all, so its register allocation is that of the long
+// path alone (the kernel is compiled twice, see synth_kernel).
+template <bool GENERIC, class Sync>
 AACFB_HD void worker_frame(int u, Sync &sync, const FrameIO &io, const SynthTables *ts, const SynthTables *tg, Pts &z,
                            Ovl &ov) {
-    const bool any_short = is_short(io.fi[0]) || (io.nch == 2 && is_short(io.fi[1]));
-    if (any_short) frame_with_short(u, sync, io, ts, tg, z, ov);
-    else if (io.nch == 2) frame_all_long<2>(u, sync, io, ts, tg, z, ov);
+    if (GENERIC) {
+        const bool any_short = is_short(io.fi[0]) || (io.nch == 2 && is_short(io.fi[1]));
+        if (any_short) { frame_with_short(u, sync, io, ts, tg, z, ov); return; }
+    }
+    if (io.nch == 2) frame_all_long<2>(u, sync, io, ts, tg, z, ov);
     else frame_all_long<1>(u, sync, io, ts, tg, z, ov);
 }
 

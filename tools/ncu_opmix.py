@@ -13,7 +13,7 @@ def main():
     hdr = rows[1]
     ci = {h: i for i, h in enumerate(hdr)}
     e, s = ci["Instructions Executed"], ci["Source"]
-    wf, wfi = ci["L1 Wavefronts Shared"], ci["L1 Wavefronts Shared Ideal"]
+    wf, wfi = ci.get("L1 Wavefronts Shared", -1), ci.get("L1 Wavefronts Shared Ideal", -1)
     ops, wfs, wfid = collections.Counter(), collections.Counter(), collections.Counter()
     stalls = collections.Counter()
     stall_cols = [(h, i) for h, i in ci.items() if h.startswith("stall_") and "Not Issued" not in h]
@@ -36,8 +36,9 @@ def main():
         ops[key] += c
         total += c
         try:
-            wfs[key] += int(r[wf])
-            wfid[key] += int(r[wfi])
+            if wf >= 0:
+                wfs[key] += int(r[wf])
+                wfid[key] += int(r[wfi])
         except ValueError:
             pass
         for h, i in stall_cols:
