@@ -8,15 +8,19 @@
  * reference legs may load this file's shared object.  The shipped library
  * (aac.js_b200/csrc) never links or calls it.
  *
- * PARITY UNPINNED: the reference has no tests, fixtures or golden vectors
- * for this path and no JavaScript engine exists in this
- * image, so the reference itself cannot be executed here.  The restatement is
- * pinned only (a) by the source text it follows line by line, (b) by
- * tests/test_oracle_pin.py, which interprets the reference's own .js source
- * for this path with a small ES5-subset evaluator when /root/reference is
- * present and commits the resulting vectors under tests/golden/, and (c) by
- * reference-independent identities (direct O(N^2) IMDCT, TDAC, window
- * power-complementarity) in tests/test_oracle_identities.py.
+ * PINNING.  The reference has no tests, fixtures or golden vectors for this
+ * path and no JavaScript engine exists in this image, so
+ * it cannot be run by a stock engine here.  Instead its own, unmodified source
+ * files for the path are executed by tools/jsmini.py (a generic ES5-subset
+ * interpreter written for this repository): tools/js_reference.py produced
+ * tests/golden/jsref_*.npz, and tests/test_oracle_pin.py requires this oracle
+ * to reproduce them BIT FOR BIT (all four window sequences, both window
+ * shapes, TNS as shipped = identity, TNS with the one-token fix in both
+ * branches, the decoder's interleave) -- live on fresh random frames too when
+ * /root/reference is present.  Caveat, stated once: the interpreter, not V8,
+ * ran the code; Math.sin/cos/sqrt come from libm (table generation only).
+ * Reference-independent identities (direct O(N^2) IMDCT, TDAC, window power
+ * complementarity) are in tests/test_oracle_identities.py.
  *
  * Build:  make -C oracle      (gcc -O2 -ffp-contract=off, never -ffast-math)
  *
@@ -97,7 +101,7 @@ static void gen_fft_table_long(int len, float (*f)[3]) {
 /* mdct_tables.js prints sqrt(2/N)*(cos,sin)(2*pi*(k+1/8)/N) to 15 decimals;
  * the JS value is the double nearest that decimal literal.  Reproduce by
  * formatting the closed form to 15 decimals and parsing it back
- * (tests/test_oracle_pin.py checks every entry against the reference file). */
+ * (tests/test_tables.py checks every entry against the reference file). */
 static double round15(double v) {
     char b[64];
     snprintf(b, sizeof b, "%.15f", v);

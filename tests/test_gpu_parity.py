@@ -62,8 +62,12 @@ def test_golden_fixtures(path):
     from tests.test_golden import load_case
 
     if os.path.basename(path).startswith("jsref_"):
-        pytest.skip("covered by test_jsref_golden")
-    w, pcm, ov = load_case(path)
+        from tests.test_oracle_pin import load_jsref
+
+        w, pcm, ov = load_jsref(path)  # vectors produced by the reference's own JS (tools/js_reference.py)
+        w["sample_index"] = 4
+    else:
+        w, pcm, ov = load_case(path)
     S, T, C = w["spectra"].shape[:3]
     got, ovg = gpu_process(w, S, C)
     assert np.abs(got.astype(np.float64) - pcm).max() <= TOL

@@ -1,0 +1,165 @@
+"""Run the reference's own JavaScript for the hot path through tools/jsmini.py.
+
+    python tools/js_reference.py            # regenerate tests/golden/jsref_*.npz (needs /root/reference)
+
+What is executed is the reference's unmodified source text: src/filter_bank.js (which requires
+src/ics.js, src/mdct.js, src/fft.js, src/mdct_tables.js, src/tables.js, src/huffman.js, src/tns.js),
+src/tns.js `TNS.prototype.process`, and lines 204-213 of src/decoder.js (the interleave, cut out of
+the file by its comment markers at run time).  The only substitution ever made is the documented
+one-token fix of reference defect C1 (`tmp` -> `top` at tns.js:122), applied in memory to obtain
+the FIXED_AR / FIXED_MA behaviour; the as-shipped file is run too and shows the identity.
+
+Used by tests/test_oracle_pin.py (live, when /root/reference exists) and to make the committed
+golden vectors the GPU box checks against.
+"""
+from __future__ import annotations
+
+import os
+import re
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from tools import jsmini as J  # noqa: E402
+from tools import workloads as W  # noqa: E402
+
+REF_SRC = "/root/reference/src"
+
+
+class Reference:
+    def __init__(self, src_dir=REF_SRC, fix_tns=False):
+        self.rt = J.Runtime(src_dir)
+        self.fix_tns = fix_tns
+        if fix_tns:
+            # load tns.js with the one-token fix (reference defect C1) BEFORE anything requires it
+            path = os.path.join(src_dir, "tns.js")
+            text = open(path).read()
+            fixed, n = re.subn(r"bottom = Math\.max\(0, tmp - length_w\[filt\]\)",
+                               "bottom = Math.max(0, top - length_w[filt])", text)
+            assert n == 1, "tns.js:122 not found"
+            self.rt.modules[os.path.normpath(path)] = self._load_text(fixed)
+        self.FilterBank = self.rt.require("./filter_bank")
+        self.TNS = self.rt.require("./tns")
+        self.tables = self.rt.require("./tables")
+        dec = open(os.path.join(src_dir, "decoder.js")).read()
+        m = re.search(r"// Interleave channels\n(.*?)\n\s*return output;", dec, re.S)
+        assert m, "decoder.js interleave block not found"
+        self.interleave_src = m.group(1)
+
+    def _load_text(self, text):
+        module, exports = J.JSObject(J.OBJECT_PROTO), J.JSObject(J.OBJECT_PROTO)
+        module.put("exports", exports)
+        ast = J.Parser(J.tokenize(text)).program()
+        names = set()
+        J.hoisted_names(ast, names)
+        scope = {n: J.UNDEF for n in names}
+        scope.update(module=module, exports=exports, this=exports,
+                     require=J.native(lambda this, args: self.rt.require(J.to_string(args[0]))))
+        J.compile_node(ast)((scope, (self.rt.globals, None)))
+        return module
+
+    def new_filterbank(self, channels):
+        return self.FilterBank.construct([False, float(channels)])
+
+    def filterbank_process(self, fb, seq, shape_prev, shape_cur, x, channel):
+        info = J.obj(windowSequence=int(seq), windowShape=J.int32array([shape_prev, shape_cur]))
+        out = J.float32array(np.zeros(1024))
+        self.FilterBank.get("prototype").get("process").call(fb, [info, J.float32array(x), out, float(channel)])
+        return out.a.copy()
+
+    def overlaps(self, fb):
+        return np.stack([o.a.copy() for o in fb.get("overlaps").items])
+
+    def make_tns(self, sample_index, block: bytes):
+        """A reference TNS object (tns.js:22-44) filled from one aacfb.h TNS block."""
+        tns = self.TNS.construct([J.obj(sampleIndex=sample_index)])
+        n_filt, pos = block[:8], 8
+        for w in range(8):
+            J.set_member(tns.get("nFilt"), float(w), float(n_filt[w]))
+            for f in range(n_filt[w]):
+                length, order, direction = block[pos], block[pos + 1], block[pos + 2]
+                coef = np.frombuffer(block[pos + 4:pos + 4 + 4 * order], np.float32)
+                pos += 4 + 4 * order
+                J.set_member(tns.get("length").items[w], float(f), float(length))
+                J.set_member(tns.get("order").items[w], float(f), float(order))
+                J.set_member(tns.get("direction").items[w], float(f), bool(direction))
+                dst = tns.get("coef").items[w].items[f]
+                for i, c in enumerate(coef):
+                    J.set_member(dst, float(i), float(c))
+        return tns
+
+    def tns_process(self, sample_index, seq, max_sfb, block, data, decode):
+        tns = self.make_tns(sample_index, block)
+        short = seq == 2
+        info = J.obj(windowSequence=int(seq), windowCount=8 if short else 1,
+                     swbCount=J.get_member(self.tables.get("SWB_SHORT_WINDOW_COUNT" if short else "SWB_LONG_WINDOW_COUNT"),
+                                           float(sample_index)),
+                     swbOffsets=J.get_member(self.tables.get("SWB_OFFSET_128" if short else "SWB_OFFSET_1024"),
+                                             float(sample_index)))
+        ics = J.obj(maxSFB=int(max_sfb), info=info)
+        d = J.float32array(data)
+        self.TNS.get("prototype").get("process").call(tns, [ics, d, bool(decode)])
+        return d.a.copy()
+
+    def interleave(self, chans):
+        """decoder.js:204-213 on this.data = chans (list of Float32Array rows)."""
+        data = J.JSArray([J.float32array(c) for c in chans])
+        scope = self.rt.run(self.interleave_src, {"this": J.obj(data=data), "frameLength": 1024.0})
+        return scope["output"].a.copy()
+
+    def process(self, spectra, info, tns_blob, tns_offsets, sample_index, mode):
+        """The whole path the way decoder.js drives it (tns.process, filter_bank.process per channel,
+        interleave), for a [S][T][C][1024] batch.  mode: 0 as shipped (decode=false, decoder.js:264),
+        1 = decode true, 2 = decode false (both meaningful only with fix_tns)."""
+        S, T, C, _ = spectra.shape
+        pcm = np.empty((S, T, 1024, C), np.float32)
+        ovl = np.empty((S, C, 1024), np.float32)
+        for s in range(S):
+            fb = self.new_filterbank(C)
+            for t in range(T):
+                chans = []
+                for c in range(C):
+                    fi = info[s, t, c]
+                    data = spectra[s, t, c]
+                    cf = (s * T + t) * C + c
+                    if fi["tns_present"] and tns_blob is not None and tns_offsets[cf + 1] > tns_offsets[cf]:
+                        blk = bytes(tns_blob[tns_offsets[cf]:tns_offsets[cf + 1]])
+                        data = self.tns_process(sample_index, fi["window_sequence"], fi["max_sfb"], blk, data,
+                                                decode=(mode == 1))
+                    chans.append(self.filterbank_process(fb, fi["window_sequence"], fi["shape_prev"], fi["shape_cur"],
+                                                         data, c))
+                pcm[s, t] = self.interleave(chans).reshape(1024, C)
+            ovl[s] = self.overlaps(fb)
+        return pcm, ovl
+
+
+CASES = {
+    # name: (config, S, T, C, seed, shape_prev_mode, fix_tns, mode)
+    "config1_mono_long": (1, 1, 1, 1, 0, "as_shipped", False, 0),
+    "config2_long": (2, 1, 4, 2, 11, "as_shipped", False, 0),
+    "config3_short": (3, 1, 3, 2, 12, "carried", False, 0),
+    "config4_tns_as_shipped": (4, 1, 3, 2, 13, "as_shipped", False, 0),
+    "config4_tns_fixed_ar": (4, 1, 3, 2, 13, "as_shipped", True, 1),
+    "config4_tns_fixed_ma": (4, 1, 3, 2, 13, "as_shipped", True, 2),
+    "config5_mixed": (5, 1, 18, 2, 14, "carried", False, 0),
+}
+
+
+def main():
+    out_dir = os.path.join(ROOT, "tests", "golden")
+    refs = {}
+    for name, (cfg, S, T, C, seed, spm, fix, mode) in CASES.items():
+        ref = refs.setdefault(fix, Reference(fix_tns=fix))
+        w = W.make(cfg, S, T, C, seed, spm)
+        if cfg == 4 and not fix:
+            pass  # the as-shipped reference ignores TNS (tns.js:122): same inputs, TNS side info present
+        pcm, ovl = ref.process(w["spectra"], w["info"], w["tns_blob"], w["tns_offsets"], w["sample_index"], mode)
+        np.savez_compressed(os.path.join(out_dir, f"jsref_{name}.npz"), pcm=pcm, overlap=ovl,
+                            meta=np.array([cfg, S, T, C, seed, int(spm == "carried"), int(fix), mode]))
+        print(name, pcm.shape, float(np.abs(pcm).max()))
+
+
+if __name__ == "__main__":
+    main()
