@@ -167,9 +167,12 @@ int enqueue(aacfb_ctx *ctx, const float *d_spectra, const aacfb_frame_info *d_in
     sp.scale = scale;
     // Two instantiations walk the same item list: the long-only one takes the items without
     // EIGHT_SHORT frames, the generic one the rest (each item is classified on the device).
+    // If the long-only pass finds no such item the generic pass exits at once.
+    unsigned *slots = ctx->d_counters + 4 * (ctx->counter_next++ % (kCounters / 4));
+    CU(ctx, cudaMemsetAsync(slots, 0, 4 * sizeof(unsigned), stream));
+    sp.short_items = slots + 2;
     for (int generic = 0; generic < 2; ++generic) {
-        sp.counter = ctx->d_counters + (ctx->counter_next++ % kCounters);
-        CU(ctx, cudaMemsetAsync(sp.counter, 0, sizeof(unsigned), stream));
+        sp.counter = slots + generic;
         CU(ctx, launch_synth(sp, ctx->num_sms, generic != 0, stream));
         ctx->launches++;
     }

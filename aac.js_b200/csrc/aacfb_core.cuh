@@ -76,11 +76,14 @@ struct Ovl {
 
 // ---------------------------------------------------------------- butterflies
 // fft.js:180-188: t = x[hi]*w (kept in double there); x[hi] = x[lo]-t; x[lo] += t.
+// lo = a + t takes two FMAs per component; hi = a - t is formed as 2a - lo (one FMA, 2a is
+// exact): 6 instead of 8 FMAs per butterfly, at the price of lo's rounding error (<= 1 ulp of
+// lo) reappearing in hi -- well inside the parity budget (tests measure ~3e-7 of 1e-5).
 AACFB_HD void bfly(float &ar, float &ai, float &br, float &bi, float wr, float wi) {
     const float lr = f_fma(br, wr, f_fma(-bi, wi, ar));
     const float li = f_fma(br, wi, f_fma(bi, wr, ai));
-    const float hr = f_fma(-br, wr, f_fma(bi, wi, ar));
-    const float hi = f_fma(-br, wi, f_fma(-bi, wr, ai));
+    const float hr = f_fma(2.0f, ar, -lr);
+    const float hi = f_fma(2.0f, ai, -li);
     ar = lr; ai = li; br = hr; bi = hi;
 }
 AACFB_HD void bfly1(float &ar, float &ai, float &br, float &bi) {  // w = (1, 0): exact in the reference too
@@ -218,7 +221,8 @@ struct Out {
 struct OutDst {
     bool emit;          // false for the halo frame of a chunk
     bool interleaved;   // chains are channels 0, 1 of one stereo stream: pcm[n][2]
-    float scale;        // 2^-15 (decoder.js:210) or 1 for the inner seam
+    float scale;        // 2^-15 (decoder.js:210) or 1 for the inner seam; a power of two
+    float inv_scale;    // 1 / scale
     float *out0, *out1; // sample 0 of this frame for each chain
     int ostride;        // distance between successive samples of one chain
 };
@@ -228,13 +232,25 @@ struct OutDst {
 //                LONG_STOP            -> 0 | short asc | 1            (filter_bank.js:184-194)
 //   second half: ONLY_LONG/LONG_STOP  -> reversed long window of shape_cur (filter_bank.js:114-116,198-200)
 //                LONG_START           -> 1 | short desc | 0           (filter_bank.js:129-139)
-AACFB_HD float2 win_first(FrameBits fi, int k, const float2 (*wz)[512], const SynthTables *g) {
-    return fb_seq(fi) == AACFB_LONG_STOP_SEQUENCE ? g->fwz_stop[fb_shape_prev(fi)][k] : wz[fb_shape_prev(fi)][k];
+// `wz` (the worker's shared-memory copy) already carries the output scale: multiplying a window
+// by a power of two commutes with every rounding downstream, so (ov + F*W) * 2^-15 of
+// decoder.js:210 becomes ov' + F*(W*2^-15) with the overlap kept in scaled units -- bit-identical,
+// two multiplies per bin cheaper.  The window-switching tables in global memory are unscaled.
+AACFB_HD float2 win_first(FrameBits fi, int k, const float2 (*wz)[512], const SynthTables *g, float scale) {
+    if (fb_seq(fi) != AACFB_LONG_STOP_SEQUENCE) return wz[fb_shape_prev(fi)][k];
+    float2 w = g->fwz_stop[fb_shape_prev(fi)][k];
+    w.x = f_mul(w.x, scale); w.y = f_mul(w.y, scale);
+    return w;
 }
-AACFB_HD float2 win_second(FrameBits fi, int k, const float2 (*wz)[512], const SynthTables *g) {
-    if (fb_seq(fi) == AACFB_LONG_START_SEQUENCE) return g->swz_start[fb_shape_cur(fi)][k];
+AACFB_HD float2 win_second(FrameBits fi, int k, const float2 (*wz)[512], const SynthTables *g, float scale) {
+    float2 r;
+    if (fb_seq(fi) == AACFB_LONG_START_SEQUENCE) {
+        const float2 w = g->swz_start[fb_shape_cur(fi)][k];
+        r.x = f_mul(w.x, scale); r.y = f_mul(w.y, scale);
+        return r;
+    }
     const float2 w = wz[fb_shape_cur(fi)][k];
-    float2 r; r.x = w.y; r.y = w.x;
+    r.x = w.y; r.y = w.x;
     return r;
 }
 
@@ -299,8 +315,8 @@ AACFB_HD void out_store(int u, Sync &sync, const Out &o, const OutDst &d) {
 }
 
 // Post-twiddle (mdct.js:82-87), reorder (mdct.js:90-114), window and
-// overlap-add (filter_bank.js:105-141,180-202), scale (decoder.js:210).
-// Thread u owns bins k = 64q+u, i.e. output positions m and 1023-m with
+// overlap-add (filter_bank.js:105-141,180-202); the scale of decoder.js:210
+// rides in the window table (see win_first).  Thread u owns bins k = 64q+u, i.e. output positions m and 1023-m with
 // m = long_pos_of_bin(k); the same thread owned them in every earlier frame,
 // so the overlap lives in registers.
 //   UNIFORM  : all chains are ONLY_LONG with the same shapes (the common case):
@@ -332,11 +348,11 @@ AACFB_HD void long_finish(int u, Sync &sync, const Pts &z, Ovl &ov, const SynthT
                 const float F = (q < 4) ? pr : pi;
                 const float S = (q < 4) ? -pi : pr;
                 if (d.emit) {
-                    const float2 wf = UNIFORM ? wf_u : win_first(fi[c], k, ts->wz, tg);
-                    a[h][c] = f_mul(f_fma(F, wf.x, ov.a[c][q]), d.scale);
-                    b[h][c] = f_mul(f_fma(-F, wf.y, ov.b[c][q]), d.scale);
+                    const float2 wf = UNIFORM ? wf_u : win_first(fi[c], k, ts->wz, tg, d.scale);
+                    a[h][c] = f_fma(F, wf.x, ov.a[c][q]);
+                    b[h][c] = f_fma(-F, wf.y, ov.b[c][q]);
                 }
-                const float2 ws = UNIFORM ? ws_u : win_second(fi[c], k, ts->wz, tg);
+                const float2 ws = UNIFORM ? ws_u : win_second(fi[c], k, ts->wz, tg, d.scale);
                 ov.a[c][q] = f_mul(S, ws.x);
                 ov.b[c][q] = f_mul(S, ws.y);
             }
@@ -436,38 +452,41 @@ AACFB_HD float short_second(int n, const float *buf, const float *wcur) {
 }
 // Window + overlap-add of ONE chain of an EIGHT_SHORT frame from buf[2048].
 template <int C>
+// The overlap registers are kept in output-scaled units (see win_first); this path unscales and
+// rescales them (exact: powers of two).
 AACFB_HD void short_finish(int u, const float *buf, Ovl &ov, FrameBits fi,
-                           const float (*wshort)[128], bool emit, float scale, Out &o) {
+                           const float (*wshort)[128], bool emit, float scale, float inv_scale, Out &o) {
     const float *wprev = wshort[fb_shape_prev(fi)], *wcur = wshort[fb_shape_cur(fi)];
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
         const int m = long_pos_of_bin(64 * q + u), mm = 1023 - m;
         if (emit) {
-            o.a[C][q] = f_mul(short_first(m, buf, ov.a[C][q], wprev, wcur), scale);
-            o.b[C][q] = f_mul(short_first(mm, buf, ov.b[C][q], wprev, wcur), scale);
+            o.a[C][q] = f_mul(short_first(m, buf, f_mul(ov.a[C][q], inv_scale), wprev, wcur), scale);
+            o.b[C][q] = f_mul(short_first(mm, buf, f_mul(ov.b[C][q], inv_scale), wprev, wcur), scale);
         }
-        ov.a[C][q] = short_second(m, buf, wcur);
-        ov.b[C][q] = short_second(mm, buf, wcur);
+        ov.a[C][q] = f_mul(short_second(m, buf, wcur), scale);
+        ov.b[C][q] = f_mul(short_second(mm, buf, wcur), scale);
     }
 }
 
 // ---------------------------------------------------------------- overlap I/O
+// The state in memory is FilterBank.overlaps (unscaled); registers hold it times `scale`.
 template <int C>
-AACFB_HD void ovl_load(int u, const float *state, Ovl &ov) {
+AACFB_HD void ovl_load(int u, const float *state, Ovl &ov, float scale) {
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
         const int m = long_pos_of_bin(64 * q + u);
-        ov.a[C][q] = state ? state[m] : 0.f;
-        ov.b[C][q] = state ? state[1023 - m] : 0.f;
+        ov.a[C][q] = f_mul(state[m], scale);
+        ov.b[C][q] = f_mul(state[1023 - m], scale);
     }
 }
 template <int C>
-AACFB_HD void ovl_store(int u, const Ovl &ov, float *state) {
+AACFB_HD void ovl_store(int u, const Ovl &ov, float *state, float inv_scale) {
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
         const int m = long_pos_of_bin(64 * q + u);
-        state[m] = ov.a[C][q];
-        state[1023 - m] = ov.b[C][q];
+        state[m] = f_mul(ov.a[C][q], inv_scale);
+        state[1023 - m] = f_mul(ov.b[C][q], inv_scale);
     }
 }
 

@@ -41,7 +41,13 @@ extern "C" __attribute__((visibility("default"))) int aacfb_emul_process(
     float *overlap /*[S][C][1024] in/out*/, float *pcm, int S, int T, int C, int sample_index, uint32_t flags,
     int chunk_len) {
     const HostTables &H = host_tables();
-    const SynthTables *tab = &H.synth;
+    const float kScale = 1.0f / 32768.0f;
+    // the worker's shared-memory copy of the tables: long windows carry the output scale
+    static SynthTables scaled;
+    scaled = H.synth;
+    for (int sh = 0; sh < 2; ++sh)
+        for (int k = 0; k < 512; ++k) { scaled.wz[sh][k].x *= kScale; scaled.wz[sh][k].y *= kScale; }
+    const SynthTables *tab = &scaled;
     const TnsBandTables &bt = tns_band_tables();
     const uint32_t mode = flags & AACFB_TNS_MODE_MASK;
 
@@ -85,8 +91,8 @@ extern "C" __attribute__((visibility("default"))) int aacfb_emul_process(
             Ovl ov;
             std::memset(&ov, 0, sizeof ov);
             if (it.t0 == 0) {
-                ovl_load<0>(u, overlap + state_index(g, it.s[0], it.j[0]), ov);
-                if (it.nch == 2) ovl_load<1>(u, overlap + state_index(g, it.s[1], it.j[1]), ov);
+                ovl_load<0>(u, overlap + state_index(g, it.s[0], it.j[0]), ov, kScale);
+                if (it.nch == 2) ovl_load<1>(u, overlap + state_index(g, it.s[1], it.j[1]), ov, kScale);
             }
             for (int t = f_begin; t < it.t1; ++t) {
                 // "TMA": thread 0 fills the stage, everyone waits
@@ -100,17 +106,18 @@ extern "C" __attribute__((visibility("default"))) int aacfb_emul_process(
                 io.nch = it.nch;
                 io.dst.emit = t >= it.t0;
                 io.dst.interleaved = it.interleaved;
-                io.dst.scale = 1.0f / 32768.0f;
+                io.dst.scale = kScale;
+                io.dst.inv_scale = 1.0f / kScale;
                 io.dst.ostride = g.nc;
                 for (int c = 0; c < 2; ++c) io.fi[c] = fb_pack(info[cf_index(g, it.s[c], t, it.j[c])]);
                 io.dst.out0 = pcm + ((size_t)it.s[0] * g.T + t) * 1024 * g.nc + it.j[0];
                 io.dst.out1 = pcm + ((size_t)it.s[1] * g.T + t) * 1024 * g.nc + it.j[1];
-                if (item_has_short) worker_frame<true>(u, sync, io, tab, tab, z, ov);
-                else worker_frame<false>(u, sync, io, tab, tab, z, ov);
+                if (item_has_short) worker_frame<true>(u, sync, io, tab, &H.synth, z, ov);
+                else worker_frame<false>(u, sync, io, tab, &H.synth, z, ov);
             }
             if (it.t1 == g.T) {
-                ovl_store<0>(u, ov, overlap + state_index(g, it.s[0], it.j[0]));
-                if (it.nch == 2) ovl_store<1>(u, ov, overlap + state_index(g, it.s[1], it.j[1]));
+                ovl_store<0>(u, ov, overlap + state_index(g, it.s[0], it.j[0]), 1.0f / kScale);
+                if (it.nch == 2) ovl_store<1>(u, ov, overlap + state_index(g, it.s[1], it.j[1]), 1.0f / kScale);
             }
         };
         std::vector<std::thread> th;

@@ -16,6 +16,7 @@
 // rows of finished PCM.  See aacfb_worker.cuh for
 // the per-frame schedule and aacfb_core.cuh for the arithmetic.
 #include <cuda_runtime.h>
+#include <stddef.h>
 #include <stdint.h>
 
 #include "aacfb_kernels.h"
@@ -122,6 +123,8 @@ __global__ void __launch_bounds__(W * 64, 1) synth_kernel(const __grid_constant_
     constexpr int kCtaThreads = W * 64, kWorkers = W, kStages = ST, kBufsPerWorker = L::kBufsPerWorker;
     constexpr int kOffStages = L::kOffStages, kOffBars = L::kOffBars, kOffSlots = L::kOffSlots;
     extern __shared__ __align__(128) uint8_t smem[];
+    // the long-only instantiation (launched first) counts the items it had to leave to us
+    if (GENERIC && *P.short_items == 0u) return;
     const int tid = threadIdx.x, w = tid >> 6;
     const int u = worker_thread_index((tid >> 5) & 1, tid & 31);
     const bool leader = u == 0;
@@ -131,6 +134,10 @@ __global__ void __launch_bounds__(W * 64, 1) synth_kernel(const __grid_constant_
         const float4 *src = reinterpret_cast<const float4 *>(P.tab);
         float4 *dst = reinterpret_cast<float4 *>(smem);
         for (int i = tid; i < kSmemTableBytes / 16; i += kCtaThreads) dst[i] = src[i];
+        __syncthreads();
+        // the long windows carry the output scale (a power of two; see win_first in aacfb_core.cuh)
+        float *wz = reinterpret_cast<float *>(smem + offsetof(SynthTables, wz));
+        for (int i = tid; i < 2 * 512 * 2; i += kCtaThreads) wz[i] *= P.scale;
     }
     const SynthTables *ts = reinterpret_cast<const SynthTables *>(smem);
     float *stages = reinterpret_cast<float *>(smem + kOffStages) + (size_t)w * kBufsPerWorker * kStageFloats;
@@ -179,7 +186,10 @@ __global__ void __launch_bounds__(W * 64, 1) synth_kernel(const __grid_constant_
             sync.barrier();
             const bool has_short = slot[1] != 0;
             sync.barrier();  // slot is rewritten by the leader at the next item
-            if (has_short != GENERIC) continue;
+            if (has_short != GENERIC) {
+                if (!GENERIC && leader) atomicAdd(P.short_items, 1u);
+                continue;
+            }
         }
 
         if (leader) {  // prologue: fill the ring
@@ -194,8 +204,8 @@ __global__ void __launch_bounds__(W * 64, 1) synth_kernel(const __grid_constant_
             }
         }
         if (it.t0 == 0) {
-            ovl_load<0>(u, P.ovl_in + state_index(g, it.s[0], it.j[0]), ov);
-            if (it.nch == 2) ovl_load<1>(u, P.ovl_in + state_index(g, it.s[1], it.j[1]), ov);
+            ovl_load<0>(u, P.ovl_in + state_index(g, it.s[0], it.j[0]), ov, P.scale);
+            if (it.nch == 2) ovl_load<1>(u, P.ovl_in + state_index(g, it.s[1], it.j[1]), ov, P.scale);
         }
 
         for (int f = 0; f < nf; ++f, ++fc) {
@@ -208,6 +218,7 @@ __global__ void __launch_bounds__(W * 64, 1) synth_kernel(const __grid_constant_
             io.dst.emit = t >= it.t0;
             io.dst.interleaved = it.interleaved;
             io.dst.scale = P.scale;
+            io.dst.inv_scale = 1.0f / P.scale;
             io.dst.ostride = g.nc;
             io.fi[0] = info_lo(P, cf_index(g, it.s[0], t, it.j[0]));
             io.fi[1] = info_lo(P, cf_index(g, it.s[1], t, it.j[1]));
@@ -225,8 +236,8 @@ __global__ void __launch_bounds__(W * 64, 1) synth_kernel(const __grid_constant_
             worker_frame<GENERIC>(u, sync, io, ts, P.tab, z, ov);
         }
         if (it.t1 == g.T) {
-            ovl_store<0>(u, ov, P.ovl_out + state_index(g, it.s[0], it.j[0]));
-            if (it.nch == 2) ovl_store<1>(u, ov, P.ovl_out + state_index(g, it.s[1], it.j[1]));
+            ovl_store<0>(u, ov, P.ovl_out + state_index(g, it.s[0], it.j[0]), 1.0f / P.scale);
+            if (it.nch == 2) ovl_store<1>(u, ov, P.ovl_out + state_index(g, it.s[1], it.j[1]), 1.0f / P.scale);
         }
     }
 }

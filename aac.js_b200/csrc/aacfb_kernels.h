@@ -33,6 +33,7 @@ struct SynthParams {
     Geometry g;
     int n_items;
     unsigned *counter;              // zeroed before launch (one per kernel instantiation)
+    unsigned *short_items;          // zeroed; number of items with EIGHT_SHORT frames (set by the long-only pass)
     float scale;
 };
 

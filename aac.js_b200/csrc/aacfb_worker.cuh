@@ -100,11 +100,11 @@ AACFB_HD void frame_with_short(int u, Sync &sync, const FrameIO &io, const Synth
         short_fft<0, 2>(u, sync, io, ts, z);
         short_scatter<0>(u, z, ts->cs256, io.stage);        // rows are dead since the exchange barrier
         sync.barrier();
-        short_finish<0>(u, io.stage, ov, io.fi[0], ts->wshort, d.emit, d.scale, o);
+        short_finish<0>(u, io.stage, ov, io.fi[0], ts->wshort, d.emit, d.scale, d.inv_scale, o);
         short_scatter<1>(u, z, ts->cs256, io.scratch);      // exchange data dead since the last barrier
         sync.barrier();
         sync.stage_free();                                   // chain 0's IMDCT buffer has been consumed
-        short_finish<1>(u, io.scratch, ov, io.fi[1], ts->wshort, d.emit, d.scale, o);
+        short_finish<1>(u, io.scratch, ov, io.fi[1], ts->wshort, d.emit, d.scale, d.inv_scale, o);
         if (d.emit) out_store<0, 2>(u, sync, o, d);
         return;
     }
@@ -112,7 +112,7 @@ AACFB_HD void frame_with_short(int u, Sync &sync, const FrameIO &io, const Synth
         short_fft<0, 1>(u, sync, io, ts, z);
         short_scatter<0>(u, z, ts->cs256, io.stage);
         sync.barrier();
-        short_finish<0>(u, io.stage, ov, io.fi[0], ts->wshort, d.emit, d.scale, o);
+        short_finish<0>(u, io.stage, ov, io.fi[0], ts->wshort, d.emit, d.scale, d.inv_scale, o);
         sync.stage_free();
         if (d.emit) out_store<0, 1>(u, sync, o, d);
         return;
@@ -123,14 +123,14 @@ AACFB_HD void frame_with_short(int u, Sync &sync, const FrameIO &io, const Synth
         short_fft<0, 1>(u, sync, io, ts, z);
         short_scatter<0>(u, z, ts->cs256, io.stage);
         sync.barrier();
-        short_finish<0>(u, io.stage, ov, io.fi[0], ts->wshort, d.emit, d.scale, o);
+        short_finish<0>(u, io.stage, ov, io.fi[0], ts->wshort, d.emit, d.scale, d.inv_scale, o);
     } else {
         long_fft<0, 1>(u, sync, io, ts, z);
         long_finish<0, 1, false, false>(u, sync, z, ov, ts, tg, io.fi, d, o);
         short_fft<1, 1>(u, sync, io, ts, z);
         short_scatter<1>(u, z, ts->cs256, io.stage);
         sync.barrier();
-        short_finish<1>(u, io.stage, ov, io.fi[1], ts->wshort, d.emit, d.scale, o);
+        short_finish<1>(u, io.stage, ov, io.fi[1], ts->wshort, d.emit, d.scale, d.inv_scale, o);
     }
     sync.stage_free();
     if (d.emit) out_store<0, 2>(u, sync, o, d);
