@@ -9,10 +9,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
-#include <map>
 #include <mutex>
-#include <queue>
-#include <tuple>
 #include <new>
 #include <vector>
 
@@ -89,54 +86,19 @@ struct DeviceGuard {
     ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
 };
 
-// Chunk length.  Workers are latency-bound and take items one after another
-// (static first round, then a shared counter), so the launch lasts as long as
-// the busiest worker: simulate that hand-out for every candidate L and keep
-// the L with the smallest makespan, in frames incl. the halo frame of every
-// chunk that does not start at t = 0.  AACFB_CHUNK_LEN overrides (tuning aid).
-long simulate_makespan(int n_pairs, int T, int L, int workers) {
-    const int chunks = (T + L - 1) / L;
-    const long items = (long)n_pairs * chunks;
-    if (items <= workers) return L + (chunks > 1 ? 1 : 0);
-    std::priority_queue<long, std::vector<long>, std::greater<long>> heap;
-    for (int i = 0; i < workers; ++i) heap.push(0);
-    long makespan = 0;
-    for (int c = 0; c < chunks; ++c) {
-        const int len = std::min(L, T - c * L) + (c > 0 ? 1 : 0);
-        for (int p = 0; p < n_pairs; ++p) {
-            const long t = heap.top() + len;
-            heap.pop();
-            heap.push(t);
-            makespan = std::max(makespan, t);
-        }
-    }
-    return makespan;
-}
-
-int pick_chunk(int n_pairs, int T, int workers) {
-    if (const char *env = std::getenv("AACFB_CHUNK_LEN")) {
+// Slice length: the flattened sequence of pair-frames is cut into equal slices, one per worker
+// (frames cost the same, so equal static shares balance perfectly and cost one halo frame each);
+// tiny batches use fewer, longer slices so that the halo stays below ~1/8 of the work.
+// AACFB_SLICE_LEN overrides (tuning aid).
+int pick_slice(int n_pairs, int T, int workers) {
+    if (const char *env = std::getenv("AACFB_SLICE_LEN")) {
         const int v = std::atoi(env);
-        if (v >= 1) return std::min(v, T);
+        if (v >= 1) return v;
     }
-    static std::mutex mu;
-    static std::map<std::tuple<int, int, int>, int> cache;
-    std::lock_guard<std::mutex> lock(mu);
-    const auto key = std::make_tuple(n_pairs, T, workers);
-    const auto hit = cache.find(key);
-    if (hit != cache.end()) return hit->second;
-    long best_cost = -1;
-    int best_L = T, last_chunks = 0;
-    for (int L = T; L >= 1; --L) {
-        const int chunks = (T + L - 1) / L;
-        if (chunks == last_chunks) continue;  // the largest L of each chunk count comes first... keep the most even split
-        last_chunks = chunks;
-        const int Le = (T + chunks - 1) / chunks;  // most even split into `chunks` pieces
-        if ((long)n_pairs * chunks > 64L * workers && best_cost >= 0) break;
-        const long cost = simulate_makespan(n_pairs, T, Le, workers);
-        if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_L = Le; }
-    }
-    cache[key] = best_L;
-    return best_L;
+    const long total = (long)n_pairs * T;
+    long q = (total + workers - 1) / workers;
+    if (q < 8) q = std::min<long>(8, total);
+    return (int)std::max<long>(1, q);
 }
 
 // Enqueue TNS pre-pass (if the context's mode asks for it) and the synthesis
@@ -161,9 +123,10 @@ int enqueue(aacfb_ctx *ctx, const float *d_spectra, const aacfb_frame_info *d_in
     sp.ovl_out = in_place_state ? ctx->d_ovl[ctx->cur] : ctx->d_ovl[ctx->cur ^ 1];
     sp.tab = ctx->d_tab;
     const int n_pairs = (S_sub * nc + 1) / 2;
-    const int L = in_place_state ? T : pick_chunk(n_pairs, T, ctx->num_sms * kWorkers);
-    sp.g = make_geometry(S_sub, T, nc, ctx->C, c0, s_base, L);
-    sp.n_items = sp.g.n_pairs * sp.g.n_chunks;
+    if ((long long)S_sub * T * nc >= (1ll << 30)) return fail(ctx, AACFB_ERR_ARG, "batch too large: split it (channel-frames < 2^30)");
+    // in-place state (inner seam): one item, so the state is read before it is written
+    const int Q = in_place_state ? n_pairs * T : pick_slice(n_pairs, T, ctx->num_sms * kWorkers);
+    sp.g = make_geometry(S_sub, T, nc, ctx->C, c0, s_base, Q);
     sp.scale = scale;
     // Two instantiations walk the same item list: the long-only one takes the items without
     // EIGHT_SHORT frames, the generic one the rest (each item is classified on the device).

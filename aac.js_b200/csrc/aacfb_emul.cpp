@@ -66,58 +66,63 @@ extern "C" __attribute__((visibility("default"))) int aacfb_emul_process(
     }
     const float *rows = tns_on ? scratch.data() : spectra;
 
-    const Geometry g = make_geometry(S, T, C, C, 0, 0, chunk_len);
-    const int n_items = g.n_pairs * g.n_chunks;
-    alignas(16) static thread_local float dummy;
-    (void)dummy;
+    Geometry g = make_geometry(S, T, C, C, 0, 0, chunk_len);
+    g.stride = 1;  // in-place overlap state below: visit the slices in memory order
 
-    for (int item = 0; item < n_items; ++item) {
-        const Item it = make_item(g, item);
+    for (int item = 0; item < g.n_items; ++item) {
+        const int f0 = item_begin(g, item), f1 = item_end(g, item);
+        const int fb = (f0 % g.T) != 0 ? f0 - 1 : f0;
+        const int nf = f1 - fb;
         std::barrier<> bar(kWorkerThreads);
         std::vector<float> stage_mem(3 * kStageFloats + 4);
         float *stage = stage_mem.data();
         while (reinterpret_cast<uintptr_t>(stage) & 15) ++stage;
         float *scratch2[2] = {stage + kStageFloats, stage + 2 * kStageFloats};
         float mailbox[kWorkerThreads];
-        const int f_begin = it.t0 > 0 ? it.t0 - 1 : 0;
         bool item_has_short = false;  // the kernel's per-item classification
-        for (int t = f_begin; t < it.t1; ++t)
-            for (int c = 0; c < it.nch; ++c)
-                item_has_short |= info[cf_index(g, it.s[c], t, it.j[c])].window_sequence == AACFB_EIGHT_SHORT_SEQUENCE;
+        for (int f = 0; f < nf; ++f) {
+            const Pair pp = make_pair(g, (int)((fb + f) / g.T));
+            const int t = (int)((fb + f) % g.T);
+            for (int c = 0; c < pp.nch; ++c)
+                item_has_short |= info[cf_index(g, pp.s[c], t, pp.j[c])].window_sequence == AACFB_EIGHT_SHORT_SEQUENCE;
+        }
 
         auto body = [&](int u) {
             HostSync sync{&bar, mailbox};
             Pts z;
             Ovl ov;
             std::memset(&ov, 0, sizeof ov);
-            if (it.t0 == 0) {
-                ovl_load<0>(u, overlap + state_index(g, it.s[0], it.j[0]), ov, kScale);
-                if (it.nch == 2) ovl_load<1>(u, overlap + state_index(g, it.s[1], it.j[1]), ov, kScale);
-            }
-            for (int t = f_begin; t < it.t1; ++t) {
+            for (int f = 0; f < nf; ++f) {
+                const Pair pr = make_pair(g, (int)((fb + f) / g.T));
+                const int t = (int)((fb + f) % g.T);
+                if (t == 0) {
+                    ovl_load<0>(u, overlap + state_index(g, pr.s[0], pr.j[0]), ov, kScale);
+                    if (pr.nch == 2) ovl_load<1>(u, overlap + state_index(g, pr.s[1], pr.j[1]), ov, kScale);
+                }
                 // "TMA": thread 0 fills the stage, everyone waits
                 if (u == 0)
-                    for (int c = 0; c < it.nch; ++c)
-                        std::memcpy(stage + 1024 * c, rows + cf_index(g, it.s[c], t, it.j[c]) * 1024, 4096);
+                    for (int c = 0; c < pr.nch; ++c)
+                        std::memcpy(stage + 1024 * c, rows + cf_index(g, pr.s[c], t, pr.j[c]) * 1024, 4096);
                 bar.arrive_and_wait();
                 FrameIO io;
                 io.stage = stage;
-                io.scratch = scratch2[(t - f_begin) & 1];
-                io.nch = it.nch;
-                io.dst.emit = t >= it.t0;
-                io.dst.interleaved = it.interleaved;
+                io.scratch = scratch2[f & 1];
+                io.nch = pr.nch;
+                io.dst.emit = fb + f >= f0;
+                io.dst.interleaved = pr.interleaved;
                 io.dst.scale = kScale;
                 io.dst.inv_scale = 1.0f / kScale;
                 io.dst.ostride = g.nc;
-                for (int c = 0; c < 2; ++c) io.fi[c] = fb_pack(info[cf_index(g, it.s[c], t, it.j[c])]);
-                io.dst.out0 = pcm + ((size_t)it.s[0] * g.T + t) * 1024 * g.nc + it.j[0];
-                io.dst.out1 = pcm + ((size_t)it.s[1] * g.T + t) * 1024 * g.nc + it.j[1];
+                for (int c = 0; c < 2; ++c) io.fi[c] = fb_pack(info[cf_index(g, pr.s[c], t, pr.j[c])]);
+                io.dst.out0 = pcm + ((size_t)pr.s[0] * g.T + t) * 1024 * g.nc + pr.j[0];
+                io.dst.out1 = pcm + ((size_t)pr.s[1] * g.T + t) * 1024 * g.nc + pr.j[1];
                 if (item_has_short) worker_frame<true>(u, sync, io, tab, &H.synth, z, ov);
                 else worker_frame<false>(u, sync, io, tab, &H.synth, z, ov);
-            }
-            if (it.t1 == g.T) {
-                ovl_store<0>(u, ov, overlap + state_index(g, it.s[0], it.j[0]), 1.0f / kScale);
-                if (it.nch == 2) ovl_store<1>(u, ov, overlap + state_index(g, it.s[1], it.j[1]), 1.0f / kScale);
+                if (t == g.T - 1) {
+                    // NOTE: in place -- safe here because items run one after the other, in order
+                    ovl_store<0>(u, ov, overlap + state_index(g, pr.s[0], pr.j[0]), 1.0f / kScale);
+                    if (pr.nch == 2) ovl_store<1>(u, ov, overlap + state_index(g, pr.s[1], pr.j[1]), 1.0f / kScale);
+                }
             }
         };
         std::vector<std::thread> th;

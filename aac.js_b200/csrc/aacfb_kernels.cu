@@ -36,7 +36,7 @@ struct Layout {
     static constexpr int kOffStages = kTabBytes;
     static constexpr int kOffBars = kOffStages + W * kBufsPerWorker * kStageBytes;
     static constexpr int kOffSlots = kOffBars + W * ST * 8;
-    static constexpr int kTotal = kOffSlots + W * 8;
+    static constexpr int kTotal = kOffSlots + W * 32;
     static_assert(kTotal <= 227 * 1024, "shared memory budget");
     static_assert(2 * W + 1 <= 16, "named barriers");
 };
@@ -143,7 +143,7 @@ __global__ void __launch_bounds__(W * 64, 1) synth_kernel(const __grid_constant_
     float *stages = reinterpret_cast<float *>(smem + kOffStages) + (size_t)w * kBufsPerWorker * kStageFloats;
     float *scratch = stages + kStages * kStageFloats;
     const uint32_t bars = smem_u32(smem + kOffBars) + w * kStages * 8;
-    volatile int *slot = reinterpret_cast<volatile int *>(smem + kOffSlots) + 2 * w;  // [0] item, [1] short flag
+    volatile int *slot = reinterpret_cast<volatile int *>(smem + kOffSlots) + 8 * w;  // [0] item, [1] short flag, [2..6] prefetch cursor
     if (leader) {
         for (int s = 0; s < kStages; ++s) mbar_init(bars + 8 * s, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -172,15 +172,20 @@ __global__ void __launch_bounds__(W * 64, 1) synth_kernel(const __grid_constant_
         first = false;
         sync.barrier();
         const int item = slot[0];
-        if (item >= P.n_items) break;
-        const Item it = make_item(g, item);
-        const int f_begin = it.t0 > 0 ? it.t0 - 1 : 0;
-        const int nf = it.t1 - f_begin;
+        if (item >= g.n_items) break;
+        const int f0 = item_begin(g, item), f1 = item_end(g, item);
+        const int p0 = f0 / g.T, t0 = f0 - p0 * g.T;
+        const int fb = t0 != 0 ? f0 - 1 : f0;   // halo frame first, unless the slice starts a pair
+        const int tb = t0 != 0 ? t0 - 1 : 0;
+        const int nf = f1 - fb;
         {   // does this item contain an EIGHT_SHORT frame?  (64 threads scan its side info)
             bool mine = false;
             for (int f = tid & 63; f < nf; f += 64) {
-                mine |= is_short(info_lo(P, cf_index(g, it.s[0], f_begin + f, it.j[0])));
-                if (it.nch == 2) mine |= is_short(info_lo(P, cf_index(g, it.s[1], f_begin + f, it.j[1])));
+                const int ff = fb + f, pi = ff / g.T;
+                const Pair pp = make_pair(g, pi);
+                const int t = ff - pi * g.T;
+                mine |= is_short(info_lo(P, cf_index(g, pp.s[0], t, pp.j[0])));
+                if (pp.nch == 2) mine |= is_short(info_lo(P, cf_index(g, pp.s[1], t, pp.j[1])));
             }
             if (__any_sync(0xffffffffu, mine) && (tid & 31) == 0) slot[1] = 1;
             sync.barrier();
@@ -192,52 +197,75 @@ __global__ void __launch_bounds__(W * 64, 1) synth_kernel(const __grid_constant_
             }
         }
 
+        // Prefetch cursor: the frame whose rows go into the ring next.  Only the leader thread
+        // uses it, so it lives in shared memory rather than in every thread's registers:
+        // [0] pair, [1] t, [2],[3] channel-frame index of the two chains (advance by nc per frame).
+        volatile int *cur = slot + 2;
+        auto cursor_to = [&](int pair, int t) {
+            const Pair pn = make_pair(g, pair);
+            cur[0] = pair; cur[1] = t;
+            cur[2] = (int)cf_index(g, pn.s[0], t, pn.j[0]);
+            cur[3] = (int)cf_index(g, pn.s[1], t, pn.j[1]);
+            cur[4] = pn.nch;
+        };
+        if (leader) cursor_to(p0, tb);
+        auto refill = [&](uint32_t st) {
+            const int tn = cur[1], ca = cur[2], cb = cur[3];
+            sync.dst = smem_u32(stages + st * kStageFloats);
+            sync.mbar = bars + 8 * st;
+            sync.nrows = cur[4];
+            sync.src[0] = row_ptr(P, (size_t)ca);
+            sync.src[1] = row_ptr(P, (size_t)cb);
+            if (tn + 1 == g.T) { if (cur[0] + 1 < g.n_pairs) cursor_to(cur[0] + 1, 0); }
+            else { cur[1] = tn + 1; cur[2] = ca + g.nc; cur[3] = cb + g.nc; }
+        };
         if (leader) {  // prologue: fill the ring
             for (int i = 0; i < kStages && i < nf; ++i) {
-                const uint32_t st = (fc + i) % kStages;
-                sync.dst = smem_u32(stages + st * kStageFloats);
-                sync.mbar = bars + 8 * st;
-                sync.nrows = it.nch;
-                sync.src[0] = row_ptr(P, cf_index(g, it.s[0], f_begin + i, it.j[0]));
-                sync.src[1] = row_ptr(P, cf_index(g, it.s[1], f_begin + i, it.j[1]));
+                refill((fc + i) % kStages);
                 sync.issue();
             }
         }
-        if (it.t0 == 0) {
-            ovl_load<0>(u, P.ovl_in + state_index(g, it.s[0], it.j[0]), ov, P.scale);
-            if (it.nch == 2) ovl_load<1>(u, P.ovl_in + state_index(g, it.s[1], it.j[1]), ov, P.scale);
-        }
 
+        Pair pr = make_pair(g, p0);
+        int t = tb, pi = p0;
+        // channel-frame indices and PCM offsets of the two chains advance linearly inside a pair
+        size_t cfa = cf_index(g, pr.s[0], t, pr.j[0]), cfb = cf_index(g, pr.s[1], t, pr.j[1]);
+        size_t oa = ((size_t)pr.s[0] * g.T + t) * 1024 * g.nc + pr.j[0], ob = ((size_t)pr.s[1] * g.T + t) * 1024 * g.nc + pr.j[1];
         for (int f = 0; f < nf; ++f, ++fc) {
-            const int t = f_begin + f;
+            if (t == 0) {  // a pair starts here: its overlap comes from the state
+                ovl_load<0>(u, P.ovl_in + state_index(g, pr.s[0], pr.j[0]), ov, P.scale);
+                if (pr.nch == 2) ovl_load<1>(u, P.ovl_in + state_index(g, pr.s[1], pr.j[1]), ov, P.scale);
+            }
             const uint32_t st = fc % kStages;
             FrameIO io;
             io.stage = stages + st * kStageFloats;
             io.scratch = scratch + (fc & 1u) * kStageFloats;
-            io.nch = it.nch;
-            io.dst.emit = t >= it.t0;
-            io.dst.interleaved = it.interleaved;
+            io.nch = pr.nch;
+            io.dst.emit = fb + f >= f0;
+            io.dst.interleaved = pr.interleaved;
             io.dst.scale = P.scale;
             io.dst.inv_scale = 1.0f / P.scale;
             io.dst.ostride = g.nc;
-            io.fi[0] = info_lo(P, cf_index(g, it.s[0], t, it.j[0]));
-            io.fi[1] = info_lo(P, cf_index(g, it.s[1], t, it.j[1]));
-            io.dst.out0 = P.pcm + ((size_t)it.s[0] * g.T + t) * 1024 * g.nc + it.j[0];
-            io.dst.out1 = P.pcm + ((size_t)it.s[1] * g.T + t) * 1024 * g.nc + it.j[1];
+            io.fi[0] = info_lo(P, cfa);
+            io.fi[1] = info_lo(P, cfb);
+            io.dst.out0 = P.pcm + oa;
+            io.dst.out1 = P.pcm + ob;
             sync.next_valid = f + kStages < nf;
-            if (leader && sync.next_valid) {
-                sync.dst = smem_u32(io.stage);
-                sync.mbar = bars + 8 * st;
-                sync.nrows = it.nch;
-                sync.src[0] = row_ptr(P, cf_index(g, it.s[0], t + kStages, it.j[0]));
-                sync.src[1] = row_ptr(P, cf_index(g, it.s[1], t + kStages, it.j[1]));
-            }
+            if (leader && sync.next_valid) refill(st);
             mbar_wait(bars + 8 * st, (fc / kStages) & 1u);
             worker_frame<GENERIC>(u, sync, io, ts, P.tab, z, ov);
-        }
-        if (it.t1 == g.T) {
-            ovl_store<0>(u, ov, P.ovl_out + state_index(g, it.s[0], it.j[0]), 1.0f / P.scale);
-            if (it.nch == 2) ovl_store<1>(u, ov, P.ovl_out + state_index(g, it.s[1], it.j[1]), 1.0f / P.scale);
+            cfa += g.nc; cfb += g.nc;
+            oa += (size_t)1024 * g.nc; ob += (size_t)1024 * g.nc;
+            if (++t == g.T) {  // the pair is complete: its overlap goes back to the state
+                ovl_store<0>(u, ov, P.ovl_out + state_index(g, pr.s[0], pr.j[0]), 1.0f / P.scale);
+                if (pr.nch == 2) ovl_store<1>(u, ov, P.ovl_out + state_index(g, pr.s[1], pr.j[1]), 1.0f / P.scale);
+                t = 0;
+                if (f + 1 < nf) {
+                    pr = make_pair(g, ++pi);
+                    cfa = cf_index(g, pr.s[0], 0, pr.j[0]); cfb = cf_index(g, pr.s[1], 0, pr.j[1]);
+                    oa = (size_t)pr.s[0] * g.T * 1024 * g.nc + pr.j[0]; ob = (size_t)pr.s[1] * g.T * 1024 * g.nc + pr.j[1];
+                }
+            }
         }
     }
 }
@@ -267,7 +295,7 @@ static cudaError_t launch_one(const SynthParams &P, int num_sms, cudaStream_t st
         if (e != cudaSuccess) return e;
         attr_done[dev] = true;
     }
-    const int grid = num_sms < (P.n_items + W - 1) / W ? num_sms : (P.n_items + W - 1) / W;
+    const int grid = num_sms < (P.g.n_items + W - 1) / W ? num_sms : (P.g.n_items + W - 1) / W;
     synth_kernel<GENERIC, W, ST><<<grid < 1 ? 1 : grid, W * 64, Layout<W, ST>::kTotal, stream>>>(P);
     return cudaGetLastError();
 }

@@ -31,7 +31,6 @@ struct SynthParams {
     float *ovl_out;                 // overlap state written by chunks ending at t = T
     const SynthTables *tab;         // device copy of the tables
     Geometry g;
-    int n_items;
     unsigned *counter;              // zeroed before launch (one per kernel instantiation)
     unsigned *short_items;          // zeroed; number of items with EIGHT_SHORT frames (set by the long-only pass)
     float scale;
