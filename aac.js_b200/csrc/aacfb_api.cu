@@ -33,6 +33,8 @@ struct Lane {                    // device staging of one in-flight sub-batch of
     uint32_t *d_offsets = nullptr;
     size_t cap_cf = 0;           // capacity in channel-frames
     size_t cap_scratch = 0;
+    // scratch holds cap_scratch rows followed by cap_scratch range words (see tns_kernel)
+    uint32_t *ranges() const { return reinterpret_cast<uint32_t *>(d_scratch + cap_scratch * 1024); }
 };
 
 }  // namespace
@@ -104,21 +106,23 @@ int pick_slice(int n_pairs, int T, int workers) {
 // Enqueue TNS pre-pass (if the context's mode asks for it) and the synthesis
 // kernel for S_sub streams starting at stream s_base, all on `stream`.
 int enqueue(aacfb_ctx *ctx, const float *d_spectra, const aacfb_frame_info *d_info, const uint8_t *d_blob,
-            const uint32_t *d_offsets, size_t blob_bytes, float *d_scratch, float *d_pcm, int S_sub, int s_base,
+            const uint32_t *d_offsets, size_t blob_bytes, float *d_scratch, uint32_t *d_ranges, float *d_pcm, int S_sub,
+            int s_base,
             int T, int nc, int c0, float scale, bool in_place_state, cudaStream_t stream) {
     const uint32_t mode = ctx->flags & AACFB_TNS_MODE_MASK;
     const size_t n_cf = (size_t)S_sub * T * nc;
     const bool tns_on = mode != AACFB_TNS_AS_SHIPPED && d_blob && d_offsets && blob_bytes > 0 && d_scratch;
     if (tns_on) {
         TnsParams tp{};
-        tp.spectra = d_spectra; tp.scratch = d_scratch; tp.info = d_info; tp.blob = d_blob; tp.offsets = d_offsets;
+        tp.spectra = d_spectra; tp.scratch = d_scratch; tp.ranges = d_ranges; tp.info = d_info; tp.blob = d_blob;
+        tp.offsets = d_offsets;
         tp.blob_bytes = blob_bytes; tp.n_cf = n_cf; tp.sample_index = ctx->sample_index;
         tp.ar = mode == AACFB_TNS_FIXED_AR; tp.bands = ctx->d_bands;
         CU(ctx, launch_tns(tp, stream));
         ctx->launches++;
     }
     SynthParams sp{};
-    sp.spectra = d_spectra; sp.scratch = tns_on ? d_scratch : nullptr; sp.info = d_info; sp.pcm = d_pcm;
+    sp.spectra = d_spectra; sp.scratch = tns_on ? d_scratch : nullptr; sp.ranges = d_ranges; sp.info = d_info; sp.pcm = d_pcm;
     sp.ovl_in = ctx->d_ovl[ctx->cur];
     sp.ovl_out = in_place_state ? ctx->d_ovl[ctx->cur] : ctx->d_ovl[ctx->cur ^ 1];
     sp.tab = ctx->d_tab;
@@ -154,7 +158,7 @@ int grow_lane(aacfb_ctx *ctx, Lane &ln, size_t n_cf, bool need_scratch) {
     }
     if (need_scratch && n_cf > ln.cap_scratch) {
         cudaFree(ln.d_scratch); ln.d_scratch = nullptr; ln.cap_scratch = 0;
-        CU(ctx, cudaMalloc(&ln.d_scratch, n_cf * 4096));
+        CU(ctx, cudaMalloc(&ln.d_scratch, n_cf * 4100));
         ln.cap_scratch = n_cf;
     }
     return AACFB_OK;
@@ -328,13 +332,14 @@ API int aacfb_process_device(aacfb_ctx *ctx, const float *d_spectra, const aacfb
         if (n_cf > ctx->cap_dev_scratch) {
             CU(ctx, cudaDeviceSynchronize());
             cudaFree(ctx->d_dev_scratch); ctx->d_dev_scratch = nullptr; ctx->cap_dev_scratch = 0;
-            CU(ctx, cudaMalloc(&ctx->d_dev_scratch, n_cf * 4096));
+            CU(ctx, cudaMalloc(&ctx->d_dev_scratch, n_cf * 4100));
             ctx->cap_dev_scratch = n_cf;
         }
         scratch = ctx->d_dev_scratch;
     }
-    const int rc = enqueue(ctx, d_spectra, d_info, d_tns_blob, d_tns_offsets, tns_blob_bytes, scratch, d_pcm, ctx->S, 0,
-                           n_frames, ctx->C, 0, 1.0f / 32768.0f, false, st);
+    uint32_t *ranges = scratch ? reinterpret_cast<uint32_t *>(scratch + ctx->cap_dev_scratch * 1024) : nullptr;
+    const int rc = enqueue(ctx, d_spectra, d_info, d_tns_blob, d_tns_offsets, tns_blob_bytes, scratch, ranges, d_pcm, ctx->S,
+                           0, n_frames, ctx->C, 0, 1.0f / 32768.0f, false, st);
     if (rc != AACFB_OK) return rc;
     ctx->cur ^= 1;
     return AACFB_OK;
@@ -383,7 +388,8 @@ API int aacfb_process(aacfb_ctx *ctx, const float *spectra, const aacfb_frame_in
         if (tns_on && blob_bytes)
             CU(ctx, cudaMemcpyAsync(ln.d_offsets, tns_offsets + off, (n_cf + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, ln.stream));
         rc = enqueue(ctx, ln.d_spectra, ln.d_info, (tns_on && blob_bytes) ? ctx->d_blob : nullptr, ln.d_offsets, blob_bytes,
-                     ln.d_scratch, ln.d_pcm, sn, s0, T, C, 0, 1.0f / 32768.0f, false, ln.stream);
+                     ln.d_scratch, ln.d_scratch ? ln.ranges() : nullptr, ln.d_pcm, sn, s0, T, C, 0, 1.0f / 32768.0f, false,
+                     ln.stream);
         if (rc != AACFB_OK) return rc;
         CU(ctx, cudaMemcpyAsync(pcm + off * 1024, ln.d_pcm, n_cf * 4096, cudaMemcpyDeviceToHost, ln.stream));
     }
@@ -409,7 +415,7 @@ API int aacfb_filterbank_process(aacfb_ctx *ctx, int stream, int channel, const 
     fi.tns_present = 0;  // the inner seam is the filterbank alone
     CU(ctx, cudaMemcpyAsync(ln.d_spectra, input, 4096, cudaMemcpyHostToDevice, ln.stream));
     CU(ctx, cudaMemcpyAsync(ln.d_info, &fi, sizeof fi, cudaMemcpyHostToDevice, ln.stream));
-    rc = enqueue(ctx, ln.d_spectra, ln.d_info, nullptr, nullptr, 0, nullptr, ln.d_pcm, 1, stream, 1, 1, channel, 1.0f,
+    rc = enqueue(ctx, ln.d_spectra, ln.d_info, nullptr, nullptr, 0, nullptr, nullptr, ln.d_pcm, 1, stream, 1, 1, channel, 1.0f,
                  true, ln.stream);
     if (rc != AACFB_OK) return rc;
     CU(ctx, cudaMemcpyAsync(output, ln.d_pcm, 4096, cudaMemcpyDeviceToHost, ln.stream));
@@ -442,7 +448,9 @@ API int aacfb_tns_process(aacfb_ctx *ctx, const aacfb_frame_info *info, const ui
     CU(ctx, cudaMemcpyAsync(ln.d_offsets, offs, sizeof offs, cudaMemcpyHostToDevice, ln.stream));
     CU(ctx, cudaMemcpyAsync(ctx->d_blob, tns_block, block_bytes, cudaMemcpyHostToDevice, ln.stream));
     TnsParams tp{};
-    tp.spectra = ln.d_spectra; tp.scratch = ln.d_scratch; tp.info = ln.d_info; tp.blob = ctx->d_blob;
+    // the kernel writes only the filtered interval of the row: start from a copy
+    CU(ctx, cudaMemcpyAsync(ln.d_scratch, ln.d_spectra, 4096, cudaMemcpyDeviceToDevice, ln.stream));
+    tp.spectra = ln.d_spectra; tp.scratch = ln.d_scratch; tp.ranges = ln.ranges(); tp.info = ln.d_info; tp.blob = ctx->d_blob;
     tp.offsets = ln.d_offsets; tp.blob_bytes = block_bytes; tp.n_cf = 1; tp.sample_index = ctx->sample_index;
     tp.ar = mode == AACFB_TNS_FIXED_AR; tp.bands = ctx->d_bands;
     CU(ctx, launch_tns(tp, ln.stream));

@@ -68,11 +68,6 @@ __device__ __forceinline__ void bulk_load(uint32_t dst, const void *src, uint32_
                  : "memory");
 }
 
-struct RowSource {
-    const float *spectra, *scratch;
-    const aacfb_frame_info *info;
-};
-
 struct DevSync {
     uint32_t bar_id;      // named barrier of this worker (all 64 threads block)
     uint32_t free_id;     // named barrier "stage is free": followers arrive, the leader's warp waits
@@ -80,13 +75,26 @@ struct DevSync {
     // the refill this frame's stage_free() has to issue (leader only)
     bool next_valid;
     uint32_t dst, mbar;
-    const float *src[2];
+    int cf[2];            // channel-frame index of the row(s) to fetch
+    uint32_t rng[2];      // lo4 | hi4 << 16: float4 interval that comes from the TNS scratch (0: none)
     int nrows;
+    const float *spectra, *scratch;
     __device__ __forceinline__ void barrier() { asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory"); }
+    // One row = 4096 bytes on the mbarrier, fetched as up to three 1-D bulk copies: the interval
+    // the TNS pass filtered comes from its scratch, the rest straight from the spectra.
+    __device__ __forceinline__ void issue_row(uint32_t d, int cfi, uint32_t r) {
+        const float *a = spectra + (size_t)cfi * 1024;
+        const uint32_t lo = r & 0xffffu, hi = r >> 16;
+        if (hi <= lo) { bulk_load(d, a, 4096u, mbar); return; }
+        const float *b = scratch + (size_t)cfi * 1024;
+        if (lo) bulk_load(d, a, 16u * lo, mbar);
+        bulk_load(d + 16u * lo, b + 4 * lo, 16u * (hi - lo), mbar);
+        if (hi < 256u) bulk_load(d + 16u * hi, a + 4 * hi, 16u * (256u - hi), mbar);
+    }
     __device__ __forceinline__ void issue() {
         mbar_expect_tx(mbar, (uint32_t)nrows * 4096u);
-        bulk_load(dst, src[0], 4096u, mbar);
-        if (nrows == 2) bulk_load(dst + 4096u, src[1], 4096u, mbar);
+        issue_row(dst, cf[0], rng[0]);
+        if (nrows == 2) issue_row(dst + 4096u, cf[1], rng[1]);
     }
     __device__ __forceinline__ void stage_free() {
         // order this thread's generic-proxy accesses to the stage before the async-proxy refill
@@ -107,9 +115,10 @@ __device__ __forceinline__ uint2 info_raw(const SynthParams &P, size_t cf) {
     return __ldg(reinterpret_cast<const uint2 *>(P.info) + cf);
 }
 __device__ __forceinline__ FrameBits info_lo(const SynthParams &P, size_t cf) { return info_raw(P, cf).x; }
-__device__ __forceinline__ const float *row_ptr(const SynthParams &P, size_t cf) {
+// which float4 interval of row cf lives in the TNS scratch (0: the whole row comes from the spectra)
+__device__ __forceinline__ uint32_t row_range(const SynthParams &P, size_t cf) {
     const bool tns = P.scratch != nullptr && (info_raw(P, cf).y & 0xffu) != 0;
-    return (tns ? P.scratch : P.spectra) + cf * 1024;
+    return tns ? __ldg(P.ranges + cf) : 0u;
 }
 
 }  // namespace
@@ -155,6 +164,8 @@ __global__ void __launch_bounds__(W * 64, 1) synth_kernel(const __grid_constant_
     sync.free_id = 1 + kWorkers + w;
     sync.leader_warp = ((tid >> 5) & 1) == 0;
     sync.leader = leader;
+    sync.spectra = P.spectra;
+    sync.scratch = P.scratch;
     const Geometry g = P.g;
     uint32_t fc = 0;  // frames this worker has staged so far: ring position and mbarrier phase
     Pts z;
@@ -214,8 +225,9 @@ __global__ void __launch_bounds__(W * 64, 1) synth_kernel(const __grid_constant_
             sync.dst = smem_u32(stages + st * kStageFloats);
             sync.mbar = bars + 8 * st;
             sync.nrows = cur[4];
-            sync.src[0] = row_ptr(P, (size_t)ca);
-            sync.src[1] = row_ptr(P, (size_t)cb);
+            sync.cf[0] = ca; sync.cf[1] = cb;
+            sync.rng[0] = row_range(P, (size_t)ca);
+            sync.rng[1] = row_range(P, (size_t)cb);
             if (tn + 1 == g.T) { if (cur[0] + 1 < g.n_pairs) cursor_to(cur[0] + 1, 0); }
             else { cur[1] = tn + 1; cur[2] = ca + g.nc; cur[3] = cb + g.nc; }
         };
@@ -270,18 +282,213 @@ __global__ void __launch_bounds__(W * 64, 1) synth_kernel(const __grid_constant_
     }
 }
 
-// One thread per channel-frame that carries TNS: write its filtered copy to
-// `scratch` (every float4 exactly once).  The chain is serial by construction
-// (see tns_run), parallelism is across channel-frames.
-__global__ void __launch_bounds__(kTnsThreads, 8) tns_kernel(const __grid_constant__ TnsParams P) {
-    const size_t cf = (size_t)blockIdx.x * kTnsThreads + threadIdx.x;
-    if (cf >= P.n_cf) return;
-    const uint2 raw = __ldg(reinterpret_cast<const uint2 *>(P.info) + cf);
-    if ((raw.y & 0xffu) == 0) return;
-    const uint32_t o0 = P.offsets[cf], o1 = P.offsets[cf + 1];
-    const bool has_block = o1 > o0 && o1 <= P.blob_bytes;
-    tns_apply((FrameBits)raw.x & 0xffffff03u, P.blob + (has_block ? o0 : 0), has_block ? o1 - o0 : 0, P.sample_index,
-              P.ar != 0, *P.bands, P.spectra + cf * 1024, P.scratch + cf * 1024);
+// ------------------------------------------------------------------ TNS
+// tns_kernel: TNS.process (tns.js:105-177) for every channel-frame that carries TNS.
+//
+// The chain of one filter run is serial by construction (each tap is a rounded f32
+// read-modify-write in the reference's order), so parallelism is across channel-frames:
+// one LANE per row, each WARP autonomous over 32 consecutive rows (no CTA-level sync).
+// What is new against a thread-per-row loop is the data movement: a lane never touches
+// global memory for its own row.  The warp moves *tiles* of 32 rows x 32 coefficients
+//   global --cp.async 16 B, 4 whole 128-byte lines per instruction--> shared ring (3 tiles)
+//   shared: lane r filters row r of the tile in place (LDS.128 / STS.128, pitch 36 floats:
+//           conflict-free both for the row-per-lane and the line-per-quarter-warp pattern)
+//   shared --LDS.128 / STG.128, whole lines--> scratch
+// so every global access is a full line and the next two tiles are in flight while one is
+// being filtered.  A tile's column window is per row: block b of a run that starts at
+// `start` and walks in direction `inc` covers coefficients start + inc*(32b .. 32b+31).
+//
+// Only the filtered coefficients are written: scratch[cf] is valid on the bounding interval
+// [lo4, hi4) (float4 units) of the row's runs -- coefficients inside it that no filter touches
+// are copied -- and `ranges[cf]` = lo4 | hi4 << 16 tells synth_kernel which part of the row to
+// fetch from scratch (the rest comes straight from the spectra).
+constexpr int kTnsPitch = 36;                           // floats per tile row: 32 + 4 (144 B)
+constexpr int kTnsRing = 3;
+constexpr int kTnsTileFloats = 32 * kTnsPitch;
+constexpr int kTnsSmemBytes = kTnsWarps * kTnsRing * kTnsTileFloats * 4;
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait0() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// One run slot of the warp: lane r filters its run (start, size, inc; size = 0: none) of row r
+// (x_base / y_base point at row 0 of the warp).
+// ORD >= every lane's order (coefficients beyond a lane's order are zero: no-ops).
+template <int ORD, bool AR>
+__device__ __noinline__ void tns_tile_run(float *ring, int lane, const float *x_base, float *y_base, int start, int size,
+                                          int inc, const float *lpc, int order) {
+    float h[ORD], c[ORD];
+#pragma unroll
+    for (int i = 0; i < ORD; ++i) { h[i] = 0.f; c[i] = i < order ? lpc[i] : 0.f; }
+    const bool nan_from = order == AACFB_TNS_MAX_ORDER;
+    // the 8 rows this lane moves: r = (lane >> 3) + 4k, 16-byte column cc = lane & 7
+    const int cc = lane & 7;
+    int g_off[8], g_sz[8];   // g_off: element offset of block 0's float4 `cc`; g_sz: size, negative = downward
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int r = (lane >> 3) + 4 * k;
+        const int st_k = __shfl_sync(0xffffffffu, start, r);
+        const int sz_k = __shfl_sync(0xffffffffu, size, r), in_k = __shfl_sync(0xffffffffu, inc, r);
+        g_off[k] = r * 1024 + (in_k > 0 ? st_k : st_k - 31) + 4 * cc;
+        g_sz[k] = in_k > 0 ? sz_k : -sz_k;
+    }
+    int nblk = (size + 31) >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) nblk = max(nblk, __shfl_xor_sync(0xffffffffu, nblk, o));
+    const uint32_t ring_s = smem_u32(ring);
+    // is float4 `cc` of block b inside the run of served row k?  (position of the quad in run order)
+    auto quad_ok = [&](int k, int b) {
+        const int sz = g_sz[k];
+        return sz > 0 ? 32 * b + 4 * cc < sz : 32 * b + 4 * (7 - cc) < -sz;
+    };
+    auto load_tile = [&](int b, int slot) {
+        if (b < nblk) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                if (quad_ok(k, b)) {
+                    const int r = (lane >> 3) + 4 * k;
+                    const int off = g_off[k] + (g_sz[k] > 0 ? 32 * b : -32 * b);
+                    cp_async16(ring_s + 4u * (uint32_t)(slot * kTnsTileFloats + r * kTnsPitch + 4 * cc), x_base + off);
+                }
+        }
+        cp_async_commit();
+    };
+    load_tile(0, 0);
+    load_tile(1, 1);
+    int slot = 0;
+    for (int b = 0; b < nblk; ++b) {
+        cp_async_wait1();
+        __syncwarp();  // tile b has landed for every lane; tile b-1's write-out has been read
+        load_tile(b + 2, slot >= 1 ? slot - 1 : kTnsRing - 1);  // == (b + 2) % kTnsRing
+        float *tile = ring + slot * kTnsTileFloats;
+        const int left = size - 32 * b;
+        if (left > 0) {
+            float4 *row = reinterpret_cast<float4 *>(tile + lane * kTnsPitch);
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+                if (4 * q < left) {
+                    float4 *p = row + (inc > 0 ? q : 7 - q);
+                    *p = tns_quad<ORD, AR>(*p, inc, h, c, nan_from, 32 * b + 4 * q);
+                }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            if (quad_ok(k, b)) {
+                const int r = (lane >> 3) + 4 * k;
+                const int off = g_off[k] + (g_sz[k] > 0 ? 32 * b : -32 * b);
+                *reinterpret_cast<float4 *>(y_base + off) = *reinterpret_cast<const float4 *>(tile + r * kTnsPitch + 4 * cc);
+            }
+        slot = slot + 1 == kTnsRing ? 0 : slot + 1;
+    }
+    cp_async_wait0();
+    __syncwarp();
+}
+
+template <bool AR>
+__device__ __forceinline__ void tns_tile_dispatch(int ord_max, float *ring, int lane, const float *x, float *y, int start,
+                                                  int size, int inc, const float *lpc, int order) {
+    if (ord_max <= 4) tns_tile_run<4, AR>(ring, lane, x, y, start, size, inc, lpc, order);
+    else if (ord_max <= 8) tns_tile_run<8, AR>(ring, lane, x, y, start, size, inc, lpc, order);
+    else if (ord_max <= 12) tns_tile_run<12, AR>(ring, lane, x, y, start, size, inc, lpc, order);
+    else if (ord_max <= 16) tns_tile_run<16, AR>(ring, lane, x, y, start, size, inc, lpc, order);
+    else tns_tile_run<20, AR>(ring, lane, x, y, start, size, inc, lpc, order);
+}
+
+__global__ void __launch_bounds__(kTnsWarps * 32, 4) tns_kernel(const __grid_constant__ TnsParams P) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    float *ring = reinterpret_cast<float *>(smem) + wid * kTnsRing * kTnsTileFloats;
+    const size_t cf0 = ((size_t)blockIdx.x * kTnsWarps + wid) * 32;  // row 0 of this warp
+    if (cf0 >= P.n_cf) return;
+    const bool in_range = cf0 + lane < P.n_cf;
+    const size_t cf = in_range ? cf0 + lane : cf0;
+    uint2 raw = make_uint2(0u, 0u);
+    if (in_range) raw = __ldg(reinterpret_cast<const uint2 *>(P.info) + cf);
+    const bool present = in_range && (raw.y & 0xffu) != 0;
+    const FrameBits fi = (FrameBits)raw.x & 0xffffff03u;
+    uint32_t o0 = 0, o1 = 0;
+    if (present) { o0 = P.offsets[cf]; o1 = P.offsets[cf + 1]; }
+    const bool has_block = present && o1 > o0 && o1 <= P.blob_bytes;
+    const uint8_t *block = P.blob + (has_block ? o0 : 0);
+    const uint32_t block_bytes = has_block ? o1 - o0 : 0;
+
+    // pass 1: which float4s of the row do the runs cover, and their bounding interval
+    uint32_t covered[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) covered[i] = 0u;
+    int lo4 = 256, hi4 = 0;
+    if (has_block) {
+        TnsWalker wk(fi, block, block_bytes, P.sample_index, *P.bands);
+        for (TnsFilter ft = wk.next(); ft.valid; ft = wk.next()) {
+            if (!ft.active) continue;
+            const int lo = ft.inc > 0 ? ft.start : ft.start - ft.size + 1;
+            const int a = lo >> 2, b = (lo + ft.size) >> 2;
+            lo4 = min(lo4, a); hi4 = max(hi4, b);
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {  // bits [a, b) of the 256-bit map
+                const int s = max(a - 32 * g, 0), e = min(b - 32 * g, 32);
+                if (e > s) covered[g] |= (e - s == 32 ? 0xffffffffu : ((1u << (e - s)) - 1u) << s);
+            }
+        }
+    }
+    if (hi4 <= lo4) lo4 = hi4 = 0;
+    if (in_range) P.ranges[cf] = (uint32_t)lo4 | ((uint32_t)hi4 << 16);
+
+    // pass 2: the runs, one run slot of the warp at a time
+    {
+        TnsWalker wk(fi, block, block_bytes, P.sample_index, *P.bands);
+        bool more = has_block;
+        for (;;) {
+            TnsFilter ft;
+            ft.active = false; ft.valid = false; ft.size = 0; ft.start = 0; ft.inc = 1; ft.order = 0; ft.coef = nullptr;
+            while (more) {
+                ft = wk.next();
+                if (!ft.valid) { more = false; ft.active = false; }
+                if (ft.active || !more) break;
+            }
+            if (!__any_sync(0xffffffffu, ft.active)) break;
+            float lpc[AACFB_TNS_MAX_ORDER];
+            int order = 0, size = 0;
+            if (ft.active) {
+                order = ft.order; size = ft.size;
+                for (int i = 0; i < order; ++i) {  // reflection -> direct form, tns.js:128-140
+                    const float r = -ft.coef[i];
+                    lpc[i] = r;
+                    for (int j = 0, len = (i + 1) >> 1; j < len; ++j) {
+                        const float fwd = lpc[j], bwd = lpc[i - 1 - j];
+                        lpc[j] = f_fma(r, bwd, fwd);
+                        lpc[i - 1 - j] = f_fma(r, fwd, bwd);
+                    }
+                }
+            }
+            int ord_max = order;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) ord_max = max(ord_max, __shfl_xor_sync(0xffffffffu, ord_max, o));
+            const float *x0 = P.spectra + cf0 * 1024;
+            float *y0 = P.scratch + cf0 * 1024;
+            if (P.ar) tns_tile_dispatch<true>(ord_max, ring, lane, x0, y0, ft.start, size, ft.inc, lpc, order);
+            else tns_tile_dispatch<false>(ord_max, ring, lane, x0, y0, ft.start, size, ft.inc, lpc, order);
+        }
+    }
+
+    // pass 3: coefficients inside the interval that no run covers are copied (whole lines, row by row)
+    const float4 *x4 = reinterpret_cast<const float4 *>(P.spectra);
+    float4 *y4 = reinterpret_cast<float4 *>(P.scratch);
+    for (int r = 0; r < 32; ++r) {
+        const int lo_r = __shfl_sync(0xffffffffu, lo4, r), hi_r = __shfl_sync(0xffffffffu, hi4, r);
+        if (hi_r <= lo_r) continue;
+        const size_t cf_r = cf0 + r;
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+            const uint32_t cv = __shfl_sync(0xffffffffu, covered[g], r);
+            const int idx = 32 * g + lane;
+            if (!((cv >> lane) & 1u) && idx >= lo_r && idx < hi_r) y4[cf_r * 256 + idx] = x4[cf_r * 256 + idx];
+        }
+    }
 }
 
 template <bool GENERIC, int W, int ST>
@@ -306,9 +513,18 @@ cudaError_t launch_synth(const SynthParams &P, int num_sms, bool generic, cudaSt
 }
 
 cudaError_t launch_tns(const TnsParams &P, cudaStream_t stream) {
-    const unsigned grid = (unsigned)((P.n_cf + kTnsThreads - 1) / kTnsThreads);
+    static bool attr_done[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 64 && !attr_done[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(tns_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTnsSmemBytes);
+        if (e != cudaSuccess) return e;
+        attr_done[dev] = true;
+    }
+    const size_t rows_per_cta = (size_t)kTnsWarps * 32;
+    const unsigned grid = (unsigned)((P.n_cf + rows_per_cta - 1) / rows_per_cta);
     if (grid == 0) return cudaSuccess;
-    tns_kernel<<<grid, kTnsThreads, 0, stream>>>(P);
+    tns_kernel<<<grid, kTnsWarps * 32, kTnsSmemBytes, stream>>>(P);
     return cudaGetLastError();
 }
 

@@ -20,11 +20,12 @@ constexpr int kWorkers = AACFB_WORKERS;     // workers per CTA (6 x 64 threads -
 constexpr int kStages = AACFB_STAGES;       // TMA ring depth per worker
 constexpr int kWorkersGeneric = 6;          // generic instantiation (items with EIGHT_SHORT frames)
 constexpr int kStagesGeneric = 2;
-constexpr int kTnsThreads = 64;
+constexpr int kTnsWarps = 4;                // autonomous warps per tns_kernel CTA, 32 rows each
 
 struct SynthParams {
     const float *spectra;           // [S][T][nc][1024]
-    const float *scratch;           // TNS-filtered rows (same layout) or nullptr
+    const float *scratch;           // TNS-filtered rows (same layout, valid on `ranges` only) or nullptr
+    const uint32_t *ranges;         // [S][T][nc] lo4 | hi4 << 16: the float4 interval of a row that lives in scratch
     const aacfb_frame_info *info;   // [S][T][nc]
     float *pcm;                     // [S][T][1024][nc]
     const float *ovl_in;            // overlap state read by chunks starting at t = 0
@@ -39,6 +40,7 @@ struct SynthParams {
 struct TnsParams {
     const float *spectra;
     float *scratch;
+    uint32_t *ranges;               // out: per channel-frame interval of scratch that was written
     const aacfb_frame_info *info;
     const uint8_t *blob;
     const uint32_t *offsets;
