@@ -590,15 +590,30 @@ struct TnsFilter {
 struct TnsWalker {
     const uint8_t *block;
     uint32_t bytes, pos;
+    uint32_t nf[2];  // n_filt[0..7], fetched once (blocks are 4-byte aligned)
     const uint16_t *swb;
     int swb_count, window_count, mmm, w, f, bottom;
-    AACFB_HD TnsWalker(FrameBits fi, const uint8_t *b, uint32_t n, int sample_index, const TnsBandTables &bt)
-        : block(b), bytes(n), pos(8), w(0), f(0) {
+    AACFB_HD TnsWalker(FrameBits fi, const uint8_t *b, uint32_t n, int sample_index, const TnsBandTables &bt) {
+        init(fi, b, n, bt.swb_long[sample_index], bt.swb_long_count[sample_index], bt.swb_short[sample_index],
+             bt.swb_short_count[sample_index], bt.tns_max_bands[sample_index]);
+    }
+    // the same from one sample rate's tables (the kernel keeps them in shared memory)
+    AACFB_HD TnsWalker(FrameBits fi, const uint8_t *b, uint32_t n, const uint16_t *swb_long, int n_long,
+                       const uint16_t *swb_short, int n_short, int max_bands) {
+        init(fi, b, n, swb_long, n_long, swb_short, n_short, max_bands);
+    }
+    AACFB_HD void init(FrameBits fi, const uint8_t *b, uint32_t n, const uint16_t *swb_long, int n_long,
+                       const uint16_t *swb_short, int n_short, int max_bands /* tns.js:23: the long table, for short windows too */) {
+        block = b; bytes = n; pos = 8; w = 0; f = 0;
+        nf[0] = nf[1] = 0u;
+        if (n >= 8) {
+            nf[0] = reinterpret_cast<const uint32_t *>(b)[0];
+            nf[1] = reinterpret_cast<const uint32_t *>(b)[1];
+        }
         const bool is_short = fb_seq(fi) == AACFB_EIGHT_SHORT_SEQUENCE;
-        swb = is_short ? bt.swb_short[sample_index] : bt.swb_long[sample_index];
-        swb_count = is_short ? bt.swb_short_count[sample_index] : bt.swb_long_count[sample_index];
+        swb = is_short ? swb_short : swb_long;
+        swb_count = is_short ? n_short : n_long;
         window_count = is_short ? 8 : 1;
-        const int max_bands = bt.tns_max_bands[sample_index];  // tns.js:23 (the long table, for short windows too)
         const int max_sfb = (int)(fi >> 24);
         mmm = max_bands < max_sfb ? max_bands : max_sfb;
         bottom = swb_count;
@@ -607,9 +622,10 @@ struct TnsWalker {
         TnsFilter r;
         r.valid = false; r.active = false; r.start = r.size = r.order = 0; r.inc = 1; r.coef = nullptr;
         if (bytes < 8) return r;
-        while (w < 8 && f >= block[w]) { ++w; f = 0; bottom = swb_count; }
+        while (w < 8 && f >= (int)((nf[w >> 2] >> (8 * (w & 3))) & 0xffu)) { ++w; f = 0; bottom = swb_count; }
         if (w >= 8 || pos + 4 > bytes) return r;
-        const int length = block[pos], order = block[pos + 1], direction = block[pos + 2];
+        const uint32_t hdr = *reinterpret_cast<const uint32_t *>(block + pos);  // aacfb_tns_filter
+        const int length = hdr & 0xffu, order = (hdr >> 8) & 0xffu, direction = (hdr >> 16) & 0xffu;
         r.coef = reinterpret_cast<const float *>(block + pos + 4);
         pos += 4 + 4 * order;
         ++f;

@@ -305,7 +305,8 @@ __global__ void __launch_bounds__(W * 64, 1) synth_kernel(const __grid_constant_
 constexpr int kTnsPitch = 36;                           // floats per tile row: 32 + 4 (144 B)
 constexpr int kTnsRing = 3;
 constexpr int kTnsTileFloats = 32 * kTnsPitch;
-constexpr int kTnsSmemBytes = kTnsWarps * kTnsRing * kTnsTileFloats * 4;
+constexpr int kTnsSmemRing = kTnsWarps * kTnsRing * kTnsTileFloats * 4;
+constexpr int kTnsSmemBytes = kTnsSmemRing + 256;      // + the band tables of one sample rate
 
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void *src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
@@ -324,64 +325,100 @@ __device__ __noinline__ void tns_tile_run(float *ring, int lane, const float *x_
 #pragma unroll
     for (int i = 0; i < ORD; ++i) { h[i] = 0.f; c[i] = i < order ? lpc[i] : 0.f; }
     const bool nan_from = order == AACFB_TNS_MAX_ORDER;
-    // the 8 rows this lane moves: r = (lane >> 3) + 4k, 16-byte column cc = lane & 7
+    // The 8 rows this lane moves: r = (lane >> 3) + 4k, 16-byte column cc = lane & 7.
+    //   g_off : element offset (from row 0 of the warp) of float4 `cc` of the current block
+    //   g_step: +32 / -32 elements per block (direction of the served row's run)
+    //   g_nv  : my float4 is inside the run for blocks b < g_nv (its position in run order is
+    //           quad cc of an upward run, quad 7 - cc of a downward one)
     const int cc = lane & 7;
-    int g_off[8], g_sz[8];   // g_off: element offset of block 0's float4 `cc`; g_sz: size, negative = downward
+    int g_off[8], g_step[8], g_nv[8];
+    int nv_min = 1 << 30;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
         const int r = (lane >> 3) + 4 * k;
         const int st_k = __shfl_sync(0xffffffffu, start, r);
         const int sz_k = __shfl_sync(0xffffffffu, size, r), in_k = __shfl_sync(0xffffffffu, inc, r);
         g_off[k] = r * 1024 + (in_k > 0 ? st_k : st_k - 31) + 4 * cc;
-        g_sz[k] = in_k > 0 ? sz_k : -sz_k;
+        g_step[k] = in_k > 0 ? 32 : -32;
+        const int quad = in_k > 0 ? cc : 7 - cc;
+        g_nv[k] = sz_k > 4 * quad ? (sz_k - 4 * quad + 31) >> 5 : 0;
+        nv_min = min(nv_min, g_nv[k]);
     }
     int nblk = (size + 31) >> 5;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) nblk = max(nblk, __shfl_xor_sync(0xffffffffu, nblk, o));
-    const uint32_t ring_s = smem_u32(ring);
-    // is float4 `cc` of block b inside the run of served row k?  (position of the quad in run order)
-    auto quad_ok = [&](int k, int b) {
-        const int sz = g_sz[k];
-        return sz > 0 ? 32 * b + 4 * cc < sz : 32 * b + 4 * (7 - cc) < -sz;
-    };
-    auto load_tile = [&](int b, int slot) {
-        if (b < nblk) {
+    for (int o = 16; o > 0; o >>= 1) {
+        nblk = max(nblk, __shfl_xor_sync(0xffffffffu, nblk, o));
+        nv_min = min(nv_min, __shfl_xor_sync(0xffffffffu, nv_min, o));
+    }
+    const uint32_t ring_s = smem_u32(ring) + 4u * (uint32_t)((lane >> 3) * kTnsPitch + 4 * cc);
+    const float *tile_rd = ring + (lane >> 3) * kTnsPitch + 4 * cc;  // my float4 of served row k = 0
+    // Blocks b < nv_min are whole for every row of the warp: no predicates there.
+    auto load_tile = [&](int b, int slot) {  // tile b -> ring slot
+        if (b < nv_min) {
 #pragma unroll
             for (int k = 0; k < 8; ++k)
-                if (quad_ok(k, b)) {
-                    const int r = (lane >> 3) + 4 * k;
-                    const int off = g_off[k] + (g_sz[k] > 0 ? 32 * b : -32 * b);
-                    cp_async16(ring_s + 4u * (uint32_t)(slot * kTnsTileFloats + r * kTnsPitch + 4 * cc), x_base + off);
-                }
+                cp_async16(ring_s + 4u * (uint32_t)(slot * kTnsTileFloats + 4 * k * kTnsPitch),
+                           x_base + (g_off[k] + 2 * g_step[k]));
+        } else if (b < nblk) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                if (b < g_nv[k])
+                    cp_async16(ring_s + 4u * (uint32_t)(slot * kTnsTileFloats + 4 * k * kTnsPitch),
+                               x_base + (g_off[k] + 2 * g_step[k]));
         }
         cp_async_commit();
     };
+    // g_off describes block b while tile b + 2 is being fetched: start it two blocks back
+#pragma unroll
+    for (int k = 0; k < 8; ++k) g_off[k] -= 2 * g_step[k];
     load_tile(0, 0);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) g_off[k] += g_step[k];
     load_tile(1, 1);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) g_off[k] += g_step[k];
     int slot = 0;
     for (int b = 0; b < nblk; ++b) {
         cp_async_wait1();
         __syncwarp();  // tile b has landed for every lane; tile b-1's write-out has been read
         load_tile(b + 2, slot >= 1 ? slot - 1 : kTnsRing - 1);  // == (b + 2) % kTnsRing
         float *tile = ring + slot * kTnsTileFloats;
+        float4 *row = reinterpret_cast<float4 *>(tile + lane * kTnsPitch);
         const int left = size - 32 * b;
-        if (left > 0) {
-            float4 *row = reinterpret_cast<float4 *>(tile + lane * kTnsPitch);
+        if (left >= 32) {  // straight-line: the history shift is pure register renaming
+            // all loads first (shared-memory latency is paid once per half block, not per quad)
+            constexpr int kHalf = ORD > 12 ? 4 : 8;
 #pragma unroll
-            for (int q = 0; q < 8; ++q)
-                if (4 * q < left) {
-                    float4 *p = row + (inc > 0 ? q : 7 - q);
-                    *p = tns_quad<ORD, AR>(*p, inc, h, c, nan_from, 32 * b + 4 * q);
-                }
+            for (int q0 = 0; q0 < 8; q0 += kHalf) {
+                float4 v[kHalf];
+#pragma unroll
+                for (int q = 0; q < kHalf; ++q) v[q] = row[inc > 0 ? q0 + q : 7 - q0 - q];
+#pragma unroll
+                for (int q = 0; q < kHalf; ++q) v[q] = tns_quad<ORD, AR>(v[q], inc, h, c, nan_from, 32 * b + 4 * (q0 + q));
+#pragma unroll
+                for (int q = 0; q < kHalf; ++q) row[inc > 0 ? q0 + q : 7 - q0 - q] = v[q];
+            }
+        } else if (left > 0) {
+            for (int q = 0; 4 * q < left; ++q) {
+                float4 *p = row + (inc > 0 ? q : 7 - q);
+                *p = tns_quad<ORD, AR>(*p, inc, h, c, nan_from, 32 * b + 4 * q);
+            }
         }
         __syncwarp();
+        if (b < nv_min) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k)
-            if (quad_ok(k, b)) {
-                const int r = (lane >> 3) + 4 * k;
-                const int off = g_off[k] + (g_sz[k] > 0 ? 32 * b : -32 * b);
-                *reinterpret_cast<float4 *>(y_base + off) = *reinterpret_cast<const float4 *>(tile + r * kTnsPitch + 4 * cc);
-            }
+            for (int k = 0; k < 8; ++k)
+                *reinterpret_cast<float4 *>(y_base + g_off[k]) =
+                    *reinterpret_cast<const float4 *>(tile_rd + slot * kTnsTileFloats + 4 * k * kTnsPitch);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                if (b < g_nv[k])
+                    *reinterpret_cast<float4 *>(y_base + g_off[k]) =
+                        *reinterpret_cast<const float4 *>(tile_rd + slot * kTnsTileFloats + 4 * k * kTnsPitch);
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) g_off[k] += g_step[k];
         slot = slot + 1 == kTnsRing ? 0 : slot + 1;
     }
     cp_async_wait0();
@@ -402,47 +439,67 @@ __global__ void __launch_bounds__(kTnsWarps * 32, 4) tns_kernel(const __grid_con
     extern __shared__ __align__(128) uint8_t smem[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     float *ring = reinterpret_cast<float *>(smem) + wid * kTnsRing * kTnsTileFloats;
+    // scalefactor-band tables of this sample rate -> shared memory (tables.js:34-163, tns.js:65)
+    uint16_t *bands = reinterpret_cast<uint16_t *>(smem + kTnsSmemRing);  // [0,52) long, [52,68) short, [68..70] counts
+    {
+        const int si = P.sample_index, t = threadIdx.x;
+        if (t < 52) bands[t] = P.bands->swb_long[si][t];
+        else if (t < 68) bands[t] = P.bands->swb_short[si][t - 52];
+        else if (t == 68) bands[68] = P.bands->swb_long_count[si];
+        else if (t == 69) bands[69] = P.bands->swb_short_count[si];
+        else if (t == 70) bands[70] = P.bands->tns_max_bands[si];
+    }
     const size_t cf0 = ((size_t)blockIdx.x * kTnsWarps + wid) * 32;  // row 0 of this warp
-    if (cf0 >= P.n_cf) return;
     const bool in_range = cf0 + lane < P.n_cf;
-    const size_t cf = in_range ? cf0 + lane : cf0;
+    const size_t cf = in_range ? cf0 + lane : 0;
+    // side info: the loads below do not depend on each other
     uint2 raw = make_uint2(0u, 0u);
-    if (in_range) raw = __ldg(reinterpret_cast<const uint2 *>(P.info) + cf);
+    uint32_t o0 = 0, o1 = 0;
+    if (in_range) {
+        raw = __ldg(reinterpret_cast<const uint2 *>(P.info) + cf);
+        o0 = __ldg(P.offsets + cf); o1 = __ldg(P.offsets + cf + 1);
+    }
+    __syncthreads();  // band tables are in place (the only CTA-wide synchronisation)
+    if (cf0 >= P.n_cf) return;
     const bool present = in_range && (raw.y & 0xffu) != 0;
     const FrameBits fi = (FrameBits)raw.x & 0xffffff03u;
-    uint32_t o0 = 0, o1 = 0;
-    if (present) { o0 = P.offsets[cf]; o1 = P.offsets[cf + 1]; }
-    const bool has_block = present && o1 > o0 && o1 <= P.blob_bytes;
-    const uint8_t *block = P.blob + (has_block ? o0 : 0);
+    const bool has_block = present && o1 > o0 && o1 <= P.blob_bytes && (o0 & 3u) == 0;
     const uint32_t block_bytes = has_block ? o1 - o0 : 0;
+    // The blocks of consecutive channel-frames are contiguous in the blob: the warp copies the
+    // whole region [rlo, rhi) into its (idle) tile ring with coalesced loads and parses it there.
+    uint32_t rlo = has_block ? o0 : 0xffffffffu, rhi = has_block ? o1 : 0u;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        rlo = min(rlo, __shfl_xor_sync(0xffffffffu, rlo, o));
+        rhi = max(rhi, __shfl_xor_sync(0xffffffffu, rhi, o));
+    }
+    const bool staged = rhi > rlo && rhi - rlo <= (uint32_t)(kTnsRing * kTnsTileFloats * 4);
+    auto stage_blob = [&]() {
+        if (!staged) return;
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(P.blob + rlo);
+        uint32_t *dst = reinterpret_cast<uint32_t *>(ring);
+        const uint32_t words = (rhi - rlo + 3u) >> 2;
+#pragma unroll 4
+        for (uint32_t i = lane; i < words; i += 32) dst[i] = __ldg(src + i);
+        __syncwarp();
+    };
+    const uint8_t *block = staged ? reinterpret_cast<const uint8_t *>(ring) + (has_block ? o0 - rlo : 0)
+                                  : P.blob + (has_block ? o0 : 0);
 
-    // pass 1: which float4s of the row do the runs cover, and their bounding interval
+    // One walk over the filters: each run slot of the warp is filtered as it is found; on the
+    // way every lane records which float4s of its row the runs cover and their bounding interval.
     uint32_t covered[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) covered[i] = 0u;
     int lo4 = 256, hi4 = 0;
-    if (has_block) {
-        TnsWalker wk(fi, block, block_bytes, P.sample_index, *P.bands);
-        for (TnsFilter ft = wk.next(); ft.valid; ft = wk.next()) {
-            if (!ft.active) continue;
-            const int lo = ft.inc > 0 ? ft.start : ft.start - ft.size + 1;
-            const int a = lo >> 2, b = (lo + ft.size) >> 2;
-            lo4 = min(lo4, a); hi4 = max(hi4, b);
-#pragma unroll
-            for (int g = 0; g < 8; ++g) {  // bits [a, b) of the 256-bit map
-                const int s = max(a - 32 * g, 0), e = min(b - 32 * g, 32);
-                if (e > s) covered[g] |= (e - s == 32 ? 0xffffffffu : ((1u << (e - s)) - 1u) << s);
-            }
-        }
-    }
-    if (hi4 <= lo4) lo4 = hi4 = 0;
-    if (in_range) P.ranges[cf] = (uint32_t)lo4 | ((uint32_t)hi4 << 16);
-
-    // pass 2: the runs, one run slot of the warp at a time
     {
-        TnsWalker wk(fi, block, block_bytes, P.sample_index, *P.bands);
+        stage_blob();
+        TnsWalker wk(fi, block, block_bytes, bands, bands[68], bands + 52, bands[69], bands[70]);
         bool more = has_block;
-        for (;;) {
+        const float *x0 = P.spectra + cf0 * 1024;
+        float *y0 = P.scratch + cf0 * 1024;
+        for (bool first = true;; first = false) {
+            if (!first) stage_blob();  // the previous run used the ring
             TnsFilter ft;
             ft.active = false; ft.valid = false; ft.size = 0; ft.start = 0; ft.inc = 1; ft.order = 0; ft.coef = nullptr;
             while (more) {
@@ -450,11 +507,18 @@ __global__ void __launch_bounds__(kTnsWarps * 32, 4) tns_kernel(const __grid_con
                 if (!ft.valid) { more = false; ft.active = false; }
                 if (ft.active || !more) break;
             }
-            if (!__any_sync(0xffffffffu, ft.active)) break;
             float lpc[AACFB_TNS_MAX_ORDER];
             int order = 0, size = 0;
             if (ft.active) {
                 order = ft.order; size = ft.size;
+                const int lo = ft.inc > 0 ? ft.start : ft.start - ft.size + 1;
+                const int a = lo >> 2, b = (lo + ft.size) >> 2;
+                lo4 = min(lo4, a); hi4 = max(hi4, b);
+#pragma unroll
+                for (int g = 0; g < 8; ++g) {  // bits [a, b) of the 256-bit map
+                    const int s = max(a - 32 * g, 0), e = min(b - 32 * g, 32);
+                    if (e > s) covered[g] |= (e - s == 32 ? 0xffffffffu : ((1u << (e - s)) - 1u) << s);
+                }
                 for (int i = 0; i < order; ++i) {  // reflection -> direct form, tns.js:128-140
                     const float r = -ft.coef[i];
                     lpc[i] = r;
@@ -465,22 +529,32 @@ __global__ void __launch_bounds__(kTnsWarps * 32, 4) tns_kernel(const __grid_con
                     }
                 }
             }
+            if (!__any_sync(0xffffffffu, ft.active)) break;
+            __syncwarp();  // every lane has parsed its block: the ring may be reused
             int ord_max = order;
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) ord_max = max(ord_max, __shfl_xor_sync(0xffffffffu, ord_max, o));
-            const float *x0 = P.spectra + cf0 * 1024;
-            float *y0 = P.scratch + cf0 * 1024;
             if (P.ar) tns_tile_dispatch<true>(ord_max, ring, lane, x0, y0, ft.start, size, ft.inc, lpc, order);
             else tns_tile_dispatch<false>(ord_max, ring, lane, x0, y0, ft.start, size, ft.inc, lpc, order);
         }
     }
+    if (hi4 <= lo4) lo4 = hi4 = 0;
+    if (in_range) P.ranges[cf] = (uint32_t)lo4 | ((uint32_t)hi4 << 16);
 
-    // pass 3: coefficients inside the interval that no run covers are copied (whole lines, row by row)
+    // Coefficients inside the interval that no run covers are copied (whole lines, row by row;
+    // only rows that have such gaps are visited).
+    bool gaps = false;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+        const int s = max(lo4 - 32 * g, 0), e = min(hi4 - 32 * g, 32);
+        const uint32_t inside = e > s ? (e - s == 32 ? 0xffffffffu : ((1u << (e - s)) - 1u) << s) : 0u;
+        gaps |= (inside & ~covered[g]) != 0u;
+    }
     const float4 *x4 = reinterpret_cast<const float4 *>(P.spectra);
     float4 *y4 = reinterpret_cast<float4 *>(P.scratch);
-    for (int r = 0; r < 32; ++r) {
+    for (uint32_t todo = __ballot_sync(0xffffffffu, gaps); todo; todo &= todo - 1) {
+        const int r = __ffs(todo) - 1;
         const int lo_r = __shfl_sync(0xffffffffu, lo4, r), hi_r = __shfl_sync(0xffffffffu, hi4, r);
-        if (hi_r <= lo_r) continue;
         const size_t cf_r = cf0 + r;
 #pragma unroll
         for (int g = 0; g < 8; ++g) {
