@@ -414,12 +414,34 @@ AACFB_HD void exs_read(int u, float2 *const *buf, Pts &z) {
             z.r[c][q] = t.x; z.i[c][q] = t.y;
         }
 }
-// Post-twiddle and reorder of the 8 short IMDCTs of ONE chain into
-// buf[256w + i] (filter_bank.js:144-146 -> mdct.js:82-114 with N = 256).
+// ---- EIGHT_SHORT window + overlap-add through two product arrays ----------------------
+// filter_bank.js:148-176 adds, at position t = 128j + i of the 1152-sample short-window
+// sequence (j = 0..8, i = 0..127),
+//     Z[t] = y_{j-1}[128 + i] * W[127 - i]  +  y_j[i] * W'[i]
+// (y_w = the 256 IMDCT outputs of window w, y_{-1} = y_8 = 0, W = short window of shape_cur,
+// W' = shape_prev's for j = 0), with  out[n] = overlap[n] + Z[n - 448]  for n >= 448  and
+// overlap'[n] = Z[n + 576]  for n < 576, 0 above.  The thread that holds bin k of window w after
+// the FFT owns exactly four IMDCT outputs of that window (mdct.js:90-114 writes every post-twiddled
+// value at two mirrored positions), so it multiplies them by their window values right away and
+// stores the PRODUCTS:
+//     P1[128w + i]  = y_w[i]       * W'[i]          (first halves)
+//     P2[128w + i]  = y_w[128 + i] * W[127 - i]     (second halves, i.e. Z's first term at t = 128(w+1) + i)
+// 2 x 1024 floats = one 8 KiB staging buffer per chain.  The consumer then needs two loads per
+// Z value instead of four loads, two multiplies and the window-sequence branching.
+// Index swizzle (both arrays): flipping bit 0 with bit 5 makes the consumers' stride-2 reads
+// (threads own positions 2u + const) conflict-free; flipping bit 4 with bit 7 spreads the four
+// windows a warp's producers write at once over both halves of the banks.
+AACFB_HD int short_swz(int t) { return t ^ ((t >> 5) & 1) ^ (((t >> 7) & 1) << 4); }
+
+// Producer: thread u = 8w + g, bins k = 8q + g of window w.  `wshort` carries the output scale
+// (a power of two, see win_first), so the products are in output units like the overlap registers.
 template <int C>
-AACFB_HD void short_scatter(int u, const Pts &z, const float2 *cs256, float *buf) {
+AACFB_HD void short_products(int u, const Pts &z, const float2 *cs256, const float (*wshort)[128], FrameBits fi,
+                             float *buf) {
     const int w = u >> 3, g = u & 7;
-    float *y = buf + 256 * w;
+    const float *wcur = wshort[fb_shape_cur(fi)];
+    const float *wfirst = w == 0 ? wshort[fb_shape_prev(fi)] : wcur;  // filter_bank.js:153 vs :157-160
+    float *p1 = buf, *p2 = buf + 1024;
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
         const int k = 8 * q + g;
@@ -427,45 +449,59 @@ AACFB_HD void short_scatter(int u, const Pts &z, const float2 *cs256, float *buf
         const float re = z.r[C][q], im = z.i[C][q];
         const float pr = f_fma(re, cs.x, -f_mul(im, cs.y));
         const float pi = f_fma(im, cs.x, f_mul(re, cs.y));
-        if (q < 4) {  // k < 32
-            y[(64 + 2 * k)] = pr;  y[(63 - 2 * k)] = -pr;
-            y[(192 + 2 * k)] = -pi; y[(191 - 2 * k)] = -pi;
-        } else {
-            y[2 * (k - 32)] = pi; y[(191 - 2 * k)] = -pi;
-            y[(128 + 2 * (k - 32))] = pr; y[(319 - 2 * k)] = pr;
+        // the two positions (one even, one odd) of this bin in either half of the window
+        const int pa = q < 4 ? 64 + 2 * k : 2 * (k - 32);
+        const int pb = q < 4 ? 63 - 2 * k : 191 - 2 * k;
+        const float wa = wcur[pa], wb = wcur[pb];
+        const float fa = wfirst[pa], fb = wfirst[pb];
+        const int ia = short_swz(128 * w + pa), ib = short_swz(128 * w + pb);
+        if (q < 4) {  // k < 32: y[64+2k] = pr, y[63-2k] = -pr, y[192+2k] = y[191-2k] = -pi
+            p1[ia] = f_mul(pr, fa);
+            p1[ib] = f_mul(-pr, fb);
+            p2[ia] = f_mul(-pi, wb);   // second-half index i = pa uses W[127 - pa] = W[pb]
+            p2[ib] = f_mul(-pi, wa);
+        } else {      // k >= 32: y[2(k-32)] = pi, y[191-2k] = -pi, y[128+2(k-32)] = y[319-2k] = pr
+            p1[ia] = f_mul(pi, fa);
+            p1[ib] = f_mul(-pi, fb);
+            p2[ia] = f_mul(pr, wb);
+            p2[ib] = f_mul(pr, wa);
         }
     }
 }
-// filter_bank.js:148-161: output sample n of an EIGHT_SHORT frame.
-AACFB_HD float short_first(int n, const float *buf, float ov, const float *wprev, const float *wcur) {
-    if (n < 448) return ov;
-    const int t = n - 448, j = t >> 7, i = t & 127;
-    if (j == 0) return f_fma(buf[i], wprev[i], ov);
-    return f_fma(buf[256 * j + i], wcur[i], f_fma(buf[256 * j - 128 + i], wcur[127 - i], ov));
+
+// Consumer for output position n (range [LO, HI] known at compile time): returns the sample
+// out[n] (if EMIT) and replaces the overlap.  Loads that cannot apply to the range fold away.
+template <int LO, int HI>
+AACFB_HD void short_ola(int n, const float *buf, bool emit, float &ovl, float &out) {
+    const float *p1 = buf, *p2 = buf + 1024;
+    // out[n] = (overlap + y_{j-1} term) + y_j term, t = n - 448   (filter_bank.js:153-161)
+    float o = ovl;
+    if (HI >= 576) { const bool on = LO >= 576 || n >= 576; const float v = on ? p2[short_swz(on ? n - 576 : 0)] : 0.f; o = f_add(o, v); }
+    if (HI >= 448) { const bool on = LO >= 448 || n >= 448; const float v = on ? p1[short_swz(on ? n - 448 : 0)] : 0.f; o = f_add(o, v); }
+    if (emit) out = o;
+    // overlap'[n] = y_{j-1} term + y_j term, t = n + 576             (filter_bank.js:164-176)
+    float nv = 0.f;
+    if (LO < 576) { const bool on = HI < 576 || n < 576; nv = on ? p2[short_swz(on ? n + 448 : 0)] : 0.f; }
+    if (LO < 448) { const bool on = HI < 448 || n < 448; const float v = on ? p1[short_swz(on ? n + 576 : 0)] : 0.f; nv = f_add(nv, v); }
+    ovl = nv;
 }
-// filter_bank.js:164-176: overlap sample n saved by an EIGHT_SHORT frame.
-AACFB_HD float short_second(int n, const float *buf, const float *wcur) {
-    if (n >= 576) return 0.f;
-    if (n >= 448) { const int i = n - 448; return f_mul(buf[1920 + i], wcur[127 - i]); }
-    const int t = n + 576, j = t >> 7, i = t & 127;
-    return f_fma(buf[256 * j + i], wcur[i], f_mul(buf[256 * j - 128 + i], wcur[127 - i]));
-}
-// Window + overlap-add of ONE chain of an EIGHT_SHORT frame from buf[2048].
+// Window + overlap-add of ONE chain of an EIGHT_SHORT frame from its product arrays.
 template <int C>
-// The overlap registers are kept in output-scaled units (see win_first); this path unscales and
-// rescales them (exact: powers of two).
-AACFB_HD void short_finish(int u, const float *buf, Ovl &ov, FrameBits fi,
-                           const float (*wshort)[128], bool emit, float scale, float inv_scale, Out &o) {
-    const float *wprev = wshort[fb_shape_prev(fi)], *wcur = wshort[fb_shape_cur(fi)];
+AACFB_HD void short_finish(int u, const float *buf, Ovl &ov, bool emit, Out &o) {
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
+        // m = long_pos_of_bin(64q + u): 512 + 128q + 2u (q < 4), 128(q - 4) + 2u (q >= 4); mirror 1023 - m
         const int m = long_pos_of_bin(64 * q + u), mm = 1023 - m;
-        if (emit) {
-            o.a[C][q] = f_mul(short_first(m, buf, f_mul(ov.a[C][q], inv_scale), wprev, wcur), scale);
-            o.b[C][q] = f_mul(short_first(mm, buf, f_mul(ov.b[C][q], inv_scale), wprev, wcur), scale);
+        switch (q) {  // compile-time ranges of m and 1023 - m (u = 0..63)
+        case 0: short_ola<512, 638>(m, buf, emit, ov.a[C][0], o.a[C][0]); short_ola<385, 511>(mm, buf, emit, ov.b[C][0], o.b[C][0]); break;
+        case 1: short_ola<640, 766>(m, buf, emit, ov.a[C][1], o.a[C][1]); short_ola<257, 383>(mm, buf, emit, ov.b[C][1], o.b[C][1]); break;
+        case 2: short_ola<768, 894>(m, buf, emit, ov.a[C][2], o.a[C][2]); short_ola<129, 255>(mm, buf, emit, ov.b[C][2], o.b[C][2]); break;
+        case 3: short_ola<896, 1022>(m, buf, emit, ov.a[C][3], o.a[C][3]); short_ola<1, 127>(mm, buf, emit, ov.b[C][3], o.b[C][3]); break;
+        case 4: short_ola<0, 126>(m, buf, emit, ov.a[C][4], o.a[C][4]); short_ola<897, 1023>(mm, buf, emit, ov.b[C][4], o.b[C][4]); break;
+        case 5: short_ola<128, 254>(m, buf, emit, ov.a[C][5], o.a[C][5]); short_ola<769, 895>(mm, buf, emit, ov.b[C][5], o.b[C][5]); break;
+        case 6: short_ola<256, 382>(m, buf, emit, ov.a[C][6], o.a[C][6]); short_ola<641, 767>(mm, buf, emit, ov.b[C][6], o.b[C][6]); break;
+        default: short_ola<384, 510>(m, buf, emit, ov.a[C][7], o.a[C][7]); short_ola<513, 639>(mm, buf, emit, ov.b[C][7], o.b[C][7]); break;
         }
-        ov.a[C][q] = f_mul(short_second(m, buf, wcur), scale);
-        ov.b[C][q] = f_mul(short_second(mm, buf, wcur), scale);
     }
 }
 

@@ -47,6 +47,8 @@ extern "C" __attribute__((visibility("default"))) int aacfb_emul_process(
     scaled = H.synth;
     for (int sh = 0; sh < 2; ++sh)
         for (int k = 0; k < 512; ++k) { scaled.wz[sh][k].x *= kScale; scaled.wz[sh][k].y *= kScale; }
+    for (int sh = 0; sh < 2; ++sh)
+        for (int i = 0; i < 128; ++i) scaled.wshort[sh][i] *= kScale;
     const SynthTables *tab = &scaled;
     const TnsBandTables &bt = tns_band_tables();
     const uint32_t mode = flags & AACFB_TNS_MODE_MASK;

@@ -144,9 +144,11 @@ __global__ void __launch_bounds__(W * 64, 1) synth_kernel(const __grid_constant_
         float4 *dst = reinterpret_cast<float4 *>(smem);
         for (int i = tid; i < kSmemTableBytes / 16; i += kCtaThreads) dst[i] = src[i];
         __syncthreads();
-        // the long windows carry the output scale (a power of two; see win_first in aacfb_core.cuh)
+        // the windows carry the output scale (a power of two; see win_first in aacfb_core.cuh)
         float *wz = reinterpret_cast<float *>(smem + offsetof(SynthTables, wz));
         for (int i = tid; i < 2 * 512 * 2; i += kCtaThreads) wz[i] *= P.scale;
+        float *ws = reinterpret_cast<float *>(smem + offsetof(SynthTables, wshort));
+        for (int i = tid; i < 2 * 128; i += kCtaThreads) ws[i] *= P.scale;
     }
     const SynthTables *ts = reinterpret_cast<const SynthTables *>(smem);
     float *stages = reinterpret_cast<float *>(smem + kOffStages) + (size_t)w * kBufsPerWorker * kStageFloats;

@@ -5,7 +5,7 @@
 // has been consumed into registers the same 4 KiB serve as that chain's FFT
 // second exchange buffer (the first exchange goes through a per-worker scratch
 // buffer); for EIGHT_SHORT frames stage and scratch serve as the 2048-sample
-// IMDCT buffers `buf` of filter_bank.js:43.  Finished PCM never touches
+// window-product arrays of short_products (the windowed halves of `buf`, filter_bank.js:43).  Finished PCM never touches
 // shared memory: it is paired up by a warp shuffle and stored directly.
 //
 // `Sync` provides what the schedule needs from the outside:
@@ -98,21 +98,21 @@ AACFB_HD void frame_with_short(int u, Sync &sync, const FrameIO &io, const Synth
     const bool s1 = io.nch == 2 && is_short(io.fi[1]);
     if (io.nch == 2 && s0 && s1) {
         short_fft<0, 2>(u, sync, io, ts, z);
-        short_scatter<0>(u, z, ts->cs256, io.stage);        // rows are dead since the exchange barrier
+        short_products<0>(u, z, ts->cs256, ts->wshort, io.fi[0], io.stage);    // rows are dead since the exchange barrier
         sync.barrier();
-        short_finish<0>(u, io.stage, ov, io.fi[0], ts->wshort, d.emit, d.scale, d.inv_scale, o);
-        short_scatter<1>(u, z, ts->cs256, io.scratch);      // exchange data dead since the last barrier
+        short_finish<0>(u, io.stage, ov, d.emit, o);
+        short_products<1>(u, z, ts->cs256, ts->wshort, io.fi[1], io.scratch);  // exchange data dead since the last barrier
         sync.barrier();
         sync.stage_free();                                   // chain 0's IMDCT buffer has been consumed
-        short_finish<1>(u, io.scratch, ov, io.fi[1], ts->wshort, d.emit, d.scale, d.inv_scale, o);
+        short_finish<1>(u, io.scratch, ov, d.emit, o);
         if (d.emit) out_store<0, 2>(u, sync, o, d);
         return;
     }
     if (io.nch == 1) {
         short_fft<0, 1>(u, sync, io, ts, z);
-        short_scatter<0>(u, z, ts->cs256, io.stage);
+        short_products<0>(u, z, ts->cs256, ts->wshort, io.fi[0], io.stage);
         sync.barrier();
-        short_finish<0>(u, io.stage, ov, io.fi[0], ts->wshort, d.emit, d.scale, d.inv_scale, o);
+        short_finish<0>(u, io.stage, ov, d.emit, o);
         sync.stage_free();
         if (d.emit) out_store<0, 1>(u, sync, o, d);
         return;
@@ -121,16 +121,16 @@ AACFB_HD void frame_with_short(int u, Sync &sync, const FrameIO &io, const Synth
         long_fft<1, 1>(u, sync, io, ts, z);
         long_finish<1, 1, false, false>(u, sync, z, ov, ts, tg, io.fi, d, o);
         short_fft<0, 1>(u, sync, io, ts, z);
-        short_scatter<0>(u, z, ts->cs256, io.stage);
+        short_products<0>(u, z, ts->cs256, ts->wshort, io.fi[0], io.stage);
         sync.barrier();
-        short_finish<0>(u, io.stage, ov, io.fi[0], ts->wshort, d.emit, d.scale, d.inv_scale, o);
+        short_finish<0>(u, io.stage, ov, d.emit, o);
     } else {
         long_fft<0, 1>(u, sync, io, ts, z);
         long_finish<0, 1, false, false>(u, sync, z, ov, ts, tg, io.fi, d, o);
         short_fft<1, 1>(u, sync, io, ts, z);
-        short_scatter<1>(u, z, ts->cs256, io.stage);
+        short_products<1>(u, z, ts->cs256, ts->wshort, io.fi[1], io.stage);
         sync.barrier();
-        short_finish<1>(u, io.stage, ov, io.fi[1], ts->wshort, d.emit, d.scale, d.inv_scale, o);
+        short_finish<1>(u, io.stage, ov, d.emit, o);
     }
     sync.stage_free();
     if (d.emit) out_store<0, 2>(u, sync, o, d);
