@@ -44,7 +44,8 @@ struct aacfb_ctx {
     uint32_t flags = 0;
     float *d_ovl[2] = {nullptr, nullptr};
     int cur = 0;
-    SynthTables *d_tab = nullptr;
+    SynthTables *d_tab = nullptr;       // windows carry the 2^-15 output scale (decoder.js:210)
+    SynthTables *d_tab_unit = nullptr;  // unscaled windows, for the inner seam (FilterBank.process output)
     TnsBandTables *d_bands = nullptr;
     unsigned *d_counters = nullptr;
     unsigned counter_next = 0;
@@ -125,7 +126,7 @@ int enqueue(aacfb_ctx *ctx, const float *d_spectra, const aacfb_frame_info *d_in
     sp.spectra = d_spectra; sp.scratch = tns_on ? d_scratch : nullptr; sp.ranges = d_ranges; sp.info = d_info; sp.pcm = d_pcm;
     sp.ovl_in = ctx->d_ovl[ctx->cur];
     sp.ovl_out = in_place_state ? ctx->d_ovl[ctx->cur] : ctx->d_ovl[ctx->cur ^ 1];
-    sp.tab = ctx->d_tab;
+    sp.tab = scale == 1.0f ? ctx->d_tab_unit : ctx->d_tab;
     const int n_pairs = (S_sub * nc + 1) / 2;
     if ((long long)S_sub * T * nc >= (1ll << 30)) return fail(ctx, AACFB_ERR_ARG, "batch too large: split it (channel-frames < 2^30)");
     // in-place state (inner seam): one item, so the state is read before it is written
@@ -261,9 +262,18 @@ API int aacfb_create(aacfb_ctx **out, int device, int n_streams, int channels, i
         if ((e = cudaMalloc(&ctx->d_ovl[i], ovl_bytes)) != cudaSuccess) return bail(e, "cudaMalloc overlap");
         if ((e = cudaMemset(ctx->d_ovl[i], 0, ovl_bytes)) != cudaSuccess) return bail(e, "cudaMemset overlap");
     }
-    if ((e = cudaMalloc(&ctx->d_tab, sizeof(SynthTables))) != cudaSuccess) return bail(e, "cudaMalloc tables");
-    if ((e = cudaMemcpy(ctx->d_tab, &host_tables().synth, sizeof(SynthTables), cudaMemcpyHostToDevice)) != cudaSuccess)
-        return bail(e, "cudaMemcpy tables");
+    {
+        SynthTables *scaled = new (std::nothrow) SynthTables(host_tables().synth);
+        if (!scaled) { aacfb_destroy(ctx); return fail(nullptr, AACFB_ERR_NOMEM, "out of memory"); }
+        scale_windows(*scaled, 1.0f / 32768.0f);
+        e = cudaMalloc(&ctx->d_tab, sizeof(SynthTables));
+        if (e == cudaSuccess) e = cudaMemcpy(ctx->d_tab, scaled, sizeof(SynthTables), cudaMemcpyHostToDevice);
+        delete scaled;
+        if (e != cudaSuccess) return bail(e, "device tables");
+        if ((e = cudaMalloc(&ctx->d_tab_unit, sizeof(SynthTables))) != cudaSuccess) return bail(e, "cudaMalloc tables");
+        if ((e = cudaMemcpy(ctx->d_tab_unit, &host_tables().synth, sizeof(SynthTables), cudaMemcpyHostToDevice)) != cudaSuccess)
+            return bail(e, "cudaMemcpy tables");
+    }
     if ((e = cudaMalloc(&ctx->d_bands, sizeof(TnsBandTables))) != cudaSuccess) return bail(e, "cudaMalloc bands");
     if ((e = cudaMemcpy(ctx->d_bands, &tns_band_tables(), sizeof(TnsBandTables), cudaMemcpyHostToDevice)) != cudaSuccess)
         return bail(e, "cudaMemcpy bands");
@@ -284,7 +294,7 @@ API int aacfb_destroy(aacfb_ctx *ctx) {
         if (ln.stream) cudaStreamDestroy(ln.stream);
         cudaFree(ln.d_spectra); cudaFree(ln.d_pcm); cudaFree(ln.d_scratch); cudaFree(ln.d_info); cudaFree(ln.d_offsets);
     }
-    cudaFree(ctx->d_ovl[0]); cudaFree(ctx->d_ovl[1]); cudaFree(ctx->d_tab); cudaFree(ctx->d_bands);
+    cudaFree(ctx->d_ovl[0]); cudaFree(ctx->d_ovl[1]); cudaFree(ctx->d_tab); cudaFree(ctx->d_tab_unit); cudaFree(ctx->d_bands);
     cudaFree(ctx->d_counters); cudaFree(ctx->d_blob); cudaFree(ctx->d_dev_scratch);
     delete ctx;
     return AACFB_OK;

@@ -232,26 +232,19 @@ struct OutDst {
 //                LONG_STOP            -> 0 | short asc | 1            (filter_bank.js:184-194)
 //   second half: ONLY_LONG/LONG_STOP  -> reversed long window of shape_cur (filter_bank.js:114-116,198-200)
 //                LONG_START           -> 1 | short desc | 0           (filter_bank.js:129-139)
-// `wz` (the worker's shared-memory copy) already carries the output scale: multiplying a window
-// by a power of two commutes with every rounding downstream, so (ov + F*W) * 2^-15 of
-// decoder.js:210 becomes ov' + F*(W*2^-15) with the overlap kept in scaled units -- bit-identical,
-// two multiplies per bin cheaper.  The window-switching tables in global memory are unscaled.
-AACFB_HD float2 win_first(FrameBits fi, int k, const float2 (*wz)[512], const SynthTables *g, float scale) {
-    if (fb_seq(fi) != AACFB_LONG_STOP_SEQUENCE) return wz[fb_shape_prev(fi)][k];
-    float2 w = g->fwz_stop[fb_shape_prev(fi)][k];
-    w.x = f_mul(w.x, scale); w.y = f_mul(w.y, scale);
+// All four live in tables of the same layout, so a frame only picks two table pointers per
+// chain and the arithmetic is the same for every sequence.  `wz` is the worker's shared-memory
+// copy of the long windows, `g` the full table set in global memory (window switching is rare);
+// both carry the output scale already (scale_windows, aacfb_tables.h).  A second-half entry w
+// is used as (w.y, w.x).
+struct LongWin {
+    const float2 *first, *second;
+};
+AACFB_HD LongWin long_windows(FrameBits fi, const float2 (*wz)[512], const SynthTables *g) {
+    LongWin w;
+    w.first = fb_seq(fi) == AACFB_LONG_STOP_SEQUENCE ? g->fwz_stop[fb_shape_prev(fi)] : wz[fb_shape_prev(fi)];
+    w.second = fb_seq(fi) == AACFB_LONG_START_SEQUENCE ? g->swz_start[fb_shape_cur(fi)] : wz[fb_shape_cur(fi)];
     return w;
-}
-AACFB_HD float2 win_second(FrameBits fi, int k, const float2 (*wz)[512], const SynthTables *g, float scale) {
-    float2 r;
-    if (fb_seq(fi) == AACFB_LONG_START_SEQUENCE) {
-        const float2 w = g->swz_start[fb_shape_cur(fi)][k];
-        r.x = f_mul(w.x, scale); r.y = f_mul(w.y, scale);
-        return r;
-    }
-    const float2 w = wz[fb_shape_cur(fi)][k];
-    r.x = w.y; r.y = w.x;
-    return r;
 }
 
 // ------------------------------------------------------------- PCM write-out
@@ -316,7 +309,7 @@ AACFB_HD void out_store(int u, Sync &sync, const Out &o, const OutDst &d) {
 
 // Post-twiddle (mdct.js:82-87), reorder (mdct.js:90-114), window and
 // overlap-add (filter_bank.js:105-141,180-202); the scale of decoder.js:210
-// rides in the window table (see win_first).  Thread u owns bins k = 64q+u, i.e. output positions m and 1023-m with
+// rides in the window tables (scale_windows).  Thread u owns bins k = 64q+u, i.e. output positions m and 1023-m with
 // m = long_pos_of_bin(k); the same thread owned them in every earlier frame,
 // so the overlap lives in registers.
 //   UNIFORM  : all chains are ONLY_LONG with the same shapes (the common case):
@@ -325,6 +318,9 @@ AACFB_HD void out_store(int u, Sync &sync, const Out &o, const OutDst &d) {
 template <int C0, int NCH, bool UNIFORM, bool TO_GLOBAL, class Sync>
 AACFB_HD void long_finish(int u, Sync &sync, const Pts &z, Ovl &ov, const SynthTables *ts, const SynthTables *tg,
                           const FrameBits *fi, const OutDst &d, Out &o) {
+    LongWin win[2];
+#pragma unroll
+    for (int c = C0; c < C0 + NCH; ++c) win[c] = long_windows(fi[UNIFORM ? C0 : c], ts->wz, tg);
 #pragma unroll
     for (int qq = 0; qq < 4; ++qq) {
         float a[2][2], b[2][2];
@@ -336,8 +332,7 @@ AACFB_HD void long_finish(int u, Sync &sync, const Pts &z, Ovl &ov, const SynthT
             float2 wf_u, ws_u;
             if (UNIFORM) {
                 wf_u = ts->wz[fb_shape_prev(fi[C0])][k];
-                const float2 wc = fb_shape_prev(fi[C0]) == fb_shape_cur(fi[C0]) ? wf_u : ts->wz[fb_shape_cur(fi[C0])][k];
-                ws_u.x = wc.y; ws_u.y = wc.x;
+                ws_u = fb_shape_prev(fi[C0]) == fb_shape_cur(fi[C0]) ? wf_u : ts->wz[fb_shape_cur(fi[C0])][k];
             }
 #pragma unroll
             for (int c = C0; c < C0 + NCH; ++c) {
@@ -348,13 +343,13 @@ AACFB_HD void long_finish(int u, Sync &sync, const Pts &z, Ovl &ov, const SynthT
                 const float F = (q < 4) ? pr : pi;
                 const float S = (q < 4) ? -pi : pr;
                 if (d.emit) {
-                    const float2 wf = UNIFORM ? wf_u : win_first(fi[c], k, ts->wz, tg, d.scale);
+                    const float2 wf = UNIFORM ? wf_u : win[c].first[k];
                     a[h][c] = f_fma(F, wf.x, ov.a[c][q]);
                     b[h][c] = f_fma(-F, wf.y, ov.b[c][q]);
                 }
-                const float2 ws = UNIFORM ? ws_u : win_second(fi[c], k, ts->wz, tg, d.scale);
-                ov.a[c][q] = f_mul(S, ws.x);
-                ov.b[c][q] = f_mul(S, ws.y);
+                const float2 ws = UNIFORM ? ws_u : win[c].second[k];
+                ov.a[c][q] = f_mul(S, ws.y);
+                ov.b[c][q] = f_mul(S, ws.x);
             }
         }
         if (d.emit) {
@@ -434,7 +429,7 @@ AACFB_HD void exs_read(int u, float2 *const *buf, Pts &z) {
 AACFB_HD int short_swz(int t) { return t ^ ((t >> 5) & 1) ^ (((t >> 7) & 1) << 4); }
 
 // Producer: thread u = 8w + g, bins k = 8q + g of window w.  `wshort` carries the output scale
-// (a power of two, see win_first), so the products are in output units like the overlap registers.
+// (scale_windows), so the products are in output units like the overlap registers.
 template <int C>
 AACFB_HD void short_products(int u, const Pts &z, const float2 *cs256, const float (*wshort)[128], FrameBits fi,
                              float *buf) {

@@ -42,13 +42,10 @@ extern "C" __attribute__((visibility("default"))) int aacfb_emul_process(
     int chunk_len) {
     const HostTables &H = host_tables();
     const float kScale = 1.0f / 32768.0f;
-    // the worker's shared-memory copy of the tables: long windows carry the output scale
+    // the kernel's tables: every window carries the output scale (scale_windows)
     static SynthTables scaled;
     scaled = H.synth;
-    for (int sh = 0; sh < 2; ++sh)
-        for (int k = 0; k < 512; ++k) { scaled.wz[sh][k].x *= kScale; scaled.wz[sh][k].y *= kScale; }
-    for (int sh = 0; sh < 2; ++sh)
-        for (int i = 0; i < 128; ++i) scaled.wshort[sh][i] *= kScale;
+    scale_windows(scaled, kScale);
     const SynthTables *tab = &scaled;
     const TnsBandTables &bt = tns_band_tables();
     const uint32_t mode = flags & AACFB_TNS_MODE_MASK;
@@ -118,8 +115,8 @@ extern "C" __attribute__((visibility("default"))) int aacfb_emul_process(
                 for (int c = 0; c < 2; ++c) io.fi[c] = fb_pack(info[cf_index(g, pr.s[c], t, pr.j[c])]);
                 io.dst.out0 = pcm + ((size_t)pr.s[0] * g.T + t) * 1024 * g.nc + pr.j[0];
                 io.dst.out1 = pcm + ((size_t)pr.s[1] * g.T + t) * 1024 * g.nc + pr.j[1];
-                if (item_has_short) worker_frame<true>(u, sync, io, tab, &H.synth, z, ov);
-                else worker_frame<false>(u, sync, io, tab, &H.synth, z, ov);
+                if (item_has_short) worker_frame<true>(u, sync, io, tab, tab, z, ov);
+                else worker_frame<false>(u, sync, io, tab, tab, z, ov);
                 if (t == g.T - 1) {
                     // NOTE: in place -- safe here because items run one after the other, in order
                     ovl_store<0>(u, ov, overlap + state_index(g, pr.s[0], pr.j[0]), 1.0f / kScale);

@@ -36,7 +36,8 @@ struct Layout {
     static constexpr int kOffStages = kTabBytes;
     static constexpr int kOffBars = kOffStages + W * kBufsPerWorker * kStageBytes;
     static constexpr int kOffSlots = kOffBars + W * ST * 8;
-    static constexpr int kTotal = kOffSlots + W * 32;
+    static constexpr int kSlotInts = 8 + 4 * ST;   // per worker: item, flag, cursor[5], -, side-info ring [2 ST][2]
+    static constexpr int kTotal = kOffSlots + W * kSlotInts * 4;
     static_assert(kTotal <= 227 * 1024, "shared memory budget");
     static_assert(2 * W + 1 <= 16, "named barriers");
 };
@@ -101,7 +102,10 @@ struct DevSync {
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         if (leader_warp) {
             asm volatile("bar.sync %0, 64;" ::"r"(free_id) : "memory");
-            if (leader && next_valid) issue();
+            if (leader && next_valid) {
+                asm volatile("cp.async.wait_group 0;" ::: "memory");  // the prefetched side info has landed
+                issue();
+            }
         } else {
             asm volatile("bar.arrive %0, 64;" ::"r"(free_id) : "memory");
         }
@@ -143,18 +147,19 @@ __global__ void __launch_bounds__(W * 64, 1) synth_kernel(const __grid_constant_
         const float4 *src = reinterpret_cast<const float4 *>(P.tab);
         float4 *dst = reinterpret_cast<float4 *>(smem);
         for (int i = tid; i < kSmemTableBytes / 16; i += kCtaThreads) dst[i] = src[i];
-        __syncthreads();
-        // the windows carry the output scale (a power of two; see win_first in aacfb_core.cuh)
-        float *wz = reinterpret_cast<float *>(smem + offsetof(SynthTables, wz));
-        for (int i = tid; i < 2 * 512 * 2; i += kCtaThreads) wz[i] *= P.scale;
-        float *ws = reinterpret_cast<float *>(smem + offsetof(SynthTables, wshort));
-        for (int i = tid; i < 2 * 128; i += kCtaThreads) ws[i] *= P.scale;
     }
     const SynthTables *ts = reinterpret_cast<const SynthTables *>(smem);
     float *stages = reinterpret_cast<float *>(smem + kOffStages) + (size_t)w * kBufsPerWorker * kStageFloats;
     float *scratch = stages + kStages * kStageFloats;
     const uint32_t bars = smem_u32(smem + kOffBars) + w * kStages * 8;
-    volatile int *slot = reinterpret_cast<volatile int *>(smem + kOffSlots) + 8 * w;  // [0] item, [1] short flag, [2..6] prefetch cursor
+    // per worker: [0] item, [1] short flag, [2..6] prefetch cursor, [8..] side-info ring
+    volatile int *slot = reinterpret_cast<volatile int *>(smem + kOffSlots) + L::kSlotInts * w;
+    // Side info (packed aacfb_frame_info) of the frames in flight.  The leader fetches it with a
+    // 4-byte cp.async when it prefetches the frame's rows, kStages frames ahead, so no thread waits
+    // on a global load at the top of a frame; 2 kStages entries because the entry of the frame
+    // being worked on is still being read when the next prefetch is issued.
+    volatile uint32_t *fi_ring = reinterpret_cast<volatile uint32_t *>(slot + 8);
+    constexpr uint32_t kFiRing = 2 * kStages;
     if (leader) {
         for (int s = 0; s < kStages; ++s) mbar_init(bars + 8 * s, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -222,8 +227,15 @@ __global__ void __launch_bounds__(W * 64, 1) synth_kernel(const __grid_constant_
             cur[4] = pn.nch;
         };
         if (leader) cursor_to(p0, tb);
-        auto refill = [&](uint32_t st) {
+        auto refill = [&](uint32_t st, uint32_t frame_no) {
             const int tn = cur[1], ca = cur[2], cb = cur[3];
+            {
+                const uint32_t e = smem_u32(const_cast<uint32_t *>(fi_ring)) + 8u * (frame_no % kFiRing);
+                const uint32_t *inf = reinterpret_cast<const uint32_t *>(P.info);
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(e), "l"(inf + 2 * (size_t)ca) : "memory");
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(e + 4u), "l"(inf + 2 * (size_t)cb) : "memory");
+                asm volatile("cp.async.commit_group;" ::: "memory");
+            }
             sync.dst = smem_u32(stages + st * kStageFloats);
             sync.mbar = bars + 8 * st;
             sync.nrows = cur[4];
@@ -235,10 +247,12 @@ __global__ void __launch_bounds__(W * 64, 1) synth_kernel(const __grid_constant_
         };
         if (leader) {  // prologue: fill the ring
             for (int i = 0; i < kStages && i < nf; ++i) {
-                refill((fc + i) % kStages);
+                refill((fc + i) % kStages, fc + i);
                 sync.issue();
             }
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
         }
+        sync.barrier();  // the side info of the first frames is in place
 
         Pair pr = make_pair(g, p0);
         int t = tb, pi = p0;
@@ -260,12 +274,12 @@ __global__ void __launch_bounds__(W * 64, 1) synth_kernel(const __grid_constant_
             io.dst.scale = P.scale;
             io.dst.inv_scale = 1.0f / P.scale;
             io.dst.ostride = g.nc;
-            io.fi[0] = info_lo(P, cfa);
-            io.fi[1] = info_lo(P, cfb);
+            io.fi[0] = fi_ring[2 * (fc % kFiRing)];
+            io.fi[1] = fi_ring[2 * (fc % kFiRing) + 1];
             io.dst.out0 = P.pcm + oa;
             io.dst.out1 = P.pcm + ob;
             sync.next_valid = f + kStages < nf;
-            if (leader && sync.next_valid) refill(st);
+            if (leader && sync.next_valid) refill(st, fc + kStages);
             mbar_wait(bars + 8 * st, (fc / kStages) & 1u);
             worker_frame<GENERIC>(u, sync, io, ts, P.tab, z, ov);
             cfa += g.nc; cfb += g.nc;

@@ -143,7 +143,7 @@ void build(HostTables &T) {
             const int m = long_pos_of_bin(k), mm = 1023 - m;
             S.wz[sh][k] = f2(wl[sh][m], wl[sh][mm]);
             S.fwz_stop[sh][k] = f2(stop_first[m], stop_first[mm]);
-            S.swz_start[sh][k] = f2(start_second[m], start_second[mm]);
+            S.swz_start[sh][k] = f2(start_second[mm], start_second[m]);  // like wz read as a second half: (at 1023-m, at m)
         }
     }
 }
@@ -198,6 +198,17 @@ const HostTables &host_tables() {
         build(*T);
     });
     return *T;
+}
+
+void scale_windows(SynthTables &S, float scale) {
+    for (int sh = 0; sh < 2; ++sh) {
+        for (int k = 0; k < 512; ++k) {
+            S.wz[sh][k].x *= scale; S.wz[sh][k].y *= scale;
+            S.fwz_stop[sh][k].x *= scale; S.fwz_stop[sh][k].y *= scale;
+            S.swz_start[sh][k].x *= scale; S.swz_start[sh][k].y *= scale;
+        }
+        for (int i = 0; i < 128; ++i) S.wshort[sh][i] *= scale;
+    }
 }
 
 const TnsBandTables &tns_band_tables() {

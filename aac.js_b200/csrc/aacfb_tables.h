@@ -43,7 +43,8 @@ struct alignas(16) SynthTables {
     float2 roots64A[4];      // roots64[8k],  k=0..3
     // window-switching variants (global memory, read only by START/STOP frames)
     float2 fwz_stop[2][512];  // LONG_STOP first-half window:  0 | short asc | 1   (filter_bank.js:184-194)
-    float2 swz_start[2][512]; // LONG_START second-half window: 1 | short desc | 0 (filter_bank.js:129-139)
+    float2 swz_start[2][512]; // LONG_START second-half window: 1 | short desc | 0 (filter_bank.js:129-139),
+                              // stored (at 1023-m, at m) like a wz entry that is read as a second half
 };
 
 // bytes of SynthTables that the kernel stages into shared memory (everything
@@ -61,6 +62,12 @@ struct HostTables {
 };
 
 const HostTables &host_tables();   // built once, thread-safe
+
+// Multiply every window table of S by `scale` (a power of two).  The kernels work on windows
+// that carry the output scale of decoder.js:210: scaling a window by a power of two commutes
+// with every rounding downstream, so (overlap + F*W) * 2^-15 becomes overlap' + F*(W * 2^-15)
+// with the overlap kept in scaled units -- bit-identical, two multiplies per bin cheaper.
+void scale_windows(SynthTables &S, float scale);
 
 // TNS band tables (device + host share the same flat arrays)
 struct TnsBandTables {

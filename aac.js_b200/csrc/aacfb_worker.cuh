@@ -76,15 +76,18 @@ AACFB_HD void short_fft(int u, Sync &sync, const FrameIO &io, const SynthTables 
 
 // A frame whose chains are all long transforms: two blocking barriers; the PCM
 // leaves straight from the finishing arithmetic.
-template <int NCH, class Sync>
+// UNIFORM_PATH: also instantiate the specialisation for frames whose chains are all ONLY_LONG with
+// equal shapes.  The generic pass leaves it out: its code footprint (long + short paths running
+// side by side on one SM) is what the instruction cache has to hold.
+template <int NCH, bool UNIFORM_PATH, class Sync>
 AACFB_HD void frame_all_long(int u, Sync &sync, const FrameIO &io, const SynthTables *ts, const SynthTables *tg,
                              Pts &z, Ovl &ov) {
     long_fft<0, NCH>(u, sync, io, ts, z);
     sync.stage_free();  // exchange 2 has been read back: the stage may be refilled
     Out none;
-    const bool uniform = fb_seq(io.fi[0]) == AACFB_ONLY_LONG_SEQUENCE &&
+    const bool uniform = UNIFORM_PATH && fb_seq(io.fi[0]) == AACFB_ONLY_LONG_SEQUENCE &&
                          (NCH == 1 || ((io.fi[0] ^ io.fi[1]) & 0x00ffffffu) == 0);
-    if (uniform) long_finish<0, NCH, true, true>(u, sync, z, ov, ts, tg, io.fi, io.dst, none);
+    if (UNIFORM_PATH && uniform) long_finish<0, NCH, true, true>(u, sync, z, ov, ts, tg, io.fi, io.dst, none);
     else long_finish<0, NCH, false, true>(u, sync, z, ov, ts, tg, io.fi, io.dst, none);
 }
 
@@ -147,8 +150,8 @@ AACFB_HD void worker_frame(int u, Sync &sync, const FrameIO &io, const SynthTabl
         const bool any_short = is_short(io.fi[0]) || (io.nch == 2 && is_short(io.fi[1]));
         if (any_short) { frame_with_short(u, sync, io, ts, tg, z, ov); return; }
     }
-    if (io.nch == 2) frame_all_long<2>(u, sync, io, ts, tg, z, ov);
-    else frame_all_long<1>(u, sync, io, ts, tg, z, ov);
+    if (io.nch == 2) frame_all_long<2, !GENERIC>(u, sync, io, ts, tg, z, ov);
+    else frame_all_long<1, !GENERIC>(u, sync, io, ts, tg, z, ov);
 }
 
 }  // namespace aacfb
