@@ -73,7 +73,7 @@ class ClockSampler:
     def __enter__(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "20", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
@@ -118,8 +118,10 @@ def dist_env():
     return rank, world, local
 
 
-def oracle_rate(w, S_sample, threads, repeats=1):
-    """frames/s of the CPU oracle on the first S_sample streams of workload w."""
+def oracle_rate(w, S_sample, threads, repeats=1, min_seconds=0.0):
+    """frames/s of the CPU oracle on the first S_sample streams of workload w: the sample is run
+    `repeats` times and then again until `min_seconds` of wall time have been spent; returns
+    (frames/s over everything that was run, seconds, passes)."""
     from oracle import oracle as O
 
     sp, inf = w["spectra"][:S_sample], w["info"][:S_sample]
@@ -127,13 +129,13 @@ def oracle_rate(w, S_sample, threads, repeats=1):
     blob, offs = w["tns_blob"], w["tns_offsets"]
     if offs is not None:
         offs = offs[: S_sample * T * C + 1]
-    best = None
-    for _ in range(repeats):
+    total, passes = 0.0, 0
+    while passes < repeats or total < min_seconds:
         t0 = time.perf_counter()
         O.process(sp, inf, blob, offs, sample_index=w["sample_index"], flags=w["flags"], n_threads=threads)
-        dt = time.perf_counter() - t0
-        best = dt if best is None else min(best, dt)
-    return S_sample * T / best, best
+        total += time.perf_counter() - t0
+        passes += 1
+    return S_sample * T * passes / total, total, passes
 
 
 def run_reference(args):
@@ -156,7 +158,7 @@ def run_reference(args):
         oracle_rate(w, S_sample, cores)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        oracle_rate(w, S_sample, cores)
+        oracle_rate(w, S_sample, cores)  # one step = one pass over the bounded sample
     dt = time.perf_counter() - t0
     value = S_sample * T * args.steps / dt
     sample = f"{S_sample} streams x {T} frames x {C} ch of {args.workload} per step, {cores} threads"
@@ -231,6 +233,7 @@ def run_ours(args):
             step()
             evs[i + 1].record(stream)
         barrier()
+    clock_kernel = clocks.summary()
     total_ms = evs[0].elapsed_time(evs[-1])
     per_step = [evs[i].elapsed_time(evs[i + 1]) for i in range(args.steps)]
     gpu_launches = ctx.launches - launches0
@@ -256,11 +259,18 @@ def run_ours(args):
         for _ in range(2):
             ctx2.process(spec_np, info_np, side["tns_blob"], side["tns_offsets"], out=pcm_np)
         barrier()
-        t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            ctx2.process(spec_np, info_np, side["tns_blob"], side["tns_offsets"], out=pcm_np)
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
+        with ClockSampler(local) as clocks_e2e:
+            t0 = time.perf_counter()
+            for _ in range(e2e_steps):
+                ctx2.process(spec_np, info_np, side["tns_blob"], side["tns_offsets"], out=pcm_np)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+        ce = clocks_e2e.summary()
+        if ce["samples"]:  # the e2e loop is long enough for nvidia-smi's 100 ms sampling: merge
+            clock_kernel = {"sm_mhz": ce["sm_mhz"] if not clock_kernel["samples"] else clock_kernel["sm_mhz"],
+                            "sm_max_mhz": ce["sm_max_mhz"],
+                            "reasons": sorted(set(ce["reasons"]) | set(clock_kernel["reasons"])),
+                            "samples": clock_kernel["samples"], "samples_e2e": ce["samples"], "sm_mhz_e2e": ce["sm_mhz"]}
         te = torch.tensor([dt], device=dev, dtype=torch.float64)
         if world > 1:
             torch.distributed.all_reduce(te, op=torch.distributed.ReduceOp.MAX)
@@ -292,10 +302,14 @@ def run_ours(args):
             cores = os.cpu_count() or 1
             S_cpu = max(cores, min(S, 4 * cores))
             wc = W.make(cfg, S_cpu, T, C, seed=0)
-            rate, secs = oracle_rate(wc, S_cpu, cores, repeats=2)
-            rate1, _ = oracle_rate(wc, max(1, S_cpu // cores), 1)
+            oracle_rate(wc, S_cpu, cores)  # warm-up pass (page faults, thread start)
+            # a bounded sample: the same S_cpu-stream slice over and over for >= 2 s of wall time on
+            # all host cores (about 30 core-seconds on a 16-core box), then >= 1.5 s on one thread
+            rate, secs, passes = oracle_rate(wc, S_cpu, cores, min_seconds=2.0)
+            rate1, secs1, passes1 = oracle_rate(wc, max(1, S_cpu // cores), 1, min_seconds=1.5)
             cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-                   "sample": f"{S_cpu} streams x {T} frames x {C} ch of {args.workload}, best of 2 ({secs:.2f} s)",
+                   "sample": f"{S_cpu} streams x {T} frames x {C} ch of {args.workload}, {passes} passes in {secs:.2f} s "
+                             f"({cores} threads = {secs * cores:.0f} core-seconds)",
                    "single_thread": rate1,
                    "note": "C restatement of aac.js under the JS rounding model (no JS engine on this image)"}
         line = {
@@ -305,12 +319,13 @@ def run_ours(args):
             "config": {"workload": f"{args.workload}: {desc}", "streams_per_gpu": S, "frames_per_stream": T,
                        "channels": C, "parallelism": f"streams sharded over {world} GPU(s), no data-path collective",
                        "l2": "inputs+outputs 1 GiB per step >> 126 MB L2 (no flush needed)"},
-            "clocks": clocks.summary(),
+            "clocks": clock_kernel,
             "e2e": e2e,
             "gpu_launches": int(gpu_launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
                          "frac": achieved / peak_gbs, "traffic": traffic, "peak_source": peak_src,
-                         "kernel": "aacfb::synth_kernel", "algorithmic_bytes_per_launch": alg,
+                         "kernel": "aacfb::synth_kernel" + (" (+ aacfb::tns_kernel)" if tns_bytes else ""),
+                         "algorithmic_bytes_per_launch": alg,
                          "launch_ms": launch_ms},
             "cpu_baseline": cpu,
         }
@@ -323,7 +338,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=500)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="config2", choices=sorted(WORKLOADS))
