@@ -34,7 +34,7 @@ TNS_MAX_ORDER = 20  # tns.js:46
 
 INFO_DTYPE = np.dtype(
     [("window_sequence", "u1"), ("shape_prev", "u1"), ("shape_cur", "u1"),
-     ("max_sfb", "u1"), ("tns_present", "u1"), ("reserved", "u1", (3,))])
+     ("max_sfb", "u1"), ("tns_present", "u1"), ("stereo_present", "u1"), ("reserved", "u1", (2,))])
 
 ERRORS = {-1: "AACFB_ERR_ARG", -2: "AACFB_ERR_SMALL", -3: "AACFB_ERR_SEQUENCE", -4: "AACFB_ERR_TNS",
           -5: "AACFB_ERR_CUDA", -6: "AACFB_ERR_NOMEM"}
@@ -42,7 +42,13 @@ ERRORS = {-1: "AACFB_ERR_ARG", -2: "AACFB_ERR_SMALL", -3: "AACFB_ERR_SEQUENCE", 
 # every symbol include/aacfb.h declares
 ABI_SYMBOLS = ["aacfb_create", "aacfb_destroy", "aacfb_reset", "aacfb_process", "aacfb_process_device",
                "aacfb_filterbank_process", "aacfb_tns_process", "aacfb_get_overlap", "aacfb_set_overlap",
-               "aacfb_last_error", "aacfb_version", "aacfb_launch_count", "aacfb_get_table"]
+               "aacfb_last_error", "aacfb_version", "aacfb_launch_count", "aacfb_get_table",
+               "aacfb_process_stereo", "aacfb_process_device_stereo", "aacfb_get_swb_offsets"]
+
+# aacfb_stereo_ops: what to do to each group of 4 coefficients of a channel pair (include/aacfb.h)
+STEREO_DTYPE = np.dtype([("op", "u1", (256,)), ("scale", "f4", (128,))])
+STEREO_NONE, STEREO_MS, STEREO_IS = 0, 1, 2
+NOISE_BT, INTENSITY_BT2, INTENSITY_BT = 13, 14, 15  # ics.js:39-41
 
 
 class AacfbError(RuntimeError):
@@ -79,6 +85,10 @@ def lib():
         L.aacfb_launch_count.argtypes = [vp]
         L.aacfb_launch_count.restype = C.c_uint64
         L.aacfb_get_table.argtypes = [ci, vp, ci]
+        if hasattr(L, "aacfb_process_stereo"):  # (older tuning variants loaded through AACFB_LIB lack them)
+            L.aacfb_process_stereo.argtypes = [vp, vp, vp, vp, vp, vp, vp, ci]
+            L.aacfb_process_device_stereo.argtypes = [vp, vp, vp, vp, vp, vp, C.c_size_t, vp, ci, vp]
+            L.aacfb_get_swb_offsets.argtypes = [ci, ci, vp, ci]
         _lib = L
     return _lib
 
@@ -93,6 +103,15 @@ def get_table(which: int) -> np.ndarray:
     if n < 0:
         raise AacfbError(n, "bad table index")
     return out[:n].copy()
+
+
+def swb_offsets(sample_index: int, is_short: bool) -> np.ndarray:
+    """info.swbOffsets of one sample rate (tables.js:126-154): swbCount + 1 entries."""
+    out = np.empty(64, np.uint16)
+    n = lib().aacfb_get_swb_offsets(sample_index, int(bool(is_short)), _ptr(out), out.size)
+    if n < 0:
+        raise AacfbError(n, "bad sample index")
+    return out[:n + 1].copy()
 
 
 class Context:
@@ -134,8 +153,11 @@ class Context:
         assert ov.shape == (self.n_streams, self.channels, 1024)
         self._check(lib().aacfb_set_overlap(self._h, _ptr(ov)))
 
-    def process(self, spectra, info, tns_blob=None, tns_offsets=None, out=None) -> np.ndarray:
-        """Batched hot path with host arrays: spectra [S][T][C][1024] -> pcm [S][T][1024][C]."""
+    def process(self, spectra, info, tns_blob=None, tns_offsets=None, out=None, stereo_ops=None) -> np.ndarray:
+        """Batched hot path with host arrays: spectra [S][T][C][1024] -> pcm [S][T][1024][C].
+
+        stereo_ops [S][T][C/2] (STEREO_DTYPE): the spectra are ics.data BEFORE processMS / processIS
+        (decoder.js:300-307) and the device applies the ops of the records flagged by stereo_present."""
         spectra = np.ascontiguousarray(spectra, np.float32)
         S, T, Cn, n = spectra.shape
         assert (S, Cn, n) == (self.n_streams, self.channels, 1024), spectra.shape
@@ -147,13 +169,25 @@ class Context:
             assert tns_offsets.size == S * T * Cn + 1
         pcm = out if out is not None else np.empty((S, T, 1024, Cn), np.float32)
         assert pcm.dtype == np.float32 and pcm.flags.c_contiguous and pcm.size == spectra.size
+        if stereo_ops is not None:
+            stereo_ops = np.ascontiguousarray(stereo_ops, STEREO_DTYPE)
+            assert stereo_ops.size * 2 == S * T * Cn, stereo_ops.shape
+            self._check(lib().aacfb_process_stereo(self._h, _ptr(spectra), _ptr(info), _ptr(stereo_ops), _ptr(tns_blob),
+                                                   _ptr(tns_offsets), _ptr(pcm), T))
+            return pcm
         self._check(lib().aacfb_process(self._h, _ptr(spectra), _ptr(info), _ptr(tns_blob), _ptr(tns_offsets),
                                         _ptr(pcm), T))
         return pcm
 
     def process_device(self, d_spectra: int, d_info: int, d_pcm: int, n_frames: int, stream: int = 0,
-                       d_tns_blob: int = 0, d_tns_offsets: int = 0, tns_blob_bytes: int = 0):
+                       d_tns_blob: int = 0, d_tns_offsets: int = 0, tns_blob_bytes: int = 0, d_stereo_ops: int = 0):
         """Same with raw device addresses (e.g. torch.Tensor.data_ptr()), enqueued on `stream`."""
+        if d_stereo_ops:
+            self._check(lib().aacfb_process_device_stereo(
+                self._h, C.c_void_p(d_spectra), C.c_void_p(d_info), C.c_void_p(d_stereo_ops),
+                C.c_void_p(d_tns_blob or None), C.c_void_p(d_tns_offsets or None), tns_blob_bytes, C.c_void_p(d_pcm),
+                n_frames, C.c_void_p(stream or None)))
+            return
         self._check(lib().aacfb_process_device(self._h, C.c_void_p(d_spectra), C.c_void_p(d_info),
                                                C.c_void_p(d_tns_blob or None), C.c_void_p(d_tns_offsets or None),
                                                tns_blob_bytes, C.c_void_p(d_pcm), n_frames, C.c_void_p(stream or None)))
@@ -248,6 +282,60 @@ def pack_tns(blocks):
             blob += b"\0" * (-len(blob) % 4)
         offs.append(len(blob))
     return (np.frombuffer(bytes(blob), np.uint8).copy() if blob else np.zeros(4, np.uint8)), np.asarray(offs, np.uint32)
+
+
+def pack_stereo(element, sample_index: int, out=None):
+    """The host's share of processMS / processIS (decoder.js:337-404): walk the bands of one channel
+    pair element exactly as the reference does, but instead of touching the 2 x 1024 coefficients
+    write WHAT to do per group of 4 coefficients into an aacfb_stereo_ops record (Python twin of
+    js/stereo_pack.js).  `element`: record with the fields processMS / processIS read (common_window,
+    mask_present, ms_used[128], and per channel window_sequence, group_count, group_length[8],
+    max_sfb, band_types[120], sect_end[120], scale_factors[120]; tools/workloads.CPE_DTYPE).
+
+    Returns (record, present): present = False when the element has nothing to apply."""
+    rec = out if out is not None else np.zeros((), STEREO_DTYPE)
+    op, scale = rec["op"], rec["scale"]
+    op[...] = STEREO_NONE
+    present = False
+    if element["common_window"] and element["mask_present"]:   # decoder.js:295-296
+        off_t = swb_offsets(sample_index, element["window_sequence"][0] == EIGHT_SHORT_SEQUENCE)
+        btl, btr, glen = element["band_types"][0], element["band_types"][1], element["group_length"][0]
+        group_off = idx = 0
+        for g in range(int(element["group_count"][0])):
+            for i in range(int(element["max_sfb"][0])):
+                if element["ms_used"][idx] and btl[idx] < NOISE_BT and btr[idx] < NOISE_BT:
+                    for w in range(int(glen[g])):
+                        a = group_off + w * 128
+                        op[(a + off_t[i]) // 4:(a + off_t[i + 1]) // 4] = STEREO_MS
+                        present = True
+                idx += 1
+            group_off += int(glen[g]) * 128
+    off_t = swb_offsets(sample_index, element["window_sequence"][1] == EIGHT_SHORT_SEQUENCE)
+    bt, se, sf, glen = (element["band_types"][1], element["sect_end"][1], element["scale_factors"][1],
+                        element["group_length"][1])
+    idx = group_off = n_scales = 0
+    for g in range(int(element["group_count"][1])):
+        i, max_sfb = 0, int(element["max_sfb"][1])
+        while i < max_sfb:
+            end = int(se[idx])
+            if bt[idx] in (INTENSITY_BT, INTENSITY_BT2):
+                while i < end:
+                    c = 1.0 if bt[idx] == INTENSITY_BT else -1.0
+                    if element["mask_present"]:
+                        c *= -1.0 if element["ms_used"][idx] else 1.0
+                    scale[n_scales] = np.float32(c) * sf[idx]   # exact: c = +-1
+                    for w in range(int(glen[g])):
+                        a = group_off + w * 128
+                        op[(a + off_t[i]) // 4:(a + off_t[i + 1]) // 4] = STEREO_IS + n_scales
+                        present = True
+                    n_scales += 1
+                    i += 1
+                    idx += 1
+            else:
+                idx += end - i
+                i = end
+        group_off += int(glen[g]) * 128
+    return rec, present
 
 
 class AACDecoder:

@@ -31,8 +31,11 @@ struct Lane {                    // device staging of one in-flight sub-batch of
     float *d_spectra = nullptr, *d_pcm = nullptr, *d_scratch = nullptr;
     aacfb_frame_info *d_info = nullptr;
     uint32_t *d_offsets = nullptr;
+    aacfb_stereo_ops *d_stereo = nullptr;  // [cap_stereo] records of the sub-batch's pair-frames
+    float *d_stereo_out = nullptr;         // output of the stereo pre-pass (TNS modes only)
     size_t cap_cf = 0;           // capacity in channel-frames
     size_t cap_scratch = 0;
+    size_t cap_stereo = 0, cap_stereo_out = 0;
     // scratch holds cap_scratch rows followed by cap_scratch range words (see tns_kernel)
     uint32_t *ranges() const { return reinterpret_cast<uint32_t *>(d_scratch + cap_scratch * 1024); }
 };
@@ -54,6 +57,8 @@ struct aacfb_ctx {
     size_t cap_blob = 0;
     float *d_dev_scratch = nullptr;  // scratch of the device-pointer path
     size_t cap_dev_scratch = 0;
+    float *d_dev_stereo_out = nullptr;  // stereo pre-pass output of the device-pointer path
+    size_t cap_dev_stereo_out = 0;
     uint64_t launches = 0;
     char err[256] = "";
 };
@@ -104,15 +109,32 @@ int pick_slice(int n_pairs, int T, int workers) {
     return (int)std::max<long>(1, q);
 }
 
+bool stereo_needs_prepass(int nc, bool tns_on) { return tns_on || nc != 2; }
+
 // Enqueue TNS pre-pass (if the context's mode asks for it) and the synthesis
 // kernel for S_sub streams starting at stream s_base, all on `stream`.
-int enqueue(aacfb_ctx *ctx, const float *d_spectra, const aacfb_frame_info *d_info, const uint8_t *d_blob,
+//
+// Stereo tools (d_stereo != nullptr): with two channels and no TNS pass, synth_kernel applies the
+// ops to the staged rows (no extra traffic but the records).  When TNS has to run between the
+// stereo tools and the IMDCT (decoder.js:300-319), or with more than one pair per stream, a
+// pre-pass writes the processed spectra to d_stereo_out and everything downstream reads that.
+int enqueue(aacfb_ctx *ctx, const float *d_spectra, const aacfb_frame_info *d_info, const aacfb_stereo_ops *d_stereo,
+            float *d_stereo_out, const uint8_t *d_blob,
             const uint32_t *d_offsets, size_t blob_bytes, float *d_scratch, uint32_t *d_ranges, float *d_pcm, int S_sub,
             int s_base,
             int T, int nc, int c0, float scale, bool in_place_state, cudaStream_t stream) {
     const uint32_t mode = ctx->flags & AACFB_TNS_MODE_MASK;
     const size_t n_cf = (size_t)S_sub * T * nc;
     const bool tns_on = mode != AACFB_TNS_AS_SHIPPED && d_blob && d_offsets && blob_bytes > 0 && d_scratch;
+    if (d_stereo && stereo_needs_prepass(nc, tns_on)) {
+        if (!d_stereo_out) return fail(ctx, AACFB_ERR_ARG, "internal: no buffer for the stereo pre-pass");
+        StereoParams st{};
+        st.spectra = d_spectra; st.out = d_stereo_out; st.info = d_info; st.stereo = d_stereo; st.n_pairs_frames = n_cf / 2;
+        CU(ctx, launch_stereo(st, stream));
+        ctx->launches++;
+        d_spectra = d_stereo_out;
+        d_stereo = nullptr;
+    }
     if (tns_on) {
         TnsParams tp{};
         tp.spectra = d_spectra; tp.scratch = d_scratch; tp.ranges = d_ranges; tp.info = d_info; tp.blob = d_blob;
@@ -124,6 +146,7 @@ int enqueue(aacfb_ctx *ctx, const float *d_spectra, const aacfb_frame_info *d_in
     }
     SynthParams sp{};
     sp.spectra = d_spectra; sp.scratch = tns_on ? d_scratch : nullptr; sp.ranges = d_ranges; sp.info = d_info; sp.pcm = d_pcm;
+    sp.stereo = d_stereo;
     sp.ovl_in = ctx->d_ovl[ctx->cur];
     sp.ovl_out = in_place_state ? ctx->d_ovl[ctx->cur] : ctx->d_ovl[ctx->cur ^ 1];
     sp.tab = scale == 1.0f ? ctx->d_tab_unit : ctx->d_tab;
@@ -143,6 +166,20 @@ int enqueue(aacfb_ctx *ctx, const float *d_spectra, const aacfb_frame_info *d_in
         sp.counter = slots + generic;
         CU(ctx, launch_synth(sp, ctx->num_sms, generic != 0, stream));
         ctx->launches++;
+    }
+    return AACFB_OK;
+}
+
+int grow_lane_stereo(aacfb_ctx *ctx, Lane &ln, size_t n_cf, bool prepass) {
+    if (n_cf / 2 > ln.cap_stereo) {
+        cudaFree(ln.d_stereo); ln.d_stereo = nullptr; ln.cap_stereo = 0;
+        CU(ctx, cudaMalloc(&ln.d_stereo, (n_cf / 2) * sizeof(aacfb_stereo_ops)));
+        ln.cap_stereo = n_cf / 2;
+    }
+    if (prepass && n_cf > ln.cap_stereo_out) {
+        cudaFree(ln.d_stereo_out); ln.d_stereo_out = nullptr; ln.cap_stereo_out = 0;
+        CU(ctx, cudaMalloc(&ln.d_stereo_out, n_cf * 4096));
+        ln.cap_stereo_out = n_cf;
     }
     return AACFB_OK;
 }
@@ -192,6 +229,20 @@ int validate(aacfb_ctx *ctx, const aacfb_frame_info *info, const uint8_t *blob, 
     return AACFB_OK;
 }
 
+// Stereo side info: the flag belongs to the left channel of a pair, op codes index scale[128].
+int validate_stereo(aacfb_ctx *ctx, const aacfb_frame_info *info, const aacfb_stereo_ops *ops, size_t n_cf, int C) {
+    if (C & 1) return fail(ctx, AACFB_ERR_ARG, "stereo tools need an even channel count (pairs are channels 2j, 2j+1)");
+    for (size_t i = 0; i < n_cf; ++i) {
+        if (!info[i].stereo_present) continue;
+        if (i & 1) return fail(ctx, AACFB_ERR_ARG, "channel-frame %zu: stereo_present set on a right channel", i);
+        const aacfb_stereo_ops &r = ops[i >> 1];
+        for (int g = 0; g < 256; ++g)
+            if (r.op[g] > AACFB_STEREO_IS + 127)
+                return fail(ctx, AACFB_ERR_ARG, "channel-frame %zu: stereo op %u out of range", i, (unsigned)r.op[g]);
+    }
+    return AACFB_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -222,6 +273,15 @@ API int aacfb_get_table(int which, float *dst, int capacity) {
     }
     if (capacity < n) return AACFB_ERR_ARG;
     std::memcpy(dst, src, sizeof(float) * n);
+    return n;
+}
+
+API int aacfb_get_swb_offsets(int sample_index, int is_short, uint16_t *dst, int capacity) {
+    if (!dst || sample_index < 0 || sample_index > 11) return AACFB_ERR_ARG;
+    const TnsBandTables &B = tns_band_tables();
+    const int n = is_short ? B.swb_short_count[sample_index] : B.swb_long_count[sample_index];
+    if (capacity < n + 1) return AACFB_ERR_ARG;
+    std::memcpy(dst, is_short ? B.swb_short[sample_index] : B.swb_long[sample_index], sizeof(uint16_t) * (n + 1));
     return n;
 }
 
@@ -293,7 +353,9 @@ API int aacfb_destroy(aacfb_ctx *ctx) {
         Lane &ln = ctx->lane[i];
         if (ln.stream) cudaStreamDestroy(ln.stream);
         cudaFree(ln.d_spectra); cudaFree(ln.d_pcm); cudaFree(ln.d_scratch); cudaFree(ln.d_info); cudaFree(ln.d_offsets);
+        cudaFree(ln.d_stereo); cudaFree(ln.d_stereo_out);
     }
+    cudaFree(ctx->d_dev_stereo_out);
     cudaFree(ctx->d_ovl[0]); cudaFree(ctx->d_ovl[1]); cudaFree(ctx->d_tab); cudaFree(ctx->d_tab_unit); cudaFree(ctx->d_bands);
     cudaFree(ctx->d_counters); cudaFree(ctx->d_blob); cudaFree(ctx->d_dev_scratch);
     delete ctx;
@@ -327,6 +389,14 @@ API int aacfb_set_overlap(aacfb_ctx *ctx, const float *overlap) {
 API int aacfb_process_device(aacfb_ctx *ctx, const float *d_spectra, const aacfb_frame_info *d_info,
                              const uint8_t *d_tns_blob, const uint32_t *d_tns_offsets, size_t tns_blob_bytes,
                              float *d_pcm, int n_frames, void *stream) {
+    return aacfb_process_device_stereo(ctx, d_spectra, d_info, nullptr, d_tns_blob, d_tns_offsets, tns_blob_bytes, d_pcm,
+                                       n_frames, stream);
+}
+
+API int aacfb_process_device_stereo(aacfb_ctx *ctx, const float *d_spectra, const aacfb_frame_info *d_info,
+                                    const aacfb_stereo_ops *d_stereo_ops, const uint8_t *d_tns_blob,
+                                    const uint32_t *d_tns_offsets, size_t tns_blob_bytes, float *d_pcm, int n_frames,
+                                    void *stream) {
     if (!ctx) return fail(nullptr, AACFB_ERR_ARG, "null context");
     if (n_frames < 0) return fail(ctx, AACFB_ERR_ARG, "negative frame count");
     if (n_frames == 0) return AACFB_OK;
@@ -348,8 +418,23 @@ API int aacfb_process_device(aacfb_ctx *ctx, const float *d_spectra, const aacfb
         scratch = ctx->d_dev_scratch;
     }
     uint32_t *ranges = scratch ? reinterpret_cast<uint32_t *>(scratch + ctx->cap_dev_scratch * 1024) : nullptr;
-    const int rc = enqueue(ctx, d_spectra, d_info, d_tns_blob, d_tns_offsets, tns_blob_bytes, scratch, ranges, d_pcm, ctx->S,
-                           0, n_frames, ctx->C, 0, 1.0f / 32768.0f, false, st);
+    float *stereo_out = nullptr;
+    if (d_stereo_ops) {
+        if (ctx->C & 1) return fail(ctx, AACFB_ERR_ARG, "stereo tools need an even channel count (pairs are channels 2j, 2j+1)");
+        if (reinterpret_cast<uintptr_t>(d_stereo_ops) & 15) return fail(ctx, AACFB_ERR_ARG, "stereo_ops must be 16-byte aligned");
+        if (stereo_needs_prepass(ctx->C, scratch != nullptr)) {
+            const size_t n_cf = (size_t)ctx->S * n_frames * ctx->C;
+            if (n_cf > ctx->cap_dev_stereo_out) {
+                CU(ctx, cudaDeviceSynchronize());
+                cudaFree(ctx->d_dev_stereo_out); ctx->d_dev_stereo_out = nullptr; ctx->cap_dev_stereo_out = 0;
+                CU(ctx, cudaMalloc(&ctx->d_dev_stereo_out, n_cf * 4096));
+                ctx->cap_dev_stereo_out = n_cf;
+            }
+            stereo_out = ctx->d_dev_stereo_out;
+        }
+    }
+    const int rc = enqueue(ctx, d_spectra, d_info, d_stereo_ops, stereo_out, d_tns_blob, d_tns_offsets, tns_blob_bytes, scratch,
+                           ranges, d_pcm, ctx->S, 0, n_frames, ctx->C, 0, 1.0f / 32768.0f, false, st);
     if (rc != AACFB_OK) return rc;
     ctx->cur ^= 1;
     return AACFB_OK;
@@ -357,6 +442,12 @@ API int aacfb_process_device(aacfb_ctx *ctx, const float *d_spectra, const aacfb
 
 API int aacfb_process(aacfb_ctx *ctx, const float *spectra, const aacfb_frame_info *info, const uint8_t *tns_blob,
                       const uint32_t *tns_offsets, float *pcm, int n_frames) {
+    return aacfb_process_stereo(ctx, spectra, info, nullptr, tns_blob, tns_offsets, pcm, n_frames);
+}
+
+API int aacfb_process_stereo(aacfb_ctx *ctx, const float *spectra, const aacfb_frame_info *info,
+                             const aacfb_stereo_ops *stereo_ops, const uint8_t *tns_blob, const uint32_t *tns_offsets,
+                             float *pcm, int n_frames) {
     if (!ctx) return fail(nullptr, AACFB_ERR_ARG, "null context");
     if (n_frames < 0) return fail(ctx, AACFB_ERR_ARG, "negative frame count");
     if (n_frames == 0) return AACFB_OK;
@@ -365,6 +456,7 @@ API int aacfb_process(aacfb_ctx *ctx, const float *spectra, const aacfb_frame_in
     const size_t per_stream = (size_t)T * C;
     int rc = validate(ctx, info, tns_blob, tns_offsets, (size_t)S * per_stream);
     if (rc != AACFB_OK) return rc;
+    if (stereo_ops && (rc = validate_stereo(ctx, info, stereo_ops, (size_t)S * per_stream, C)) != AACFB_OK) return rc;
     DeviceGuard guard(ctx->device);
     const uint32_t mode = ctx->flags & AACFB_TNS_MODE_MASK;
     const bool tns_on = mode != AACFB_TNS_AS_SHIPPED && tns_blob && tns_offsets;
@@ -385,8 +477,12 @@ API int aacfb_process(aacfb_ctx *ctx, const float *spectra, const aacfb_frame_in
     int n_sub = std::min(S, 8);
     if ((size_t)S * per_stream * 4096 < (size_t)(8u << 20)) n_sub = 1;
     const int s_per = (S + n_sub - 1) / n_sub;
-    for (int i = 0; i < kLanes; ++i)
+    for (int i = 0; i < kLanes; ++i) {
         if ((rc = grow_lane(ctx, ctx->lane[i], (size_t)s_per * per_stream, tns_on && blob_bytes)) != AACFB_OK) return rc;
+        if (stereo_ops && (rc = grow_lane_stereo(ctx, ctx->lane[i], (size_t)s_per * per_stream,
+                                                 stereo_needs_prepass(C, tns_on && blob_bytes))) != AACFB_OK)
+            return rc;
+    }
     int li = 0;
     for (int s0 = 0; s0 < S; s0 += s_per, li ^= 1) {
         Lane &ln = ctx->lane[li];
@@ -397,7 +493,11 @@ API int aacfb_process(aacfb_ctx *ctx, const float *spectra, const aacfb_frame_in
         CU(ctx, cudaMemcpyAsync(ln.d_info, info + off, n_cf * sizeof(aacfb_frame_info), cudaMemcpyHostToDevice, ln.stream));
         if (tns_on && blob_bytes)
             CU(ctx, cudaMemcpyAsync(ln.d_offsets, tns_offsets + off, (n_cf + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, ln.stream));
-        rc = enqueue(ctx, ln.d_spectra, ln.d_info, (tns_on && blob_bytes) ? ctx->d_blob : nullptr, ln.d_offsets, blob_bytes,
+        if (stereo_ops)
+            CU(ctx, cudaMemcpyAsync(ln.d_stereo, stereo_ops + off / 2, (n_cf / 2) * sizeof(aacfb_stereo_ops),
+                                    cudaMemcpyHostToDevice, ln.stream));
+        rc = enqueue(ctx, ln.d_spectra, ln.d_info, stereo_ops ? ln.d_stereo : nullptr, ln.d_stereo_out,
+                     (tns_on && blob_bytes) ? ctx->d_blob : nullptr, ln.d_offsets, blob_bytes,
                      ln.d_scratch, ln.d_scratch ? ln.ranges() : nullptr, ln.d_pcm, sn, s0, T, C, 0, 1.0f / 32768.0f, false,
                      ln.stream);
         if (rc != AACFB_OK) return rc;
@@ -425,8 +525,8 @@ API int aacfb_filterbank_process(aacfb_ctx *ctx, int stream, int channel, const 
     fi.tns_present = 0;  // the inner seam is the filterbank alone
     CU(ctx, cudaMemcpyAsync(ln.d_spectra, input, 4096, cudaMemcpyHostToDevice, ln.stream));
     CU(ctx, cudaMemcpyAsync(ln.d_info, &fi, sizeof fi, cudaMemcpyHostToDevice, ln.stream));
-    rc = enqueue(ctx, ln.d_spectra, ln.d_info, nullptr, nullptr, 0, nullptr, nullptr, ln.d_pcm, 1, stream, 1, 1, channel, 1.0f,
-                 true, ln.stream);
+    rc = enqueue(ctx, ln.d_spectra, ln.d_info, nullptr, nullptr, nullptr, nullptr, 0, nullptr, nullptr, ln.d_pcm, 1, stream, 1,
+                 1, channel, 1.0f, true, ln.stream);
     if (rc != AACFB_OK) return rc;
     CU(ctx, cudaMemcpyAsync(output, ln.d_pcm, 4096, cudaMemcpyDeviceToHost, ln.stream));
     CU(ctx, cudaStreamSynchronize(ln.stream));

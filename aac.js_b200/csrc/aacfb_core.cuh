@@ -521,6 +521,32 @@ AACFB_HD void ovl_store(int u, const Ovl &ov, float *state, float inv_scale) {
     }
 }
 
+// ------------------------------------------------------------ stereo tools
+// processMS (decoder.js:379-404) and processIS (decoder.js:337-376) on the staged rows of a
+// channel pair (chain 0 = left, chain 1 = right), driven by the host's per-4-coefficient op
+// table (aacfb_stereo_ops, include/aacfb.h).  64 threads x 4 groups of 4 coefficients.
+AACFB_HD void stereo_apply(int u, float *stage, const aacfb_stereo_ops *ops) {
+    float4 *L = reinterpret_cast<float4 *>(stage), *R = reinterpret_cast<float4 *>(stage + kRowFloats);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int g = u + 64 * i;
+        const int op = ops->op[g];
+        if (op == AACFB_STEREO_NONE) continue;
+        const float4 l = L[g];
+        float4 r = R[g];
+        if (op == AACFB_STEREO_MS) {  // t = l - r; l += r; r = t
+            float4 m;
+            m.x = f_add(l.x, r.x); m.y = f_add(l.y, r.y); m.z = f_add(l.z, r.z); m.w = f_add(l.w, r.w);
+            r.x = f_sub(l.x, r.x); r.y = f_sub(l.y, r.y); r.z = f_sub(l.z, r.z); r.w = f_sub(l.w, r.w);
+            L[g] = m;
+        } else {                      // right = left * scale
+            const float sc = ops->scale[(op - AACFB_STEREO_IS) & 127];
+            r.x = f_mul(l.x, sc); r.y = f_mul(l.y, sc); r.z = f_mul(l.z, sc); r.w = f_mul(l.w, sc);
+        }
+        R[g] = r;
+    }
+}
+
 // ------------------------------------------------------------------- TNS
 // tns.js:105-177 with `tmp` -> `top` at :122.  Strictly serial per chain:
 // each tap is a rounded f32 read-modify-write in the reference's order

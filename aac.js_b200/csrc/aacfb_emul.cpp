@@ -107,6 +107,7 @@ extern "C" __attribute__((visibility("default"))) int aacfb_emul_process(
                 io.stage = stage;
                 io.scratch = scratch2[f & 1];
                 io.nch = pr.nch;
+                io.ops = nullptr;  // the stereo tools are exercised on the device only
                 io.dst.emit = fb + f >= f0;
                 io.dst.interleaved = pr.interleaved;
                 io.dst.scale = kScale;
@@ -115,8 +116,8 @@ extern "C" __attribute__((visibility("default"))) int aacfb_emul_process(
                 for (int c = 0; c < 2; ++c) io.fi[c] = fb_pack(info[cf_index(g, pr.s[c], t, pr.j[c])]);
                 io.dst.out0 = pcm + ((size_t)pr.s[0] * g.T + t) * 1024 * g.nc + pr.j[0];
                 io.dst.out1 = pcm + ((size_t)pr.s[1] * g.T + t) * 1024 * g.nc + pr.j[1];
-                if (item_has_short) worker_frame<true>(u, sync, io, tab, tab, z, ov);
-                else worker_frame<false>(u, sync, io, tab, tab, z, ov);
+                if (item_has_short) worker_frame<true, false>(u, sync, io, tab, tab, z, ov);
+                else worker_frame<false, false>(u, sync, io, tab, tab, z, ov);
                 if (t == g.T - 1) {
                     // NOTE: in place -- safe here because items run one after the other, in order
                     ovl_store<0>(u, ov, overlap + state_index(g, pr.s[0], pr.j[0]), 1.0f / kScale);

@@ -30,14 +30,18 @@ constexpr int kStageBytes = kStageFloats * 4;
 constexpr int kTabBytes = (kSmemTableBytes + 127) & ~127;
 
 // Shared-memory layout of a CTA with W workers and a TMA ring of ST stages per worker.
-template <int W, int ST>
+// STEREO: the instantiation that also applies the stereo tools (wider side-info ring entries,
+// one aacfb_stereo_ops record per stage); the plain one is byte for byte what it was without them.
+template <int W, int ST, bool STEREO = false>
 struct Layout {
     static constexpr int kBufsPerWorker = ST + 2;  // TMA ring + two alternating scratch buffers
     static constexpr int kOffStages = kTabBytes;
     static constexpr int kOffBars = kOffStages + W * kBufsPerWorker * kStageBytes;
     static constexpr int kOffSlots = kOffBars + W * ST * 8;
-    static constexpr int kSlotInts = 8 + 4 * ST;   // per worker: item, flag, cursor[5], -, side-info ring [2 ST][2]
-    static constexpr int kTotal = kOffSlots + W * kSlotInts * 4;
+    static constexpr int kRingWords = STEREO ? 4 : 2;   // per ring entry: 2 chains x (FrameBits [, flags word])
+    static constexpr int kSlotInts = 8 + 2 * kRingWords * ST;   // per worker: item, flag, cursor[6], side-info ring [2 ST]
+    static constexpr int kOffOps = (kOffSlots + W * kSlotInts * 4 + 15) & ~15;   // aacfb_stereo_ops per worker and stage
+    static constexpr int kTotal = STEREO ? kOffOps + W * ST * (int)sizeof(aacfb_stereo_ops) : kOffSlots + W * kSlotInts * 4;
     static_assert(kTotal <= 227 * 1024, "shared memory budget");
     static_assert(2 * W + 1 <= 16, "named barriers");
 };
@@ -69,10 +73,12 @@ __device__ __forceinline__ void bulk_load(uint32_t dst, const void *src, uint32_
                  : "memory");
 }
 
+template <bool STEREO>
 struct DevSync {
     uint32_t bar_id;      // named barrier of this worker (all 64 threads block)
     uint32_t free_id;     // named barrier "stage is free": followers arrive, the leader's warp waits
     bool leader_warp, leader;
+    volatile uint32_t *ring;  // side-info ring of the worker (see synth_kernel)
     // the refill this frame's stage_free() has to issue (leader only)
     bool next_valid;
     uint32_t dst, mbar;
@@ -80,6 +86,9 @@ struct DevSync {
     uint32_t rng[2];      // lo4 | hi4 << 16: float4 interval that comes from the TNS scratch (0: none)
     int nrows;
     const float *spectra, *scratch;
+    const aacfb_stereo_ops *stereo;   // global records (nullptr: none)
+    bool pair_stereo;                 // the rows being fetched are (left, right) of one stream
+    uint32_t ring_e, ops_dst;         // side-info ring entry / shared-memory home of the frame being fetched
     __device__ __forceinline__ void barrier() { asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory"); }
     // One row = 4096 bytes on the mbarrier, fetched as up to three 1-D bulk copies: the interval
     // the TNS pass filtered comes from its scratch, the rest straight from the spectra.
@@ -92,10 +101,15 @@ struct DevSync {
         bulk_load(d + 16u * lo, b + 4 * lo, 16u * (hi - lo), mbar);
         if (hi < 256u) bulk_load(d + 16u * hi, a + 4 * hi, 16u * (256u - hi), mbar);
     }
+    // STEREO: the side info of the frame must have landed in the ring (stereo_present = byte 5 of
+    // the left channel's aacfb_frame_info = second word of its entry)
     __device__ __forceinline__ void issue() {
-        mbar_expect_tx(mbar, (uint32_t)nrows * 4096u);
+        bool ops = false;
+        if (STEREO) ops = pair_stereo && ((ring[4 * ring_e + 1] >> 8) & 0xffu) != 0;
+        mbar_expect_tx(mbar, (uint32_t)nrows * 4096u + (ops ? (uint32_t)sizeof(aacfb_stereo_ops) : 0u));
         issue_row(dst, cf[0], rng[0]);
         if (nrows == 2) issue_row(dst + 4096u, cf[1], rng[1]);
+        if (STEREO && ops) bulk_load(ops_dst, stereo + (cf[0] >> 1), (uint32_t)sizeof(aacfb_stereo_ops), mbar);
     }
     __device__ __forceinline__ void stage_free() {
         // order this thread's generic-proxy accesses to the stage before the async-proxy refill
@@ -130,9 +144,9 @@ __device__ __forceinline__ uint32_t row_range(const SynthParams &P, size_t cf) {
 // GENERIC = false: takes only work items without EIGHT_SHORT frames (the long-transform code
 // alone, best register allocation); GENERIC = true: takes only the items that have one.
 // Both instantiations are launched back to back and walk the same item list.
-template <bool GENERIC, int W, int ST>
+template <bool GENERIC, bool STEREO, int W, int ST>
 __global__ void __launch_bounds__(W * 64, 1) synth_kernel(const __grid_constant__ SynthParams P) {
-    using L = Layout<W, ST>;
+    using L = Layout<W, ST, STEREO>;
     constexpr int kCtaThreads = W * 64, kWorkers = W, kStages = ST, kBufsPerWorker = L::kBufsPerWorker;
     constexpr int kOffStages = L::kOffStages, kOffBars = L::kOffBars, kOffSlots = L::kOffSlots;
     extern __shared__ __align__(128) uint8_t smem[];
@@ -158,21 +172,25 @@ __global__ void __launch_bounds__(W * 64, 1) synth_kernel(const __grid_constant_
     // 4-byte cp.async when it prefetches the frame's rows, kStages frames ahead, so no thread waits
     // on a global load at the top of a frame; 2 kStages entries because the entry of the frame
     // being worked on is still being read when the next prefetch is issued.
-    volatile uint32_t *fi_ring = reinterpret_cast<volatile uint32_t *>(slot + 8);
-    constexpr uint32_t kFiRing = 2 * kStages;
+    volatile uint32_t *fi_ring = reinterpret_cast<volatile uint32_t *>(slot + 8);  // [entry][chain][1 or 2 words]
+    constexpr uint32_t kFiRing = 2 * kStages, kRW = L::kRingWords;
+    const aacfb_stereo_ops *ops_area =
+        reinterpret_cast<const aacfb_stereo_ops *>(smem + L::kOffOps) + (size_t)w * kStages;
     if (leader) {
         for (int s = 0; s < kStages; ++s) mbar_init(bars + 8 * s, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
 
-    DevSync sync;
+    DevSync<STEREO> sync;
     sync.bar_id = 1 + w;
     sync.free_id = 1 + kWorkers + w;
     sync.leader_warp = ((tid >> 5) & 1) == 0;
     sync.leader = leader;
     sync.spectra = P.spectra;
     sync.scratch = P.scratch;
+    sync.stereo = P.stereo;
+    sync.ring = fi_ring;
     const Geometry g = P.g;
     uint32_t fc = 0;  // frames this worker has staged so far: ring position and mbarrier phase
     Pts z;
@@ -225,16 +243,27 @@ __global__ void __launch_bounds__(W * 64, 1) synth_kernel(const __grid_constant_
             cur[2] = (int)cf_index(g, pn.s[0], t, pn.j[0]);
             cur[3] = (int)cf_index(g, pn.s[1], t, pn.j[1]);
             cur[4] = pn.nch;
+            if (STEREO) cur[5] = pn.interleaved ? 1 : 0;
         };
         if (leader) cursor_to(p0, tb);
         auto refill = [&](uint32_t st, uint32_t frame_no) {
             const int tn = cur[1], ca = cur[2], cb = cur[3];
             {
-                const uint32_t e = smem_u32(const_cast<uint32_t *>(fi_ring)) + 8u * (frame_no % kFiRing);
+                sync.ring_e = frame_no % kFiRing;
+                const uint32_t e = smem_u32(const_cast<uint32_t *>(fi_ring)) + 4u * kRW * sync.ring_e;
                 const uint32_t *inf = reinterpret_cast<const uint32_t *>(P.info);
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(e), "l"(inf + 2 * (size_t)ca) : "memory");
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(e + 4u), "l"(inf + 2 * (size_t)cb) : "memory");
+                if (STEREO) {   // the whole 8-byte record: the stereo flag sits in its second word
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(e), "l"(inf + 2 * (size_t)ca) : "memory");
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(e + 8u), "l"(inf + 2 * (size_t)cb) : "memory");
+                } else {
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(e), "l"(inf + 2 * (size_t)ca) : "memory");
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(e + 4u), "l"(inf + 2 * (size_t)cb) : "memory");
+                }
                 asm volatile("cp.async.commit_group;" ::: "memory");
+                if (STEREO) {
+                    sync.pair_stereo = cur[5] != 0;
+                    sync.ops_dst = smem_u32(ops_area + st);
+                }
             }
             sync.dst = smem_u32(stages + st * kStageFloats);
             sync.mbar = bars + 8 * st;
@@ -248,6 +277,7 @@ __global__ void __launch_bounds__(W * 64, 1) synth_kernel(const __grid_constant_
         if (leader) {  // prologue: fill the ring
             for (int i = 0; i < kStages && i < nf; ++i) {
                 refill((fc + i) % kStages, fc + i);
+                if (STEREO) asm volatile("cp.async.wait_group 0;" ::: "memory");
                 sync.issue();
             }
             asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -274,14 +304,16 @@ __global__ void __launch_bounds__(W * 64, 1) synth_kernel(const __grid_constant_
             io.dst.scale = P.scale;
             io.dst.inv_scale = 1.0f / P.scale;
             io.dst.ostride = g.nc;
-            io.fi[0] = fi_ring[2 * (fc % kFiRing)];
-            io.fi[1] = fi_ring[2 * (fc % kFiRing) + 1];
+            io.fi[0] = fi_ring[kRW * (fc % kFiRing)];
+            io.fi[1] = fi_ring[kRW * (fc % kFiRing) + kRW / 2];
+            io.ops = nullptr;
+            if (STEREO && pr.interleaved && ((fi_ring[4 * (fc % kFiRing) + 1] >> 8) & 0xffu) != 0) io.ops = ops_area + st;
             io.dst.out0 = P.pcm + oa;
             io.dst.out1 = P.pcm + ob;
             sync.next_valid = f + kStages < nf;
             if (leader && sync.next_valid) refill(st, fc + kStages);
             mbar_wait(bars + 8 * st, (fc / kStages) & 1u);
-            worker_frame<GENERIC>(u, sync, io, ts, P.tab, z, ov);
+            worker_frame<GENERIC, STEREO>(u, sync, io, ts, P.tab, z, ov);
             cfa += g.nc; cfb += g.nc;
             oa += (size_t)1024 * g.nc; ob += (size_t)1024 * g.nc;
             if (++t == g.T) {  // the pair is complete: its overlap goes back to the state
@@ -581,25 +613,66 @@ __global__ void __launch_bounds__(kTnsWarps * 32, 4) tns_kernel(const __grid_con
     }
 }
 
-template <bool GENERIC, int W, int ST>
+// Stereo tools as a pre-pass: out = spectra with processMS / processIS applied (rows of pair-frames
+// without a record are copied).  Used only when TNS has to run between the stereo tools and the
+// IMDCT (TNS_FIXED_* modes); otherwise synth_kernel applies the ops on the staged rows.
+// One warp per channel-pair frame.
+__global__ void __launch_bounds__(128) stereo_kernel(const __grid_constant__ StereoParams P) {
+    const size_t pf = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (pf >= P.n_pairs_frames) return;
+    const uint2 raw = __ldg(reinterpret_cast<const uint2 *>(P.info) + 2 * pf);
+    const bool has = ((raw.y >> 8) & 0xffu) != 0;
+    const aacfb_stereo_ops *ops = P.stereo + pf;
+    const float4 *L = reinterpret_cast<const float4 *>(P.spectra) + 2 * pf * 256, *R = L + 256;
+    float4 *Lo = reinterpret_cast<float4 *>(P.out) + 2 * pf * 256, *Ro = Lo + 256;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int g = lane + 32 * i;
+        const float4 l = L[g];
+        float4 r = R[g], m = l;
+        const int op = has ? ops->op[g] : AACFB_STEREO_NONE;
+        if (op == AACFB_STEREO_MS) {
+            m.x = f_add(l.x, r.x); m.y = f_add(l.y, r.y); m.z = f_add(l.z, r.z); m.w = f_add(l.w, r.w);
+            r.x = f_sub(l.x, r.x); r.y = f_sub(l.y, r.y); r.z = f_sub(l.z, r.z); r.w = f_sub(l.w, r.w);
+        } else if (op >= AACFB_STEREO_IS) {
+            const float sc = ops->scale[(op - AACFB_STEREO_IS) & 127];
+            r.x = f_mul(l.x, sc); r.y = f_mul(l.y, sc); r.z = f_mul(l.z, sc); r.w = f_mul(l.w, sc);
+        }
+        Lo[g] = m;
+        Ro[g] = r;
+    }
+}
+
+cudaError_t launch_stereo(const StereoParams &P, cudaStream_t stream) {
+    const size_t threads = P.n_pairs_frames * 32;
+    if (threads == 0) return cudaSuccess;
+    stereo_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, stream>>>(P);
+    return cudaGetLastError();
+}
+
+template <bool GENERIC, bool STEREO, int W, int ST>
 static cudaError_t launch_one(const SynthParams &P, int num_sms, cudaStream_t stream) {
     static bool attr_done[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 64 && !attr_done[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(synth_kernel<GENERIC, W, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             Layout<W, ST>::kTotal);
+        cudaError_t e = cudaFuncSetAttribute(synth_kernel<GENERIC, STEREO, W, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             Layout<W, ST, STEREO>::kTotal);
         if (e != cudaSuccess) return e;
         attr_done[dev] = true;
     }
     const int grid = num_sms < (P.g.n_items + W - 1) / W ? num_sms : (P.g.n_items + W - 1) / W;
-    synth_kernel<GENERIC, W, ST><<<grid < 1 ? 1 : grid, W * 64, Layout<W, ST>::kTotal, stream>>>(P);
+    synth_kernel<GENERIC, STEREO, W, ST><<<grid < 1 ? 1 : grid, W * 64, Layout<W, ST, STEREO>::kTotal, stream>>>(P);
     return cudaGetLastError();
 }
 
 cudaError_t launch_synth(const SynthParams &P, int num_sms, bool generic, cudaStream_t stream) {
-    return generic ? launch_one<true, kWorkersGeneric, kStagesGeneric>(P, num_sms, stream)
-                   : launch_one<false, kWorkers, kStages>(P, num_sms, stream);
+    if (P.stereo != nullptr)   // the instantiations that also apply the stereo tools of the pair-frames
+        return generic ? launch_one<true, true, kWorkersGeneric, kStagesGeneric>(P, num_sms, stream)
+                       : launch_one<false, true, kWorkers, kStages>(P, num_sms, stream);
+    return generic ? launch_one<true, false, kWorkersGeneric, kStagesGeneric>(P, num_sms, stream)
+                   : launch_one<false, false, kWorkers, kStages>(P, num_sms, stream);
 }
 
 cudaError_t launch_tns(const TnsParams &P, cudaStream_t stream) {

@@ -27,6 +27,7 @@ struct SynthParams {
     const float *scratch;           // TNS-filtered rows (same layout, valid on `ranges` only) or nullptr
     const uint32_t *ranges;         // [S][T][nc] lo4 | hi4 << 16: the float4 interval of a row that lives in scratch
     const aacfb_frame_info *info;   // [S][T][nc]
+    const aacfb_stereo_ops *stereo; // [S][T][nc/2] stereo tools of the pair-frames, or nullptr
     float *pcm;                     // [S][T][1024][nc]
     const float *ovl_in;            // overlap state read by chunks starting at t = 0
     float *ovl_out;                 // overlap state written by chunks ending at t = T
@@ -51,6 +52,14 @@ struct TnsParams {
     const TnsBandTables *bands;
 };
 
+struct StereoParams {            // stereo tools as a pre-pass (only when TNS has to run between them and the IMDCT)
+    const float *spectra;
+    float *out;                     // same layout: rows with the ops applied (others copied)
+    const aacfb_frame_info *info;
+    const aacfb_stereo_ops *stereo;
+    size_t n_pairs_frames;          // S * T * nc / 2
+};
+cudaError_t launch_stereo(const StereoParams &P, cudaStream_t stream);
 cudaError_t launch_synth(const SynthParams &P, int num_sms, bool generic, cudaStream_t stream);
 cudaError_t launch_tns(const TnsParams &P, cudaStream_t stream);
 int synth_smem_bytes();

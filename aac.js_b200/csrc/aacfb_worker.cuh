@@ -26,6 +26,7 @@ struct FrameIO {
     float *scratch;               // 2048 floats, alternates between two buffers from frame to frame
     FrameBits fi[2];              // packed aacfb_frame_info of each chain
     int nch;                      // 1 or 2 live chains
+    const aacfb_stereo_ops *ops;  // stereo tools of this pair-frame (staged next to the rows) or nullptr
     OutDst dst;                   // where the frame's PCM goes
 };
 
@@ -143,9 +144,13 @@ AACFB_HD void frame_with_short(int u, Sync &sync, const FrameIO &io, const Synth
 // instantiation for work items without any EIGHT_SHORT frame: it contains no
 // short-window code at all, so its register allocation is that of the long
 // path alone (the kernel is compiled twice, see synth_kernel).
-template <bool GENERIC, class Sync>
+template <bool GENERIC, bool STEREO, class Sync>
 AACFB_HD void worker_frame(int u, Sync &sync, const FrameIO &io, const SynthTables *ts, const SynthTables *tg, Pts &z,
                            Ovl &ov) {
+    if (STEREO && io.ops) {  // M/S and intensity stereo act on the spectra before anything else (decoder.js:300-307)
+        stereo_apply(u, io.stage, io.ops);
+        sync.barrier();
+    }
     if (GENERIC) {
         const bool any_short = is_short(io.fi[0]) || (io.nch == 2 && is_short(io.fi[1]));
         if (any_short) { frame_with_short(u, sync, io, ts, tg, z, ov); return; }

@@ -3,8 +3,10 @@
  *
  * Keeps the Aurora.js Decoder plugin surface of aac.js src/decoder.js (init /
  * setCookie / readChunk returning interleaved Float32 PCM).  The serial
- * ADTS / Huffman / ICS parse, M/S and intensity stereo stay exactly where they are
- * (the reference's own code, unchanged, on the CPU).  What changes is the tail of
+ * ADTS / Huffman / ICS parse stays exactly where it is (the reference's own code, unchanged,
+ * on the CPU).  M/S and intensity stereo either stay there too (stereoOnDevice = false) or,
+ * for plain stereo streams, become a 768-byte op record per frame that the device applies to
+ * the staged spectra (stereo_pack.js, aacfb_process_stereo).  What changes is the tail of
  * the frame (src/decoder.js:263-269 / 309-319 and :204-213): instead of running
  * tns.process + filter_bank.process + the interleave per frame in JS, readChunk
  * parses up to K frames ahead, stages their spectra and side info into typed
@@ -18,6 +20,7 @@ var ICStream = require('aac/src/ics');
 var CPEElement = require('aac/src/cpe');
 var addon = require('./build/Release/aacfb.node');
 var tnsPack = require('./tns_pack');
+var stereoPack = require('./stereo_pack');
 
 var B200Decoder = AACDecoder.extend(function() {
     AV.Decoder.register('mp4a', this);
@@ -25,6 +28,7 @@ var B200Decoder = AACDecoder.extend(function() {
 
     this.prototype.framesPerChunk = 64;            // K
     this.prototype.tnsMode = tnsPack.AS_SHIPPED;   // literal parity with the reference by default
+    this.prototype.stereoOnDevice = true;          // M/S + IS applied by the kernels (channel pairs of 2-channel streams)
 
     var setCookie = AACDecoder.prototype.setCookie;
     this.prototype.setCookie = function(buffer) {
@@ -37,6 +41,11 @@ var B200Decoder = AACDecoder.extend(function() {
         this.tnsBuf = new ArrayBuffer(K * C * (8 + 8 * 4 * 84));
         this.tnsBytes = new Uint8Array(this.tnsBuf);
         this.tnsView = new DataView(this.tnsBuf);
+        this.deviceStereo = this.stereoOnDevice && C === 2;
+        if (this.deviceStereo) {                   // one aacfb_stereo_ops record per frame
+            this.stereoBuf = new ArrayBuffer(K * stereoPack.RECORD_BYTES);
+            this.stereoBytes = new Uint8Array(this.stereoBuf);
+        }
     };
 
     // the part of process(elements) before TNS: M/S, IS (decoder.js:295-302), then stage
@@ -55,9 +64,19 @@ var B200Decoder = AACDecoder.extend(function() {
             var e = elements[i];
             if (e instanceof ICStream) { put(e, channel); channel += 1; }
             else if (e instanceof CPEElement) {
-                if (e.commonWindow && e.maskPresent) this.processMS(e, e.left.data, e.right.data);
-                this.processIS(e, e.left.data, e.right.data);
-                put(e.left, channel); put(e.right, channel + 1); channel += 2;
+                var onDevice = false;
+                if (this.deviceStereo) {
+                    var at = t * stereoPack.RECORD_BYTES;
+                    onDevice = stereoPack.pack(e, new Uint8Array(this.stereoBuf, at, 256),
+                                               new Float32Array(this.stereoBuf, at + 256, 128));
+                    if (onDevice) this.anyStereo = true;
+                } else {
+                    if (e.commonWindow && e.maskPresent) this.processMS(e, e.left.data, e.right.data);
+                    this.processIS(e, e.left.data, e.right.data);
+                }
+                put(e.left, channel); put(e.right, channel + 1);
+                if (onDevice) this.info[(t * C + channel) * 8 + 5] = 1;   // stereo_present, left channel
+                channel += 2;
             } else throw new Error('coupling elements are outside the accelerated path');
         }
     };
@@ -65,6 +84,7 @@ var B200Decoder = AACDecoder.extend(function() {
     this.prototype.readChunk = function() {
         var C = this.config.chanConfig, K = this.framesPerChunk, t = 0, stream = this.bitstream;
         this.tnsLen = 0;
+        this.anyStereo = false;
         while (t < K) {
             var mark = stream.offset();
             try {
@@ -78,8 +98,12 @@ var B200Decoder = AACDecoder.extend(function() {
         }
         this.tnsOffsets[t * C] = this.tnsLen;
         var pcm = new Float32Array(t * 1024 * C);
-        addon.process(this.handle, this.spectra, this.info, this.tnsLen ? this.tnsBytes : null,
-                      this.tnsLen ? this.tnsOffsets : null, pcm, t);
+        if (this.anyStereo)
+            addon.processStereo(this.handle, this.spectra, this.info, this.stereoBytes, this.tnsLen ? this.tnsBytes : null,
+                                this.tnsLen ? this.tnsOffsets : null, pcm, t);
+        else
+            addon.process(this.handle, this.spectra, this.info, this.tnsLen ? this.tnsBytes : null,
+                          this.tnsLen ? this.tnsOffsets : null, pcm, t);
         return pcm;                                     // t frames of decoder.js:204-215 output, back to back
     };
 });

@@ -69,6 +69,36 @@ static napi_value js_process(napi_env env, napi_callback_info info) {
     return NULL;
 }
 
+/* processStereo(handle, spectra f32, info u8, stereoOps u8 (768 B per pair-frame), tnsBlob, tnsOffsets, pcm f32, nFrames):
+ * spectra are ics.data BEFORE processMS / processIS (decoder.js:294-301); see js/stereo_pack.js */
+static napi_value js_process_stereo(napi_env env, napi_callback_info info) {
+    size_t argc = 8; napi_value a[8];
+    NAPI_OK(env, napi_get_cb_info(env, info, &argc, a, NULL, NULL));
+    aacfb_ctx *ctx = handle(env, a[0]);
+    int32_t n = 0; napi_get_value_int32(env, a[7], &n);
+    int rc = aacfb_process_stereo(ctx, (const float *)typed(env, a[1], NULL), (const aacfb_frame_info *)typed(env, a[2], NULL),
+                                  (const aacfb_stereo_ops *)typed(env, a[3], NULL), (const uint8_t *)typed(env, a[4], NULL),
+                                  (const uint32_t *)typed(env, a[5], NULL), (float *)typed(env, a[6], NULL), n);
+    if (rc != AACFB_OK) return fail(env, ctx, rc);
+    return NULL;
+}
+
+/* swbOffsets(sampleIndex, isShort) -> Uint16Array copy of info.swbOffsets (tables.js:126-154); the JS host
+ * has the reference's own tables, this is for hosts that do not */
+static napi_value js_swb_offsets(napi_env env, napi_callback_info info) {
+    size_t argc = 2; napi_value a[2];
+    NAPI_OK(env, napi_get_cb_info(env, info, &argc, a, NULL, NULL));
+    int32_t si = 0, sh = 0; napi_get_value_int32(env, a[0], &si); napi_get_value_int32(env, a[1], &sh);
+    uint16_t tmp[64];
+    int n = aacfb_get_swb_offsets(si, sh, tmp, 64);
+    if (n < 0) return fail(env, NULL, n);
+    void *data; napi_value ab, out;
+    NAPI_OK(env, napi_create_arraybuffer(env, sizeof(uint16_t) * (size_t)(n + 1), &data, &ab));
+    memcpy(data, tmp, sizeof(uint16_t) * (size_t)(n + 1));
+    NAPI_OK(env, napi_create_typedarray(env, napi_uint16_array, (size_t)(n + 1), ab, 0, &out));
+    return out;
+}
+
 /* filterbankProcess(handle, stream, channel, info u8[8], input f32[1024], output f32[1024]) */
 static napi_value js_filterbank(napi_env env, napi_callback_info info) {
     size_t argc = 6; napi_value a[6];
@@ -124,6 +154,8 @@ static napi_value init(napi_env env, napi_value exports) {
     const napi_property_descriptor props[] = {
         {"create", NULL, js_create, NULL, NULL, NULL, napi_default, NULL},
         {"process", NULL, js_process, NULL, NULL, NULL, napi_default, NULL},
+        {"processStereo", NULL, js_process_stereo, NULL, NULL, NULL, napi_default, NULL},
+        {"swbOffsets", NULL, js_swb_offsets, NULL, NULL, NULL, napi_default, NULL},
         {"filterbankProcess", NULL, js_filterbank, NULL, NULL, NULL, napi_default, NULL},
         {"tnsProcess", NULL, js_tns, NULL, NULL, NULL, napi_default, NULL},
         {"reset", NULL, js_reset, NULL, NULL, NULL, napi_default, NULL},

@@ -40,14 +40,18 @@ WORKLOADS = {
     "config3": (3, 256, 256, 2, "batch=65536 stereo, EIGHT_SHORT_SEQUENCE"),
     "config4": (4, 256, 256, 2, "batch=65536 stereo, LONG + TNS (order 12, all bands), FIXED_AR"),
     "config5": (5, 256, 256, 2, "batch=65536 stereo per GPU, mixed long/short (t mod 16 pattern)"),
+    # config2 with the stereo tools (processMS / processIS) applied on the device
+    "config2_stereo": (2, 256, 256, 2, "config2 + M/S on bands 0-39 and intensity stereo on bands 40-45 of every frame, "
+                                       "applied on the staged spectra"),
 }
 
 
-def algorithmic_bytes(S, T, C, tns_bytes=0):
+def algorithmic_bytes(S, T, C, tns_bytes=0, stereo_bytes=0):
     """4096 B spectrum in + 4096 B PCM out per channel-frame, plus the
-    overlap state read+written once per (stream, channel), plus 8 B side info per channel-frame."""
+    overlap state read+written once per (stream, channel), plus 8 B side info per channel-frame
+    (+ the TNS blob / the 768-byte stereo records where the workload has them)."""
     n_cf = S * T * C
-    return n_cf * 8192 + S * C * 8192 + n_cf * 8 + tns_bytes
+    return n_cf * 8192 + S * C * 8192 + n_cf * 8 + tns_bytes + stereo_bytes
 
 
 def measured_peak():
@@ -195,7 +199,7 @@ def run_ours(args):
         T = args.frames
 
     # --- synthetic batch of this rank (seeded per rank), resident in HBM --------------------
-    sigma = {2: 3.0e5, 3: 1.0e5, 4: 0.75e5, 5: 1.0e5}[cfg]
+    sigma = {2: 3.0e5, 3: 1.0e5, 4: 0.75e5, 5: 1.0e5}[cfg] * (0.5 if args.workload.endswith("_stereo") else 1.0)
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
     spectra = torch.randn((S, T, C, 1024), device=dev, generator=g) * sigma
     side = W.make(cfg, S, T, C, seed=rank, side_only=True)  # info/TNS side data only
@@ -207,6 +211,13 @@ def run_ours(args):
         blob = torch.from_numpy(side["tns_blob"]).to(dev)
         offs = torch.from_numpy(side["tns_offsets"].view(np.int32).copy()).to(dev)
         tns_bytes = int(side["tns_blob"].size)
+    ops_np = ops = None
+    if args.workload.endswith("_stereo"):
+        ops_np = W.joint_stereo_ops(S, T, seed=rank)
+        info_np["stereo_present"][:, :, 0] = 1
+        info = torch.from_numpy(info_np.view(np.uint8).reshape(S, T, C, 8).copy()).to(dev)
+        ops = torch.from_numpy(ops_np.view(np.uint8).reshape(S, T, 768).copy()).to(dev)
+    stereo_bytes = 0 if ops_np is None else int(ops_np.nbytes)
     pcm = torch.empty((S, T, 1024, C), device=dev)
     ctx = A.Context(S, C, side["sample_index"], side["flags"], device=local)
     stream = torch.cuda.current_stream()
@@ -214,7 +225,7 @@ def run_ours(args):
     def step():
         ctx.process_device(spectra.data_ptr(), info.data_ptr(), pcm.data_ptr(), T, stream.cuda_stream,
                            blob.data_ptr() if blob is not None else 0, offs.data_ptr() if offs is not None else 0,
-                           tns_bytes)
+                           tns_bytes, ops.data_ptr() if ops is not None else 0)
 
     def barrier():
         if world > 1:
@@ -257,12 +268,12 @@ def run_ours(args):
         ctx2 = A.Context(S, C, side["sample_index"], side["flags"], device=local)
         e2e_steps = max(2, min(args.steps, 5))
         for _ in range(2):
-            ctx2.process(spec_np, info_np, side["tns_blob"], side["tns_offsets"], out=pcm_np)
+            ctx2.process(spec_np, info_np, side["tns_blob"], side["tns_offsets"], out=pcm_np, stereo_ops=ops_np)
         barrier()
         with ClockSampler(local) as clocks_e2e:
             t0 = time.perf_counter()
             for _ in range(e2e_steps):
-                ctx2.process(spec_np, info_np, side["tns_blob"], side["tns_offsets"], out=pcm_np)
+                ctx2.process(spec_np, info_np, side["tns_blob"], side["tns_offsets"], out=pcm_np, stereo_ops=ops_np)
             torch.cuda.synchronize()
             dt = time.perf_counter() - t0
         ce = clocks_e2e.summary()
@@ -276,7 +287,7 @@ def run_ours(args):
             torch.distributed.all_reduce(te, op=torch.distributed.ReduceOp.MAX)
         e2e_val = world * S * T * e2e_steps / float(te.item())
         assert np.isfinite(pcm_np[0, 0]).all() and np.abs(pcm_np[-1, -1]).max() > 0
-        side_bytes = info_np.nbytes + (tns_bytes + side["tns_offsets"].nbytes if tns_bytes else 0)
+        side_bytes = info_np.nbytes + (tns_bytes + side["tns_offsets"].nbytes if tns_bytes else 0) + stereo_bytes
         e2e = {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(spec_np.nbytes + side_bytes),
                "d2h_bytes_per_step": int(pcm_np.nbytes), "steps": e2e_steps,
                "ms_per_step": float(te.item()) / e2e_steps * 1e3,
@@ -288,7 +299,7 @@ def run_ours(args):
         # synthesis-kernel launch time: each step is one memset + (tns_kernel) + synth_kernel on one
         # stream; event-to-event time of a step is the launch duration the roofline uses
         launch_ms = float(np.mean(per_step))
-        alg = algorithmic_bytes(S, T, C, tns_bytes)
+        alg = algorithmic_bytes(S, T, C, tns_bytes, stereo_bytes)
         achieved = alg / (launch_ms * 1e-3) / 1e9
         traffic = None
         prof = os.path.join(ROOT, "profiles", "traffic.json")

@@ -9,8 +9,10 @@
  *            -> FFT.process  (reference src/fft.js:105-192)
  *  -> interleave + /32768    (reference src/decoder.js:204-213)
  *
- * Everything above it (ADTS / Huffman / ICS bit parse, M/S, IS) stays in the
- * JavaScript host.  The entry points below are exactly what an N-API addon
+ * Everything above it (ADTS / Huffman / ICS bit parse, dequantisation) stays in
+ * the JavaScript host.  The stereo tools that sit between the parse and TNS
+ * (processMS / processIS, decoder.js:337-404) can optionally run on the device
+ * too: aacfb_process_stereo.  The entry points below are exactly what an N-API addon
  * for that path binds; they use plain pointers and sizes
  * only -- no torch, no C++ types.  The library has NO CPU fallback: every
  * compute entry point fails with AACFB_ERR_CUDA when no sm_100 device/kernel
@@ -80,8 +82,33 @@ typedef struct aacfb_frame_info {
     uint8_t shape_cur;       /* info.windowShape[1]                              */
     uint8_t max_sfb;         /* ics.maxSFB (TNS band clamp, tns.js:106)          */
     uint8_t tns_present;     /* ics.tnsPresent (decoder.js:263,309,312)          */
-    uint8_t reserved[3];     /* must be 0                                        */
+    uint8_t stereo_present;  /* LEFT channel of a pair only: the pair-frame has an
+                              * aacfb_stereo_ops record (M/S and/or intensity)    */
+    uint8_t reserved[2];     /* must be 0                                        */
 } aacfb_frame_info;
+
+/* Stereo tools of a channel pair element, applied to the dequantised spectra of
+ * (left, right) BEFORE TNS:
+ *     mid/side          processMS, reference src/decoder.js:379-404
+ *     intensity stereo  processIS, reference src/decoder.js:337-376
+ * The host keeps the band walk (ms_used / bandTypes / sectEnd / scaleFactors are
+ * bit-parse results) and hands over WHAT to do per group of 4 coefficients --
+ * scalefactor-band edges are multiples of 4 for every sample rate and window
+ * length (tables.js:34-124) -- instead of touching the 2 x 1024 coefficients:
+ *     op[i] (coefficients 4i .. 4i+3):  0  untouched
+ *                                       1  l' = l + r, r' = l - r      (decoder.js:395-397)
+ *                                       2+k  r' = l * scale[k]         (decoder.js:360-366,
+ *                                            scale = c * scaleFactors[idx])
+ * Supported for pairs that are channels (2j, 2j+1) of a stream with an even
+ * channel count (stereo: the CPE).  One record per channel PAIR-frame, laid out
+ * [S][T][C/2]; only records whose left channel has stereo_present != 0 are read. */
+#define AACFB_STEREO_NONE 0
+#define AACFB_STEREO_MS   1
+#define AACFB_STEREO_IS   2   /* + index into scale[] */
+typedef struct aacfb_stereo_ops {
+    uint8_t op[256];
+    float   scale[128];
+} aacfb_stereo_ops;             /* 768 bytes */
 
 /* TNS side info is a packed blob, one block per channel-frame that has
  * tns_present != 0, located by tns_offsets[] (byte offsets, 4-byte aligned,
@@ -125,6 +152,15 @@ int aacfb_process(aacfb_ctx *ctx, const float *spectra,
                   const uint8_t *tns_blob, const uint32_t *tns_offsets,
                   float *pcm, int n_frames);
 
+/* aacfb_process with the stereo tools of the pair elements run on the device as
+ * well: spectra are ics.data BEFORE processMS / processIS (decoder.js:300-307),
+ * stereo_ops [S][T][C/2] as described above (NULL = none: plain aacfb_process). */
+int aacfb_process_stereo(aacfb_ctx *ctx, const float *spectra,
+                         const aacfb_frame_info *info,
+                         const aacfb_stereo_ops *stereo_ops,
+                         const uint8_t *tns_blob, const uint32_t *tns_offsets,
+                         float *pcm, int n_frames);
+
 /* Same contract with DEVICE pointers, enqueued on `stream` (a cudaStream_t
  * passed as void*; NULL = the legacy default stream).  Asynchronous.
  * tns_blob_bytes is the size of the device blob (0 if none). */
@@ -133,6 +169,13 @@ int aacfb_process_device(aacfb_ctx *ctx, const float *d_spectra,
                          const uint8_t *d_tns_blob, const uint32_t *d_tns_offsets,
                          size_t tns_blob_bytes,
                          float *d_pcm, int n_frames, void *stream);
+
+int aacfb_process_device_stereo(aacfb_ctx *ctx, const float *d_spectra,
+                                const aacfb_frame_info *d_info,
+                                const aacfb_stereo_ops *d_stereo_ops,
+                                const uint8_t *d_tns_blob, const uint32_t *d_tns_offsets,
+                                size_t tns_blob_bytes,
+                                float *d_pcm, int n_frames, void *stream);
 
 /* The inner seam, one channel-frame at a time, HOST buffers:
  *     filterBank.process(info, input, output, channel)  filter_bank.js:88
@@ -164,6 +207,10 @@ uint64_t aacfb_launch_count(const aacfb_ctx *ctx);
  * 3 MDCT twiddles 256 [128], 4 sine1024, 5 kbd1024, 6 sine128, 7 kbd128.
  * Returns the number of floats written or a negative error. */
 int aacfb_get_table(int which, float *dst, int capacity);
+/* Scalefactor-band offsets info.swbOffsets (tables.js:126-154, ics.js:301,307) of one
+ * sample rate: is_short = 0 -> SWB_OFFSET_1024[sample_index], 1 -> SWB_OFFSET_128.
+ * Returns the number of bands (swbCount); dst receives swbCount + 1 offsets. */
+int aacfb_get_swb_offsets(int sample_index, int is_short, uint16_t *dst, int capacity);
 
 #ifdef __cplusplus
 }

@@ -417,6 +417,87 @@ static void tns_process(const aacfb_frame_info *info, const uint8_t *block, size
     }
 }
 
+/* ------------------------------------------------------------ stereo tools */
+
+/* What processMS / processIS read of a CPEElement and its two ICStreams
+ * (cpe.js:24-75, ics.js:25-34,270-310).  Index 0 = left, 1 = right. */
+typedef struct oracle_cpe {
+    int32_t common_window, mask_present;     /* element.commonWindow, element.maskPresent */
+    uint8_t ms_used[128];                    /* element.ms_used[idx]                      */
+    int32_t window_sequence[2];              /* info.windowSequence (selects swbOffsets)  */
+    int32_t group_count[2];                  /* info.groupCount                           */
+    int32_t group_length[2][8];              /* info.groupLength[g]                       */
+    int32_t max_sfb[2];                      /* info.maxSFB                               */
+    int32_t band_types[2][120];              /* ics.bandTypes[idx]                        */
+    int32_t sect_end[2][120];                /* ics.sectEnd[idx]                          */
+    float   scale_factors[2][120];           /* ics.scaleFactors[idx] (Float32Array)      */
+} oracle_cpe;
+
+enum { NOISE_BT = 13, INTENSITY_BT2 = 14, INTENSITY_BT = 15 };  /* ics.js:39-41 */
+
+static const uint16_t *cpe_offsets(const oracle_cpe *e, int ch, int sample_index) {
+    /* ics.js:300-309: EIGHT_SHORT -> SWB_OFFSET_128, else SWB_OFFSET_1024 */
+    return e->window_sequence[ch] == AACFB_EIGHT_SHORT_SEQUENCE ? SWB_OFFSET_128[sample_index].off
+                                                                : SWB_OFFSET_1024[sample_index].off;
+}
+
+/* decoder.js:379-404 */
+static void process_ms(const oracle_cpe *e, int sample_index, float *left, float *right) {
+    const uint16_t *offsets = cpe_offsets(e, 0, sample_index);   /* ics = element.left */
+    const int windowGroups = e->group_count[0], maxSFB = e->max_sfb[0];
+    int groupOff = 0, idx = 0;
+    for (int g = 0; g < windowGroups; g++) {
+        for (int i = 0; i < maxSFB; i++, idx++) {
+            if (e->ms_used[idx] && e->band_types[0][idx] < NOISE_BT && e->band_types[1][idx] < NOISE_BT) {
+                for (int w = 0; w < e->group_length[0][g]; w++) {
+                    const int off = groupOff + w * 128 + offsets[i];
+                    for (int j = 0; j < offsets[i + 1] - offsets[i]; j++) {
+                        const double t = (double)left[off + j] - (double)right[off + j];
+                        left[off + j] = (float)((double)left[off + j] + (double)right[off + j]);
+                        right[off + j] = (float)t;
+                    }
+                }
+            }
+        }
+        groupOff += e->group_length[0][g] * 128;
+    }
+}
+
+/* decoder.js:337-376 */
+static void process_is(const oracle_cpe *e, int sample_index, const float *left, float *right) {
+    const uint16_t *offsets = cpe_offsets(e, 1, sample_index);   /* ics = element.right */
+    const int windowGroups = e->group_count[1], maxSFB = e->max_sfb[1];
+    const int32_t *bandTypes = e->band_types[1], *sectEnd = e->sect_end[1];
+    int idx = 0, groupOff = 0;
+    for (int g = 0; g < windowGroups; g++) {
+        for (int i = 0; i < maxSFB;) {
+            const int end = sectEnd[idx];
+            if (bandTypes[idx] == INTENSITY_BT || bandTypes[idx] == INTENSITY_BT2) {
+                for (; i < end; i++, idx++) {
+                    double c = bandTypes[idx] == INTENSITY_BT ? 1 : -1;
+                    if (e->mask_present) c *= e->ms_used[idx] ? -1 : 1;
+                    const double scale = c * (double)e->scale_factors[1][idx];
+                    for (int w = 0; w < e->group_length[1][g]; w++) {
+                        const int off = groupOff + w * 128 + offsets[i], len = offsets[i + 1] - offsets[i];
+                        for (int j = 0; j < len; j++) right[off + j] = (float)((double)left[off + j] * scale);
+                    }
+                }
+            } else {
+                idx += end - i;
+                i = end;
+            }
+        }
+        groupOff += e->group_length[1][g] * 128;
+    }
+}
+
+/* processPair's stereo part, decoder.js:300-307: M/S only with a common window and a mask, then IS. */
+__attribute__((visibility("default")))
+void aacfb_oracle_stereo(const oracle_cpe *e, int sample_index, float *left, float *right) {
+    if (e->common_window && e->mask_present) process_ms(e, sample_index, left, right);
+    process_is(e, sample_index, left, right);
+}
+
 /* --------------------------------------------------------- exported entry */
 
 #define API __attribute__((visibility("default")))

@@ -17,7 +17,7 @@ _SO = os.path.join(_HERE, "libaacfb_oracle.so")
 
 INFO_DTYPE = np.dtype(
     [("window_sequence", "u1"), ("shape_prev", "u1"), ("shape_cur", "u1"),
-     ("max_sfb", "u1"), ("tns_present", "u1"), ("reserved", "u1", (3,))])
+     ("max_sfb", "u1"), ("tns_present", "u1"), ("stereo_present", "u1"), ("reserved", "u1", (2,))])
 assert INFO_DTYPE.itemsize == 8
 
 TNS_AS_SHIPPED, TNS_FIXED_AR, TNS_FIXED_MA = 0, 1, 2
@@ -52,6 +52,8 @@ def lib():
         L.aacfb_oracle_tns.restype = None
         L.aacfb_oracle_process.argtypes = [C.c_void_p] * 6 + [C.c_int] * 4 + [C.c_uint32, C.c_int]
         L.aacfb_oracle_process.restype = C.c_int
+        L.aacfb_oracle_stereo.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.aacfb_oracle_stereo.restype = None
         L.aacfb_oracle_init()
         _lib = L
     return _lib
@@ -139,3 +141,20 @@ def process(spectra, info, tns_blob=None, tns_offsets=None, overlap=None, *, sam
                                     S, T, Cn, sample_index, flags, n_threads)
     assert rc == 0
     return pcm, overlap
+
+
+# What processMS / processIS read of a CPEElement and its two ICStreams (struct oracle_cpe).
+CPE_DTYPE = np.dtype([("common_window", "i4"), ("mask_present", "i4"), ("ms_used", "u1", (128,)),
+                      ("window_sequence", "i4", (2,)), ("group_count", "i4", (2,)), ("group_length", "i4", (2, 8)),
+                      ("max_sfb", "i4", (2,)), ("band_types", "i4", (2, 120)), ("sect_end", "i4", (2, 120)),
+                      ("scale_factors", "f4", (2, 120))])
+
+
+def stereo(cpe: np.ndarray, sample_index: int, left: np.ndarray, right: np.ndarray):
+    """processPair's stereo part (decoder.js:300-307): processMS (:379-404) if commonWindow and
+    maskPresent, then processIS (:337-376), on copies of `left` / `right` (1024 f32 each)."""
+    cpe = np.ascontiguousarray(cpe, CPE_DTYPE)
+    l = np.ascontiguousarray(left, np.float32).copy()
+    r = np.ascontiguousarray(right, np.float32).copy()
+    lib().aacfb_oracle_stereo(_p(cpe), sample_index, _p(l), _p(r))
+    return l, r

@@ -47,6 +47,15 @@ class Reference:
         m = re.search(r"// Interleave channels\n(.*?)\n\s*return output;", dec, re.S)
         assert m, "decoder.js interleave block not found"
         self.interleave_src = m.group(1)
+        # processIS / processMS (decoder.js:337-404): the two prototype methods, cut out of the file
+        # (decoder.js itself cannot be required: it needs the `av` peer dependency at load time)
+        fns = {}
+        for name in ("processIS", "processMS"):
+            m = re.search(r"this\.prototype\.%s = (function\(element, left, right\) \{\n.*?\n    \});" % name, dec, re.S)
+            assert m, f"decoder.js {name} not found"
+            fns[name] = m.group(1)
+        self.stereo_scope = self.rt.run("var ICStream = require('./ics');\nvar processIS = %s;\nvar processMS = %s;\n"
+                                        % (fns["processIS"], fns["processMS"]))
 
     def _load_text(self, text):
         module, exports = J.JSObject(J.OBJECT_PROTO), J.JSObject(J.OBJECT_PROTO)
@@ -102,6 +111,27 @@ class Reference:
         d = J.float32array(data)
         self.TNS.get("prototype").get("process").call(tns, [ics, d, bool(decode)])
         return d.a.copy()
+
+    def stereo(self, cpe, sample_index, left, right):
+        """processPair's stereo part, decoder.js:294-301: processMS if commonWindow && maskPresent, then
+        processIS, on copies of left / right; `cpe` is a tools/workloads.CPE_DTYPE record."""
+        def ics(c):
+            short = int(cpe["window_sequence"][c]) == 2
+            info = J.obj(windowSequence=int(cpe["window_sequence"][c]), groupCount=int(cpe["group_count"][c]),
+                         maxSFB=int(cpe["max_sfb"][c]), groupLength=J.int32array(cpe["group_length"][c]),
+                         swbOffsets=J.get_member(self.tables.get("SWB_OFFSET_128" if short else "SWB_OFFSET_1024"),
+                                                 float(sample_index)))
+            return J.obj(info=info, bandTypes=J.int32array(cpe["band_types"][c]), sectEnd=J.int32array(cpe["sect_end"][c]),
+                         scaleFactors=J.float32array(cpe["scale_factors"][c]))
+        element = J.obj(commonWindow=bool(cpe["common_window"]), maskPresent=bool(cpe["mask_present"]),
+                        ms_used=J.JSArray([bool(v) for v in cpe["ms_used"]]), left=ics(0), right=ics(1))
+        if cpe["common_window"]:
+            element.props["right"].props["info"] = element.props["left"].props["info"]  # cpe.js:41
+        l, r = J.float32array(left), J.float32array(right)
+        if cpe["common_window"] and cpe["mask_present"]:
+            self.stereo_scope["processMS"].call(J.UNDEF, [element, l, r])
+        self.stereo_scope["processIS"].call(J.UNDEF, [element, l, r])
+        return l.a.copy(), r.a.copy()
 
     def interleave(self, chans):
         """decoder.js:204-213 on this.data = chans (list of Float32Array rows)."""
@@ -161,5 +191,42 @@ def main():
         print(name, pcm.shape, float(np.abs(pcm).max()))
 
 
+STEREO_SEQS = [(0, 0), (2, 2), (0, 2), (2, 0), (1, 1), (3, 3), (1, 2), (3, 0)]
+
+
+def stereo_elements(n=48, seed=77, sample_index=4):
+    """The seeded channel pair elements of tests/golden/stereo/jsref_stereo.npz."""
+    rng = np.random.default_rng(seed)
+    cpe = np.zeros(n, W.CPE_DTYPE)
+    for k in range(n):
+        a, b = STEREO_SEQS[k % len(STEREO_SEQS)]
+        cpe[k] = W.random_cpe(rng, a, b, sample_index, common_window=None if k % 3 else True, p_intensity=0.4)
+    left = (rng.standard_normal((n, 1024)) * 1e4).astype(np.float32)
+    right = (rng.standard_normal((n, 1024)) * 1e4).astype(np.float32)
+    return cpe, left, right
+
+
+def main_stereo():
+    """processMS / processIS (decoder.js:337-404) run by the interpreter: (i) per element, (ii) a whole
+    stereo stream: stereo tools -> filter_bank.process -> interleave."""
+    out_dir = os.path.join(ROOT, "tests", "golden", "stereo")
+    os.makedirs(out_dir, exist_ok=True)
+    ref = Reference()
+    cpe, left, right = stereo_elements()
+    ol, orr = np.empty_like(left), np.empty_like(right)
+    for k in range(len(cpe)):
+        ol[k], orr[k] = ref.stereo(cpe[k], 4, left[k], right[k])
+    S, T, seed = 2, 12, 78
+    case = W.random_stereo_case(S, T, np.random.default_rng(seed))
+    sp = case["spectra"].copy()
+    for s in range(S):
+        for t in range(T):
+            sp[s, t, 0], sp[s, t, 1] = ref.stereo(case["cpe"][s, t], 4, sp[s, t, 0], sp[s, t, 1])
+    pcm, ovl = ref.process(sp, case["info"], None, None, 4, 0)
+    np.savez_compressed(os.path.join(out_dir, "jsref_stereo.npz"), out_left=ol, out_right=orr, pcm=pcm, overlap=ovl,
+                        meta=np.array([len(cpe), 77, S, T, seed]))
+    print("stereo", ol.shape, pcm.shape, int((ol != left).any(axis=1).sum()), int((orr != right).any(axis=1).sum()))
+
+
 if __name__ == "__main__":
-    main()
+    main_stereo() if sys.argv[1:] == ["stereo"] else main()

@@ -10,7 +10,7 @@ import numpy as np
 
 INFO_DTYPE = np.dtype(
     [("window_sequence", "u1"), ("shape_prev", "u1"), ("shape_cur", "u1"),
-     ("max_sfb", "u1"), ("tns_present", "u1"), ("reserved", "u1", (3,))])
+     ("max_sfb", "u1"), ("tns_present", "u1"), ("stereo_present", "u1"), ("reserved", "u1", (2,))])
 
 ONLY_LONG, LONG_START, EIGHT_SHORT, LONG_STOP = 0, 1, 2, 3
 
@@ -138,3 +138,107 @@ def random_case(S, T, C, rng, tns_mode=0, sigma=1e5, short_tns_orders=True):
             blocks.append(tns_block(nf, filters))
         blob, offs = pack_tns(blocks)
     return dict(spectra=spectra, info=info, tns_blob=blob, tns_offsets=offs, flags=tns_mode, sample_index=4)
+
+
+# ------------------------------------------------------------------ stereo tools (CPE side info)
+# What processMS / processIS read of a CPEElement and its two ICStreams (reference src/cpe.js:24-75,
+# src/ics.js:25-34,270-310); index 0 = left, 1 = right.  Same layout as struct oracle_cpe.
+CPE_DTYPE = np.dtype([("common_window", "i4"), ("mask_present", "i4"), ("ms_used", "u1", (128,)),
+                      ("window_sequence", "i4", (2,)), ("group_count", "i4", (2,)), ("group_length", "i4", (2, 8)),
+                      ("max_sfb", "i4", (2,)), ("band_types", "i4", (2, 120)), ("sect_end", "i4", (2, 120)),
+                      ("scale_factors", "f4", (2, 120))])
+SWB_LONG_COUNT = [41, 41, 47, 49, 49, 51, 47, 47, 43, 43, 43, 40]    # tables.js:161-163
+SWB_SHORT_COUNT = [12, 12, 12, 14, 14, 14, 15, 15, 15, 15, 15, 15]   # tables.js:157-159
+NOISE_BT, INTENSITY_BT2, INTENSITY_BT = 13, 14, 15                   # ics.js:39-41
+
+
+def _sections(rng, n_groups, max_sfb, p_intensity):
+    """band_types / sect_end / scale_factors: per group, sections of random length with one band
+    type each, the way ics.js:130-170 leaves them (sect_end = end band of the section, per band)."""
+    bt, se = np.zeros(120, np.int32), np.zeros(120, np.int32)
+    idx = 0
+    for _ in range(n_groups):
+        k = 0
+        while k < max_sfb:
+            end = min(max_sfb, k + int(rng.integers(1, 9)))
+            r = rng.random()
+            t = INTENSITY_BT if r < p_intensity / 2 else INTENSITY_BT2 if r < p_intensity else \
+                NOISE_BT if r < p_intensity + 0.1 else int(rng.integers(0, 12))
+            bt[idx:idx + end - k] = t
+            se[idx:idx + end - k] = end
+            idx += end - k
+            k = end
+    sf = (0.5 ** (rng.integers(-40, 40, 120) / 4.0)).astype(np.float32)
+    return bt, se, sf
+
+
+def _random_ics(rng, seq, sample_index, p_intensity, like=None):
+    """(group_count, group_length[8], max_sfb, band_types, sect_end, scale_factors) of one ICStream;
+    `like`: take the groups and maxSFB of that stream (common window)."""
+    if like is not None:
+        n_groups, gl, max_sfb = like[0], like[1], like[2]
+    else:
+        if seq == EIGHT_SHORT:
+            cuts = np.sort(rng.choice(np.arange(1, 8), size=int(rng.integers(0, 8)), replace=False))
+            glen = np.diff(np.concatenate([[0], cuts, [8]])).astype(np.int32)
+            max_sfb = int(rng.integers(0, SWB_SHORT_COUNT[sample_index] + 1))
+        else:
+            glen = np.array([1], np.int32)
+            max_sfb = int(rng.integers(0, SWB_LONG_COUNT[sample_index] + 1))
+        n_groups, gl = len(glen), np.zeros(8, np.int32)
+        gl[:n_groups] = glen
+    return (n_groups, gl, max_sfb) + _sections(rng, n_groups, max_sfb, p_intensity)
+
+
+def random_cpe(rng, seq_left, seq_right, sample_index=4, common_window=None, p_intensity=0.3):
+    """One random channel pair element for the window sequences given (common window forces the
+    left one on both channels, cpe.js:40-42)."""
+    e = np.zeros((), CPE_DTYPE)
+    cw = bool(rng.integers(0, 2)) if common_window is None else bool(common_window)
+    if seq_left != seq_right:
+        cw = False
+    e["common_window"] = cw
+    mask = int(rng.integers(0, 3)) if cw else 0          # cpe.js:44-66
+    e["mask_present"] = int(mask != 0)
+    e["ms_used"] = rng.integers(0, 2, 128) if mask == 1 else (1 if mask == 2 else 0)
+    left = _random_ics(rng, seq_left, sample_index, 0.0)  # intensity codebooks occur in the right channel
+    right = _random_ics(rng, seq_right, sample_index, p_intensity)
+    if cw:   # right.info = left.info: groups and maxSFB are shared, the sections are not
+        right = _random_ics(rng, seq_left, sample_index, p_intensity, like=left)
+    for c, ics in enumerate((left, right)):
+        e["window_sequence"][c] = seq_left if (cw or c == 0) else seq_right
+        e["group_count"][c], e["group_length"][c], e["max_sfb"][c] = ics[0], ics[1], ics[2]
+        e["band_types"][c], e["sect_end"][c], e["scale_factors"][c] = ics[3], ics[4], ics[5]
+    return e
+
+
+def random_stereo_case(S, T, rng, tns_mode=0, sigma=1e5, sample_index=4):
+    """random_case for stereo streams plus one CPE per pair-frame: spectra are ics.data BEFORE
+    processMS / processIS.  Returns the case dict with `cpe` [S][T] (CPE_DTYPE)."""
+    case = random_case(S, T, 2, rng, tns_mode=tns_mode, sigma=sigma)
+    cpe = np.zeros((S, T), CPE_DTYPE)
+    for s in range(S):
+        for t in range(T):
+            ws = case["info"]["window_sequence"][s, t]
+            cpe[s, t] = random_cpe(rng, int(ws[0]), int(ws[1]), sample_index)
+    case["cpe"] = cpe
+    case["sample_index"] = sample_index
+    return case
+
+
+STEREO_DTYPE = np.dtype([("op", "u1", (256,)), ("scale", "f4", (128,))])   # aacfb_stereo_ops
+
+
+def joint_stereo_ops(S, T, seed=0):
+    """Stereo side info of a "joint stereo" batch for bench.py: every frame of every stream is a
+    common-window pair with M/S on scalefactor bands 0..39 (coefficients 0..511, ms_used all set)
+    and intensity stereo on bands 40..45 (512..767, six scales), the rest untouched -- long-window
+    band edges of 44.1 kHz (tables.js:64-68).  Returns ops [S][T][1] (STEREO_DTYPE)."""
+    rng = np.random.default_rng(seed)
+    ops = np.zeros((S, T, 1), STEREO_DTYPE)
+    edges = [512, 544, 576, 608, 640, 672, 704]   # swbOffsets[40..46] at 44.1/48 kHz
+    ops["op"][..., : 512 // 4] = 1
+    for k in range(6):
+        ops["op"][..., edges[k] // 4: edges[k + 1] // 4] = 2 + k
+    ops["scale"][..., :6] = (0.5 ** (rng.integers(-8, 8, (S, T, 1, 6)) / 4.0)).astype(np.float32)
+    return ops
