@@ -21,7 +21,7 @@ using namespace aacfb;
 
 namespace {
 
-constexpr int kLanes = 2;        // host-path pipeline depth (H2D | kernel | D2H overlap)
+constexpr int kLanes = 4;        // host-path pipeline: sub-batches in flight (H2D | kernel | D2H overlap)
 constexpr int kCounters = 64;
 
 thread_local char g_err[256] = "";
@@ -474,17 +474,19 @@ API int aacfb_process_stereo(aacfb_ctx *ctx, const float *spectra, const aacfb_f
     }
     // Sub-batches of whole streams, two in flight: the copy-in of one overlaps
     // the kernel and copy-out of the other (PCIe is the bottleneck end to end).
-    int n_sub = std::min(S, 8);
+    int n_sub = std::min(S, 8), lanes = 2;
+    if (const char *env = std::getenv("AACFB_SUB_BATCHES")) n_sub = std::max(1, std::min(S, std::atoi(env)));   // tuning aids
+    if (const char *env = std::getenv("AACFB_LANES")) lanes = std::atoi(env) >= 4 ? 4 : std::atoi(env) >= 2 ? 2 : 1;  // divisors of the counter ring
     if ((size_t)S * per_stream * 4096 < (size_t)(8u << 20)) n_sub = 1;
     const int s_per = (S + n_sub - 1) / n_sub;
-    for (int i = 0; i < kLanes; ++i) {
+    for (int i = 0; i < lanes; ++i) {
         if ((rc = grow_lane(ctx, ctx->lane[i], (size_t)s_per * per_stream, tns_on && blob_bytes)) != AACFB_OK) return rc;
         if (stereo_ops && (rc = grow_lane_stereo(ctx, ctx->lane[i], (size_t)s_per * per_stream,
                                                  stereo_needs_prepass(C, tns_on && blob_bytes))) != AACFB_OK)
             return rc;
     }
     int li = 0;
-    for (int s0 = 0; s0 < S; s0 += s_per, li ^= 1) {
+    for (int s0 = 0; s0 < S; s0 += s_per, li = (li + 1) % lanes) {
         Lane &ln = ctx->lane[li];
         const int sn = std::min(s_per, S - s0);
         const size_t n_cf = (size_t)sn * per_stream, off = (size_t)s0 * per_stream;

@@ -38,6 +38,59 @@ AACFB_HD float f_sub(float a, float b) { volatile float r = a - b; return r; }
 AACFB_HD float f_fma(float a, float b, float c) { return fmaf(a, b, c); }
 #endif
 
+// ---- packed pairs: the same quantity of chain 0 (.x) and chain 1 (.y) -----------------------
+// A worker runs identical arithmetic on its two chains with shared twiddles and windows, which
+// is the shape of sm_100's packed FP32 instructions (PTX fma/mul/add/sub.rn.f32x2 -> SASS FFMA2 /
+// FMUL2 / FADD2: one issue slot for both chains, per-lane IEEE rounding identical to the scalar
+// instruction, operand negation and scalar broadcast are free operand modifiers).  The host
+// build (CPU emulation in tests) performs the two scalar operations instead: same bits.
+struct F2 {
+    float x, y;
+};
+#if defined(__CUDA_ARCH__)
+AACFB_HD unsigned long long f2_bits(F2 v) {
+    unsigned long long d;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(v.x), "f"(v.y));
+    return d;
+}
+AACFB_HD F2 f2_from(unsigned long long d) {
+    F2 v;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(v.x), "=f"(v.y) : "l"(d));
+    return v;
+}
+AACFB_HD F2 f_fma(F2 a, F2 b, F2 c) {
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(f2_bits(a)), "l"(f2_bits(b)), "l"(f2_bits(c)));
+    return f2_from(d);
+}
+AACFB_HD F2 f_mul(F2 a, F2 b) {
+    unsigned long long d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(f2_bits(a)), "l"(f2_bits(b)));
+    return f2_from(d);
+}
+AACFB_HD F2 f_add(F2 a, F2 b) {
+    unsigned long long d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(f2_bits(a)), "l"(f2_bits(b)));
+    return f2_from(d);
+}
+AACFB_HD F2 f_sub(F2 a, F2 b) {
+    unsigned long long d;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(f2_bits(a)), "l"(f2_bits(b)));
+    return f2_from(d);
+}
+#else
+AACFB_HD F2 f_fma(F2 a, F2 b, F2 c) { return F2{f_fma(a.x, b.x, c.x), f_fma(a.y, b.y, c.y)}; }
+AACFB_HD F2 f_mul(F2 a, F2 b) { return F2{f_mul(a.x, b.x), f_mul(a.y, b.y)}; }
+AACFB_HD F2 f_add(F2 a, F2 b) { return F2{f_add(a.x, b.x), f_add(a.y, b.y)}; }
+AACFB_HD F2 f_sub(F2 a, F2 b) { return F2{f_sub(a.x, b.x), f_sub(a.y, b.y)}; }
+#endif
+AACFB_HD F2 f_neg(F2 a) { return F2{-a.x, -a.y}; }
+AACFB_HD float f_neg(float a) { return -a; }
+// a scalar (twiddle, window value) applied to both chains
+AACFB_HD F2 f_fma(F2 a, float s, F2 c) { return f_fma(a, F2{s, s}, c); }
+AACFB_HD F2 f_fma(float s, F2 a, F2 c) { return f_fma(F2{s, s}, a, c); }
+AACFB_HD F2 f_mul(F2 a, float s) { return f_mul(a, F2{s, s}); }
+
 constexpr int kWorkerThreads = 64;
 constexpr int kRowFloats = 1024;        // one channel-frame of spectrum
 constexpr int kStageFloats = 2 * 1024;  // two chains per stage
@@ -79,24 +132,28 @@ struct Ovl {
 // lo = a + t takes two FMAs per component; hi = a - t is formed as 2a - lo (one FMA, 2a is
 // exact): 6 instead of 8 FMAs per butterfly, at the price of lo's rounding error (<= 1 ulp of
 // lo) reappearing in hi -- well inside the parity budget (tests measure ~3e-7 of 1e-5).
-AACFB_HD void bfly(float &ar, float &ai, float &br, float &bi, float wr, float wi) {
-    const float lr = f_fma(br, wr, f_fma(-bi, wi, ar));
-    const float li = f_fma(br, wi, f_fma(bi, wr, ai));
-    const float hr = f_fma(2.0f, ar, -lr);
-    const float hi = f_fma(2.0f, ai, -li);
+// V = float (one chain) or F2 (both chains of the worker at once).
+template <class V>
+AACFB_HD void bfly(V &ar, V &ai, V &br, V &bi, float wr, float wi) {
+    const V lr = f_fma(br, wr, f_fma(f_neg(bi), wi, ar));
+    const V li = f_fma(br, wi, f_fma(bi, wr, ai));
+    const V hr = f_fma(2.0f, ar, f_neg(lr));
+    const V hi = f_fma(2.0f, ai, f_neg(li));
     ar = lr; ai = li; br = hr; bi = hi;
 }
-AACFB_HD void bfly1(float &ar, float &ai, float &br, float &bi) {  // w = (1, 0): exact in the reference too
-    const float lr = f_add(ar, br), li = f_add(ai, bi);
-    const float hr = f_sub(ar, br), hi = f_sub(ai, bi);
+template <class V>
+AACFB_HD void bfly1(V &ar, V &ai, V &br, V &bi) {  // w = (1, 0): exact in the reference too
+    const V lr = f_add(ar, br), li = f_add(ai, bi);
+    const V hr = f_sub(ar, br), hi = f_sub(ai, bi);
     ar = lr; ai = li; br = hr; bi = hi;
 }
 // fft.js:140-170, inverse branch: the fused first two stages on 4 points.
-AACFB_HD void base4(float *r, float *i) {
-    const float a0 = f_add(r[0], r[1]), a1 = f_add(i[0], i[1]);
-    const float b0 = f_add(r[2], r[3]), b1 = f_add(i[2], i[3]);
-    const float c0 = f_sub(r[0], r[1]), c1 = f_sub(i[0], i[1]);
-    const float d0 = f_sub(r[2], r[3]), d1 = f_sub(i[2], i[3]);
+template <class V>
+AACFB_HD void base4(V *r, V *i) {
+    const V a0 = f_add(r[0], r[1]), a1 = f_add(i[0], i[1]);
+    const V b0 = f_add(r[2], r[3]), b1 = f_add(i[2], i[3]);
+    const V c0 = f_sub(r[0], r[1]), c1 = f_sub(i[0], i[1]);
+    const V d0 = f_sub(r[2], r[3]), d1 = f_sub(i[2], i[3]);
     r[0] = f_add(a0, b0); i[0] = f_add(a1, b1);
     r[2] = f_sub(a0, b0); i[2] = f_sub(a1, b1);
     r[1] = f_sub(c0, d1); i[1] = f_add(c1, d0);
@@ -105,34 +162,74 @@ AACFB_HD void base4(float *r, float *i) {
 
 // Stages 1-3 on 8 consecutive array positions (regs indexed by position&7).
 // wA = roots[k * L/8], k = 0..3 (fft.js:173-178 with i = 4).
-template <int C0, int NCH>
+// Both chains of a worker as packed pairs (registers only: pure renaming).
+struct Pts2 {
+    F2 r[8], i[8];
+};
+AACFB_HD Pts2 pts_pack(const Pts &z) {
+    Pts2 p;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) { p.r[q] = F2{z.r[0][q], z.r[1][q]}; p.i[q] = F2{z.i[0][q], z.i[1][q]}; }
+    return p;
+}
+AACFB_HD void pts_unpack(const Pts2 &p, Pts &z) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) { z.r[0][q] = p.r[q].x; z.r[1][q] = p.r[q].y; z.i[0][q] = p.i[q].x; z.i[1][q] = p.i[q].y; }
+}
+
+// PK: run the two chains as packed pairs (NCH == 2 only).
+template <int C0, int NCH, bool PK>
 AACFB_HD void pass_a(Pts &z, const float2 *wA) {
+    if constexpr (PK && NCH == 2) {
+        Pts2 p = pts_pack(z);
+        base4(&p.r[0], &p.i[0]);
+        base4(&p.r[4], &p.i[4]);
+        bfly1(p.r[0], p.i[0], p.r[4], p.i[4]);
 #pragma unroll
-    for (int c = C0; c < C0 + NCH; ++c) {
-        base4(&z.r[c][0], &z.i[c][0]);
-        base4(&z.r[c][4], &z.i[c][4]);
-        bfly1(z.r[c][0], z.i[c][0], z.r[c][4], z.i[c][4]);
+        for (int k = 1; k < 4; ++k) bfly(p.r[k], p.i[k], p.r[4 + k], p.i[4 + k], wA[k].x, wA[k].y);
+        pts_unpack(p, z);
+    } else {
 #pragma unroll
-        for (int k = 1; k < 4; ++k) bfly(z.r[c][k], z.i[c][k], z.r[c][4 + k], z.i[c][4 + k], wA[k].x, wA[k].y);
+        for (int c = C0; c < C0 + NCH; ++c) {
+            base4(&z.r[c][0], &z.i[c][0]);
+            base4(&z.r[c][4], &z.i[c][4]);
+            bfly1(z.r[c][0], z.i[c][0], z.r[c][4], z.i[c][4]);
+#pragma unroll
+            for (int k = 1; k < 4; ++k) bfly(z.r[c][k], z.i[c][k], z.r[c][4 + k], z.i[c][4 + k], wA[k].x, wA[k].y);
+        }
     }
 }
 
 // Three stages on 8 points whose array positions differ in three consecutive
 // bits (regs indexed by those bits).  tw[0] serves the first stage, tw[1..2]
 // the second, tw[3..6] the third (see SynthTables::twB/twC/twS).
-template <int C0, int NCH>
+template <int C0, int NCH, bool PK>
 AACFB_HD void pass_3stage(Pts &z, const float2 *tw) {
+    if constexpr (PK && NCH == 2) {
+        Pts2 p = pts_pack(z);
 #pragma unroll
-    for (int c = C0; c < C0 + NCH; ++c) {
-#pragma unroll
-        for (int q = 0; q < 8; q += 2) bfly(z.r[c][q], z.i[c][q], z.r[c][q + 1], z.i[c][q + 1], tw[0].x, tw[0].y);
+        for (int q = 0; q < 8; q += 2) bfly(p.r[q], p.i[q], p.r[q + 1], p.i[q + 1], tw[0].x, tw[0].y);
 #pragma unroll
         for (int q = 0; q < 8; q += 4) {
-            bfly(z.r[c][q], z.i[c][q], z.r[c][q + 2], z.i[c][q + 2], tw[1].x, tw[1].y);
-            bfly(z.r[c][q + 1], z.i[c][q + 1], z.r[c][q + 3], z.i[c][q + 3], tw[2].x, tw[2].y);
+            bfly(p.r[q], p.i[q], p.r[q + 2], p.i[q + 2], tw[1].x, tw[1].y);
+            bfly(p.r[q + 1], p.i[q + 1], p.r[q + 3], p.i[q + 3], tw[2].x, tw[2].y);
         }
 #pragma unroll
-        for (int q = 0; q < 4; ++q) bfly(z.r[c][q], z.i[c][q], z.r[c][q + 4], z.i[c][q + 4], tw[3 + q].x, tw[3 + q].y);
+        for (int q = 0; q < 4; ++q) bfly(p.r[q], p.i[q], p.r[q + 4], p.i[q + 4], tw[3 + q].x, tw[3 + q].y);
+        pts_unpack(p, z);
+    } else {
+#pragma unroll
+        for (int c = C0; c < C0 + NCH; ++c) {
+#pragma unroll
+            for (int q = 0; q < 8; q += 2) bfly(z.r[c][q], z.i[c][q], z.r[c][q + 1], z.i[c][q + 1], tw[0].x, tw[0].y);
+#pragma unroll
+            for (int q = 0; q < 8; q += 4) {
+                bfly(z.r[c][q], z.i[c][q], z.r[c][q + 2], z.i[c][q + 2], tw[1].x, tw[1].y);
+                bfly(z.r[c][q + 1], z.i[c][q + 1], z.r[c][q + 3], z.i[c][q + 3], tw[2].x, tw[2].y);
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) bfly(z.r[c][q], z.i[c][q], z.r[c][q + 4], z.i[c][q + 4], tw[3 + q].x, tw[3 + q].y);
+        }
     }
 }
 
@@ -145,17 +242,24 @@ AACFB_HD int passb_blo(int v) { return v & 7; }
 
 // Pre-twiddle (mdct.js:73-76) straight from the staged spectrum row into the
 // bit-reversed register order pass A needs: reg q <- input n = u + 64*brev3(q).
-template <int C0, int NCH>
+template <int C0, int NCH, bool PK>
 AACFB_HD void long_load(int u, const float *const *row, const float2 *cs2048, Pts &z) {
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
         const int n = u + 64 * brev3(q);
         const float2 cs = cs2048[n];
+        if constexpr (PK && NCH == 2) {
+            const F2 x0{row[0][2 * n], row[1][2 * n]}, x1{row[0][1023 - 2 * n], row[1][1023 - 2 * n]};
+            const F2 zi = f_fma(x0, cs.x, f_mul(x1, cs.y));
+            const F2 zr = f_fma(x1, cs.x, f_neg(f_mul(x0, cs.y)));
+            z.i[0][q] = zi.x; z.i[1][q] = zi.y; z.r[0][q] = zr.x; z.r[1][q] = zr.y;
+        } else {
 #pragma unroll
-        for (int c = C0; c < C0 + NCH; ++c) {
-            const float x0 = row[c][2 * n], x1 = row[c][1023 - 2 * n];
-            z.i[c][q] = f_fma(x0, cs.x, f_mul(x1, cs.y));
-            z.r[c][q] = f_fma(x1, cs.x, -f_mul(x0, cs.y));
+            for (int c = C0; c < C0 + NCH; ++c) {
+                const float x0 = row[c][2 * n], x1 = row[c][1023 - 2 * n];
+                z.i[c][q] = f_fma(x0, cs.x, f_mul(x1, cs.y));
+                z.r[c][q] = f_fma(x1, cs.x, -f_mul(x0, cs.y));
+            }
         }
     }
 }
@@ -163,7 +267,7 @@ AACFB_HD void long_load(int u, const float *const *row, const float2 *cs2048, Pt
 // Exchange 1 (pass A -> pass B).  Element index e = array position; stored at
 // e ^ (e >> 5) so that both the scatter below and the gather in ex1_read hit
 // 16 distinct 8-byte bank pairs per half-warp.
-template <int C0, int NCH>
+template <int C0, int NCH, bool PK>
 AACFB_HD void ex1_write(int u, const Pts &z, float2 *const *buf) {
     const int a = brev6(u);
     const int base = (8 * a) ^ (a >> 2);
@@ -171,11 +275,15 @@ AACFB_HD void ex1_write(int u, const Pts &z, float2 *const *buf) {
     for (int q = 0; q < 8; ++q)
 #pragma unroll
         for (int c = C0; c < C0 + NCH; ++c) {
-            float2 t; t.x = z.r[c][q]; t.y = z.i[c][q];
+            float2 t;
+            // two chains: buffer 0 holds the real parts of both, buffer 1 the imaginary parts, so
+            // that a packed (chain 0, chain 1) register pair is one 8-byte access
+            if (PK && NCH == 2) { t.x = c == 0 ? z.r[0][q] : z.i[0][q]; t.y = c == 0 ? z.r[1][q] : z.i[1][q]; }
+            else { t.x = z.r[c][q]; t.y = z.i[c][q]; }
             buf[c][base ^ q] = t;
         }
 }
-template <int C0, int NCH>
+template <int C0, int NCH, bool PK>
 AACFB_HD void ex1_read(int v, float2 *const *buf, Pts &z) {
     const int bhi = passb_bhi(v), blo = passb_blo(v);
     const int base = ((64 * bhi) | blo) ^ (bhi << 1);
@@ -184,11 +292,12 @@ AACFB_HD void ex1_read(int v, float2 *const *buf, Pts &z) {
 #pragma unroll
         for (int c = C0; c < C0 + NCH; ++c) {
             const float2 t = buf[c][base ^ ((8 * q) ^ (q >> 2))];
-            z.r[c][q] = t.x; z.i[c][q] = t.y;
+            if (PK && NCH == 2) { if (c == 0) { z.r[0][q] = t.x; z.r[1][q] = t.y; } else { z.i[0][q] = t.x; z.i[1][q] = t.y; } }
+            else { z.r[c][q] = t.x; z.i[c][q] = t.y; }
         }
 }
 // Exchange 2 (pass B -> pass C): stored at e ^ (bit8(e) << 3).
-template <int C0, int NCH>
+template <int C0, int NCH, bool PK>
 AACFB_HD void ex2_write(int v, const Pts &z, float2 *const *buf) {
     const int bhi = passb_bhi(v), blo = passb_blo(v);
     const int base = ((64 * bhi) | blo) ^ ((bhi >> 2) << 3);
@@ -196,18 +305,23 @@ AACFB_HD void ex2_write(int v, const Pts &z, float2 *const *buf) {
     for (int q = 0; q < 8; ++q)
 #pragma unroll
         for (int c = C0; c < C0 + NCH; ++c) {
-            float2 t; t.x = z.r[c][q]; t.y = z.i[c][q];
+            float2 t;
+            // two chains: buffer 0 holds the real parts of both, buffer 1 the imaginary parts, so
+            // that a packed (chain 0, chain 1) register pair is one 8-byte access
+            if (PK && NCH == 2) { t.x = c == 0 ? z.r[0][q] : z.i[0][q]; t.y = c == 0 ? z.r[1][q] : z.i[1][q]; }
+            else { t.x = z.r[c][q]; t.y = z.i[c][q]; }
             buf[c][base ^ (8 * q)] = t;
         }
 }
-template <int C0, int NCH>
+template <int C0, int NCH, bool PK>
 AACFB_HD void ex2_read(int u, float2 *const *buf, Pts &z) {
 #pragma unroll
     for (int q = 0; q < 8; ++q)
 #pragma unroll
         for (int c = C0; c < C0 + NCH; ++c) {
             const float2 t = buf[c][(64 * q + u) ^ ((q >> 2) << 3)];
-            z.r[c][q] = t.x; z.i[c][q] = t.y;
+            if (PK && NCH == 2) { if (c == 0) { z.r[0][q] = t.x; z.r[1][q] = t.y; } else { z.i[0][q] = t.x; z.i[1][q] = t.y; } }
+            else { z.r[c][q] = t.x; z.i[c][q] = t.y; }
         }
 }
 
@@ -315,7 +429,7 @@ AACFB_HD void out_store(int u, Sync &sync, const Out &o, const OutDst &d) {
 //   UNIFORM  : all chains are ONLY_LONG with the same shapes (the common case):
 //              one shared-memory window load serves every chain and both halves.
 //   TO_GLOBAL: store the PCM right away (else park it in `o`).
-template <int C0, int NCH, bool UNIFORM, bool TO_GLOBAL, class Sync>
+template <int C0, int NCH, bool UNIFORM, bool TO_GLOBAL, bool PK, class Sync>
 AACFB_HD void long_finish(int u, Sync &sync, const Pts &z, Ovl &ov, const SynthTables *ts, const SynthTables *tg,
                           const FrameBits *fi, const OutDst &d, Out &o) {
     LongWin win[2];
@@ -334,22 +448,49 @@ AACFB_HD void long_finish(int u, Sync &sync, const Pts &z, Ovl &ov, const SynthT
                 wf_u = ts->wz[fb_shape_prev(fi[C0])][k];
                 ws_u = fb_shape_prev(fi[C0]) == fb_shape_cur(fi[C0]) ? wf_u : ts->wz[fb_shape_cur(fi[C0])][k];
             }
-#pragma unroll
-            for (int c = C0; c < C0 + NCH; ++c) {
-                const float re = z.r[c][q], im = z.i[c][q];
-                const float pr = f_fma(re, cs.x, -f_mul(im, cs.y));
-                const float pi = f_fma(im, cs.x, f_mul(re, cs.y));
-                // first-half sample at m is F, at 1023-m is -F; second-half sample is S at both
-                const float F = (q < 4) ? pr : pi;
-                const float S = (q < 4) ? -pi : pr;
+            if constexpr (PK && NCH == 2) {   // both chains at once (packed pairs)
+                const F2 re{z.r[0][q], z.r[1][q]}, im{z.i[0][q], z.i[1][q]};
+                const F2 pr = f_fma(re, cs.x, f_neg(f_mul(im, cs.y)));
+                const F2 pi = f_fma(im, cs.x, f_mul(re, cs.y));
+                const F2 F = (q < 4) ? pr : pi;
+                const F2 S = (q < 4) ? f_neg(pi) : pr;
                 if (d.emit) {
-                    const float2 wf = UNIFORM ? wf_u : win[c].first[k];
-                    a[h][c] = f_fma(F, wf.x, ov.a[c][q]);
-                    b[h][c] = f_fma(-F, wf.y, ov.b[c][q]);
+                    F2 wx, wy;
+                    if (UNIFORM) { wx = F2{wf_u.x, wf_u.x}; wy = F2{wf_u.y, wf_u.y}; }
+                    else {
+                        const float2 w0 = win[0].first[k], w1 = win[1].first[k];
+                        wx = F2{w0.x, w1.x}; wy = F2{w0.y, w1.y};
+                    }
+                    const F2 va = f_fma(F, wx, F2{ov.a[0][q], ov.a[1][q]});
+                    const F2 vb = f_fma(f_neg(F), wy, F2{ov.b[0][q], ov.b[1][q]});
+                    a[h][0] = va.x; a[h][1] = va.y; b[h][0] = vb.x; b[h][1] = vb.y;
                 }
-                const float2 ws = UNIFORM ? ws_u : win[c].second[k];
-                ov.a[c][q] = f_mul(S, ws.y);
-                ov.b[c][q] = f_mul(S, ws.x);
+                F2 sx, sy;
+                if (UNIFORM) { sx = F2{ws_u.x, ws_u.x}; sy = F2{ws_u.y, ws_u.y}; }
+                else {
+                    const float2 w0 = win[0].second[k], w1 = win[1].second[k];
+                    sx = F2{w0.x, w1.x}; sy = F2{w0.y, w1.y};
+                }
+                const F2 oa = f_mul(S, sy), ob = f_mul(S, sx);
+                ov.a[0][q] = oa.x; ov.a[1][q] = oa.y; ov.b[0][q] = ob.x; ov.b[1][q] = ob.y;
+            } else {
+#pragma unroll
+                for (int c = C0; c < C0 + NCH; ++c) {
+                    const float re = z.r[c][q], im = z.i[c][q];
+                    const float pr = f_fma(re, cs.x, -f_mul(im, cs.y));
+                    const float pi = f_fma(im, cs.x, f_mul(re, cs.y));
+                    // first-half sample at m is F, at 1023-m is -F; second-half sample is S at both
+                    const float F = (q < 4) ? pr : pi;
+                    const float S = (q < 4) ? -pi : pr;
+                    if (d.emit) {
+                        const float2 wf = UNIFORM ? wf_u : win[c].first[k];
+                        a[h][c] = f_fma(F, wf.x, ov.a[c][q]);
+                        b[h][c] = f_fma(-F, wf.y, ov.b[c][q]);
+                    }
+                    const float2 ws = UNIFORM ? ws_u : win[c].second[k];
+                    ov.a[c][q] = f_mul(S, ws.y);
+                    ov.b[c][q] = f_mul(S, ws.x);
+                }
             }
         }
         if (d.emit) {
@@ -368,24 +509,32 @@ AACFB_HD void long_finish(int u, Sync &sync, const Pts &z, Ovl &ov, const SynthT
 // ----------------------------------------------------------- short transform
 // EIGHT_SHORT: thread u = 8*w + g works on window w.  Pass A' takes inputs
 // n = g + 8*j of that window, pass B' produces bins k = 8*q + g.
-template <int C0, int NCH>
+template <int C0, int NCH, bool PK>
 AACFB_HD void short_load(int u, const float *const *row, const float2 *cs256, Pts &z) {
     const int w = u >> 3, g = u & 7;
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
         const int n = g + 8 * brev3(q);
         const float2 cs = cs256[n];
+        if constexpr (PK && NCH == 2) {
+            const int i0 = 128 * w + 2 * n, i1 = 128 * w + 127 - 2 * n;
+            const F2 x0{row[0][i0], row[1][i0]}, x1{row[0][i1], row[1][i1]};
+            const F2 zi = f_fma(x0, cs.x, f_mul(x1, cs.y));
+            const F2 zr = f_fma(x1, cs.x, f_neg(f_mul(x0, cs.y)));
+            z.i[0][q] = zi.x; z.i[1][q] = zi.y; z.r[0][q] = zr.x; z.r[1][q] = zr.y;
+        } else {
 #pragma unroll
-        for (int c = C0; c < C0 + NCH; ++c) {
-            const float x0 = row[c][128 * w + 2 * n], x1 = row[c][128 * w + 127 - 2 * n];
-            z.i[c][q] = f_fma(x0, cs.x, f_mul(x1, cs.y));
-            z.r[c][q] = f_fma(x1, cs.x, -f_mul(x0, cs.y));
+            for (int c = C0; c < C0 + NCH; ++c) {
+                const float x0 = row[c][128 * w + 2 * n], x1 = row[c][128 * w + 127 - 2 * n];
+                z.i[c][q] = f_fma(x0, cs.x, f_mul(x1, cs.y));
+                z.r[c][q] = f_fma(x1, cs.x, -f_mul(x0, cs.y));
+            }
         }
     }
 }
 // Exchange between the two passes of the 8 x 64-point FFTs.  Element
 // e = 64w + position; stored at e ^ (12*bit6(e)) ^ ((e>>4)&3).
-template <int C0, int NCH>
+template <int C0, int NCH, bool PK>
 AACFB_HD void exs_write(int u, const Pts &z, float2 *const *buf) {
     const int w = u >> 3, a = brev3(u & 7);
     const int base = ((64 * w) | (8 * a)) ^ (12 * (w & 1)) ^ (a >> 1);
@@ -393,11 +542,15 @@ AACFB_HD void exs_write(int u, const Pts &z, float2 *const *buf) {
     for (int q = 0; q < 8; ++q)
 #pragma unroll
         for (int c = C0; c < C0 + NCH; ++c) {
-            float2 t; t.x = z.r[c][q]; t.y = z.i[c][q];
+            float2 t;
+            // two chains: buffer 0 holds the real parts of both, buffer 1 the imaginary parts, so
+            // that a packed (chain 0, chain 1) register pair is one 8-byte access
+            if (PK && NCH == 2) { t.x = c == 0 ? z.r[0][q] : z.i[0][q]; t.y = c == 0 ? z.r[1][q] : z.i[1][q]; }
+            else { t.x = z.r[c][q]; t.y = z.i[c][q]; }
             buf[c][base ^ q] = t;
         }
 }
-template <int C0, int NCH>
+template <int C0, int NCH, bool PK>
 AACFB_HD void exs_read(int u, float2 *const *buf, Pts &z) {
     const int w = u >> 3, g = u & 7;
     const int base = ((64 * w) | g) ^ (12 * (w & 1));
@@ -406,7 +559,8 @@ AACFB_HD void exs_read(int u, float2 *const *buf, Pts &z) {
 #pragma unroll
         for (int c = C0; c < C0 + NCH; ++c) {
             const float2 t = buf[c][base ^ ((8 * q) ^ (q >> 1))];
-            z.r[c][q] = t.x; z.i[c][q] = t.y;
+            if (PK && NCH == 2) { if (c == 0) { z.r[0][q] = t.x; z.r[1][q] = t.y; } else { z.i[0][q] = t.x; z.i[1][q] = t.y; } }
+            else { z.r[c][q] = t.x; z.i[c][q] = t.y; }
         }
 }
 // ---- EIGHT_SHORT window + overlap-add through two product arrays ----------------------

@@ -42,37 +42,37 @@ AACFB_HD bool is_short(FrameBits fi) { return fb_seq(fi) == AACFB_EIGHT_SHORT_SE
 
 // 512-point inverse FFT of chains C0..C0+NCH-1 (fft.js:105-192 on the
 // pre-twiddled rows, mdct.js:73-79): two barriers.
-template <int C0, int NCH, class Sync>
+template <int C0, int NCH, bool PK, class Sync>
 AACFB_HD void long_fft(int u, Sync &sync, const FrameIO &io, const SynthTables *ts, Pts &z) {
     const float *row[2] = {io.stage, io.stage + kRowFloats};
     float2 *bufx[2] = {reinterpret_cast<float2 *>(io.scratch), reinterpret_cast<float2 *>(io.scratch + kRowFloats)};
     float2 *bufs[2] = {reinterpret_cast<float2 *>(io.stage), reinterpret_cast<float2 *>(io.stage + kRowFloats)};
-    long_load<C0, NCH>(u, row, ts->cs2048, z);
-    pass_a<C0, NCH>(z, ts->rootsA);
-    ex1_write<C0, NCH>(u, z, bufx);
+    long_load<C0, NCH, PK>(u, row, ts->cs2048, z);
+    pass_a<C0, NCH, PK>(z, ts->rootsA);
+    ex1_write<C0, NCH, PK>(u, z, bufx);
     sync.barrier();  // exchange 1 complete; every thread has consumed its part of the rows
-    ex1_read<C0, NCH>(u, bufx, z);
-    pass_3stage<C0, NCH>(z, ts->twB + 7 * passb_blo(u));
-    ex2_write<C0, NCH>(u, z, bufs);
+    ex1_read<C0, NCH, PK>(u, bufx, z);
+    pass_3stage<C0, NCH, PK>(z, ts->twB + 7 * passb_blo(u));
+    ex2_write<C0, NCH, PK>(u, z, bufs);
     sync.barrier();  // exchange 2 complete; exchange-1 data is dead
-    ex2_read<C0, NCH>(u, bufs, z);
+    ex2_read<C0, NCH, PK>(u, bufs, z);
     float2 twc[7];
 #pragma unroll
     for (int j = 0; j < 7; ++j) twc[j] = ts->twC[j][u];
-    pass_3stage<C0, NCH>(z, twc);
+    pass_3stage<C0, NCH, PK>(z, twc);
 }
 
 // The 8 x 64-point FFTs of EIGHT_SHORT for chains C0..C0+NCH-1: one barrier.
-template <int C0, int NCH, class Sync>
+template <int C0, int NCH, bool PK, class Sync>
 AACFB_HD void short_fft(int u, Sync &sync, const FrameIO &io, const SynthTables *ts, Pts &z) {
     const float *row[2] = {io.stage, io.stage + kRowFloats};
     float2 *bufx[2] = {reinterpret_cast<float2 *>(io.scratch), reinterpret_cast<float2 *>(io.scratch + kRowFloats)};
-    short_load<C0, NCH>(u, row, ts->cs256, z);
-    pass_a<C0, NCH>(z, ts->roots64A);
-    exs_write<C0, NCH>(u, z, bufx);
+    short_load<C0, NCH, PK>(u, row, ts->cs256, z);
+    pass_a<C0, NCH, PK>(z, ts->roots64A);
+    exs_write<C0, NCH, PK>(u, z, bufx);
     sync.barrier();
-    exs_read<C0, NCH>(u, bufx, z);
-    pass_3stage<C0, NCH>(z, ts->twS + 7 * (u & 7));
+    exs_read<C0, NCH, PK>(u, bufx, z);
+    pass_3stage<C0, NCH, PK>(z, ts->twS + 7 * (u & 7));
 }
 
 // A frame whose chains are all long transforms: two blocking barriers; the PCM
@@ -80,20 +80,20 @@ AACFB_HD void short_fft(int u, Sync &sync, const FrameIO &io, const SynthTables 
 // UNIFORM_PATH: also instantiate the specialisation for frames whose chains are all ONLY_LONG with
 // equal shapes.  The generic pass leaves it out: its code footprint (long + short paths running
 // side by side on one SM) is what the instruction cache has to hold.
-template <int NCH, bool UNIFORM_PATH, class Sync>
+template <int NCH, bool UNIFORM_PATH, bool PK, class Sync>
 AACFB_HD void frame_all_long(int u, Sync &sync, const FrameIO &io, const SynthTables *ts, const SynthTables *tg,
                              Pts &z, Ovl &ov) {
-    long_fft<0, NCH>(u, sync, io, ts, z);
+    long_fft<0, NCH, PK>(u, sync, io, ts, z);
     sync.stage_free();  // exchange 2 has been read back: the stage may be refilled
     Out none;
     const bool uniform = UNIFORM_PATH && fb_seq(io.fi[0]) == AACFB_ONLY_LONG_SEQUENCE &&
                          (NCH == 1 || ((io.fi[0] ^ io.fi[1]) & 0x00ffffffu) == 0);
-    if (UNIFORM_PATH && uniform) long_finish<0, NCH, true, true>(u, sync, z, ov, ts, tg, io.fi, io.dst, none);
-    else long_finish<0, NCH, false, true>(u, sync, z, ov, ts, tg, io.fi, io.dst, none);
+    if (UNIFORM_PATH && uniform) long_finish<0, NCH, true, true, PK>(u, sync, z, ov, ts, tg, io.fi, io.dst, none);
+    else long_finish<0, NCH, false, true, PK>(u, sync, z, ov, ts, tg, io.fi, io.dst, none);
 }
 
 // A frame with at least one EIGHT_SHORT chain: results pass through registers.
-template <class Sync>
+template <bool PK, class Sync>
 AACFB_HD void frame_with_short(int u, Sync &sync, const FrameIO &io, const SynthTables *ts, const SynthTables *tg,
                                Pts &z, Ovl &ov) {
     Out o;
@@ -101,7 +101,7 @@ AACFB_HD void frame_with_short(int u, Sync &sync, const FrameIO &io, const Synth
     const bool s0 = is_short(io.fi[0]);
     const bool s1 = io.nch == 2 && is_short(io.fi[1]);
     if (io.nch == 2 && s0 && s1) {
-        short_fft<0, 2>(u, sync, io, ts, z);
+        short_fft<0, 2, PK>(u, sync, io, ts, z);
         short_products<0>(u, z, ts->cs256, ts->wshort, io.fi[0], io.stage);    // rows are dead since the exchange barrier
         sync.barrier();
         short_finish<0>(u, io.stage, ov, d.emit, o);
@@ -113,7 +113,7 @@ AACFB_HD void frame_with_short(int u, Sync &sync, const FrameIO &io, const Synth
         return;
     }
     if (io.nch == 1) {
-        short_fft<0, 1>(u, sync, io, ts, z);
+        short_fft<0, 1, false>(u, sync, io, ts, z);
         short_products<0>(u, z, ts->cs256, ts->wshort, io.fi[0], io.stage);
         sync.barrier();
         short_finish<0>(u, io.stage, ov, d.emit, o);
@@ -122,16 +122,16 @@ AACFB_HD void frame_with_short(int u, Sync &sync, const FrameIO &io, const Synth
         return;
     }
     if (s0) {  // chain 1 long first (it only touches its own halves), then chain 0 short
-        long_fft<1, 1>(u, sync, io, ts, z);
-        long_finish<1, 1, false, false>(u, sync, z, ov, ts, tg, io.fi, d, o);
-        short_fft<0, 1>(u, sync, io, ts, z);
+        long_fft<1, 1, false>(u, sync, io, ts, z);
+        long_finish<1, 1, false, false, false>(u, sync, z, ov, ts, tg, io.fi, d, o);
+        short_fft<0, 1, false>(u, sync, io, ts, z);
         short_products<0>(u, z, ts->cs256, ts->wshort, io.fi[0], io.stage);
         sync.barrier();
         short_finish<0>(u, io.stage, ov, d.emit, o);
     } else {
-        long_fft<0, 1>(u, sync, io, ts, z);
-        long_finish<0, 1, false, false>(u, sync, z, ov, ts, tg, io.fi, d, o);
-        short_fft<1, 1>(u, sync, io, ts, z);
+        long_fft<0, 1, false>(u, sync, io, ts, z);
+        long_finish<0, 1, false, false, false>(u, sync, z, ov, ts, tg, io.fi, d, o);
+        short_fft<1, 1, false>(u, sync, io, ts, z);
         short_products<1>(u, z, ts->cs256, ts->wshort, io.fi[1], io.stage);
         sync.barrier();
         short_finish<1>(u, io.stage, ov, d.emit, o);
@@ -147,16 +147,24 @@ AACFB_HD void frame_with_short(int u, Sync &sync, const FrameIO &io, const Synth
 template <bool GENERIC, bool STEREO, class Sync>
 AACFB_HD void worker_frame(int u, Sync &sync, const FrameIO &io, const SynthTables *ts, const SynthTables *tg, Pts &z,
                            Ovl &ov) {
-    if (STEREO && io.ops) {  // M/S and intensity stereo act on the spectra before anything else (decoder.js:300-307)
+    // Packed two-chain arithmetic (FFMA2) where it pays: measured on B200 it is neutral to slightly
+    // negative for the plain long-only instantiation (bounded by the shared-memory pipe, not by
+    // issue slots) and +4..11 % for the generic and stereo ones (less code, no spills).
+    constexpr bool PK = GENERIC || STEREO;
+    // M/S and intensity stereo act on the spectra before anything else (decoder.js:294-301): in place
+    // on the staged rows, one op per group of 4 coefficients.  (Applying them per element while the
+    // rows are read into registers was measured 6 % slower: 16 byte loads + selects per thread
+    // against 4 vector read-modify-writes.)
+    if (STEREO && io.ops) {
         stereo_apply(u, io.stage, io.ops);
         sync.barrier();
     }
     if (GENERIC) {
         const bool any_short = is_short(io.fi[0]) || (io.nch == 2 && is_short(io.fi[1]));
-        if (any_short) { frame_with_short(u, sync, io, ts, tg, z, ov); return; }
+        if (any_short) { frame_with_short<PK>(u, sync, io, ts, tg, z, ov); return; }
     }
-    if (io.nch == 2) frame_all_long<2, !GENERIC>(u, sync, io, ts, tg, z, ov);
-    else frame_all_long<1, !GENERIC>(u, sync, io, ts, tg, z, ov);
+    if (io.nch == 2) frame_all_long<2, !GENERIC, PK>(u, sync, io, ts, tg, z, ov);
+    else frame_all_long<1, !GENERIC, false>(u, sync, io, ts, tg, z, ov);
 }
 
 }  // namespace aacfb
