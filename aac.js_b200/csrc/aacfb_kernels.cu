@@ -39,7 +39,8 @@ struct Layout {
     static constexpr int kOffBars = kOffStages + W * kBufsPerWorker * kStageBytes;
     static constexpr int kOffSlots = kOffBars + W * ST * 8;
     static constexpr int kRingWords = STEREO ? 4 : 2;   // per ring entry: 2 chains x (FrameBits [, flags word])
-    static constexpr int kSlotInts = 8 + 2 * kRingWords * ST;   // per worker: item, flag, cursor[6], side-info ring [2 ST]
+    static constexpr int kPendInts = 12;                // the refill the leader has prepared (see DevSync)
+    static constexpr int kSlotInts = 8 + kPendInts + 2 * kRingWords * ST;   // per worker: item, flag, cursor[6], pending refill, side-info ring [2 ST]
     static constexpr int kOffOps = (kOffSlots + W * kSlotInts * 4 + 15) & ~15;   // aacfb_stereo_ops per worker and stage
     static constexpr int kTotal = STEREO ? kOffOps + W * ST * (int)sizeof(aacfb_stereo_ops) : kOffSlots + W * kSlotInts * 4;
     static_assert(kTotal <= 227 * 1024, "shared memory budget");
@@ -73,26 +74,32 @@ __device__ __forceinline__ void bulk_load(uint32_t dst, const void *src, uint32_
                  : "memory");
 }
 
-template <bool STEREO>
+// PARK: keep the prepared refill in shared memory instead of registers.  Costs the leader's warp
+// a few dozen instructions per frame (measured -4 % on the long-only instantiations) but frees
+// ~8 registers per thread, which is what keeps the generic instantiations from spilling.
+template <bool STEREO, bool PARK>
 struct DevSync {
     uint32_t bar_id;      // named barrier of this worker (all 64 threads block)
     uint32_t free_id;     // named barrier "stage is free": followers arrive, the leader's warp waits
     bool leader_warp, leader;
     volatile uint32_t *ring;  // side-info ring of the worker (see synth_kernel)
-    // the refill this frame's stage_free() has to issue (leader only)
-    bool next_valid;
-    uint32_t dst, mbar;
-    int cf[2];            // channel-frame index of the row(s) to fetch
-    uint32_t rng[2];      // lo4 | hi4 << 16: float4 interval that comes from the TNS scratch (0: none)
-    int nrows;
+    // The refill this frame's stage_free() has to issue is prepared by the leader thread before the
+    // frame's arithmetic and issued after it.  Only that one thread needs it, so it is parked in
+    // shared memory instead of occupying registers of all 64 threads across the whole frame:
+    // pend[0] valid, [1] dst, [2] mbar, [3] nrows, [4..5] channel-frame index of the rows,
+    // [6..7] rng: lo4 | hi4 << 16 = the float4 interval that comes from the TNS scratch (0: none),
+    // [8] ring entry of the frame's side info, [9] shared-memory home of its stereo record,
+    // [10] the rows are (left, right) of one stream.
+    volatile uint32_t *pend;
+    uint32_t reg[11];     // the same record in registers (!PARK)
+    __device__ __forceinline__ void put(int i, uint32_t v) { if (PARK) pend[i] = v; else reg[i] = v; }
+    __device__ __forceinline__ uint32_t get(int i) const { return PARK ? pend[i] : reg[i]; }
     const float *spectra, *scratch;
     const aacfb_stereo_ops *stereo;   // global records (nullptr: none)
-    bool pair_stereo;                 // the rows being fetched are (left, right) of one stream
-    uint32_t ring_e, ops_dst;         // side-info ring entry / shared-memory home of the frame being fetched
     __device__ __forceinline__ void barrier() { asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory"); }
     // One row = 4096 bytes on the mbarrier, fetched as up to three 1-D bulk copies: the interval
     // the TNS pass filtered comes from its scratch, the rest straight from the spectra.
-    __device__ __forceinline__ void issue_row(uint32_t d, int cfi, uint32_t r) {
+    __device__ __forceinline__ void issue_row(uint32_t d, uint32_t mbar, int cfi, uint32_t r) {
         const float *a = spectra + (size_t)cfi * 1024;
         const uint32_t lo = r & 0xffffu, hi = r >> 16;
         if (hi <= lo) { bulk_load(d, a, 4096u, mbar); return; }
@@ -101,22 +108,24 @@ struct DevSync {
         bulk_load(d + 16u * lo, b + 4 * lo, 16u * (hi - lo), mbar);
         if (hi < 256u) bulk_load(d + 16u * hi, a + 4 * hi, 16u * (256u - hi), mbar);
     }
-    // STEREO: the side info of the frame must have landed in the ring (stereo_present = byte 5 of
-    // the left channel's aacfb_frame_info = second word of its entry)
+    // Leader only: issue the prepared refill.  STEREO: the side info of the frame must have landed
+    // in the ring (stereo_present = byte 5 of the left channel's aacfb_frame_info = second word of
+    // its entry).
     __device__ __forceinline__ void issue() {
+        const uint32_t dst = get(1), mbar = get(2), nrows = get(3);
         bool ops = false;
-        if (STEREO) ops = pair_stereo && ((ring[4 * ring_e + 1] >> 8) & 0xffu) != 0;
-        mbar_expect_tx(mbar, (uint32_t)nrows * 4096u + (ops ? (uint32_t)sizeof(aacfb_stereo_ops) : 0u));
-        issue_row(dst, cf[0], rng[0]);
-        if (nrows == 2) issue_row(dst + 4096u, cf[1], rng[1]);
-        if (STEREO && ops) bulk_load(ops_dst, stereo + (cf[0] >> 1), (uint32_t)sizeof(aacfb_stereo_ops), mbar);
+        if (STEREO) ops = get(10) != 0 && ((ring[4 * get(8) + 1] >> 8) & 0xffu) != 0;
+        mbar_expect_tx(mbar, nrows * 4096u + (ops ? (uint32_t)sizeof(aacfb_stereo_ops) : 0u));
+        issue_row(dst, mbar, (int)get(4), get(6));
+        if (nrows == 2) issue_row(dst + 4096u, mbar, (int)get(5), get(7));
+        if (STEREO && ops) bulk_load(get(9), stereo + (get(4) >> 1), (uint32_t)sizeof(aacfb_stereo_ops), mbar);
     }
     __device__ __forceinline__ void stage_free() {
         // order this thread's generic-proxy accesses to the stage before the async-proxy refill
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         if (leader_warp) {
             asm volatile("bar.sync %0, 64;" ::"r"(free_id) : "memory");
-            if (leader && next_valid) {
+            if (leader && get(0) != 0u) {
                 asm volatile("cp.async.wait_group 0;" ::: "memory");  // the prefetched side info has landed
                 issue();
             }
@@ -172,7 +181,7 @@ __global__ void __launch_bounds__(W * 64, 1) synth_kernel(const __grid_constant_
     // 4-byte cp.async when it prefetches the frame's rows, kStages frames ahead, so no thread waits
     // on a global load at the top of a frame; 2 kStages entries because the entry of the frame
     // being worked on is still being read when the next prefetch is issued.
-    volatile uint32_t *fi_ring = reinterpret_cast<volatile uint32_t *>(slot + 8);  // [entry][chain][1 or 2 words]
+    volatile uint32_t *fi_ring = reinterpret_cast<volatile uint32_t *>(slot + 8 + L::kPendInts);  // [entry][chain][1 or 2 words]
     constexpr uint32_t kFiRing = 2 * kStages, kRW = L::kRingWords;
     const aacfb_stereo_ops *ops_area =
         reinterpret_cast<const aacfb_stereo_ops *>(smem + L::kOffOps) + (size_t)w * kStages;
@@ -182,7 +191,7 @@ __global__ void __launch_bounds__(W * 64, 1) synth_kernel(const __grid_constant_
     }
     __syncthreads();
 
-    DevSync<STEREO> sync;
+    DevSync<STEREO, GENERIC> sync;
     sync.bar_id = 1 + w;
     sync.free_id = 1 + kWorkers + w;
     sync.leader_warp = ((tid >> 5) & 1) == 0;
@@ -191,6 +200,7 @@ __global__ void __launch_bounds__(W * 64, 1) synth_kernel(const __grid_constant_
     sync.scratch = P.scratch;
     sync.stereo = P.stereo;
     sync.ring = fi_ring;
+    sync.pend = reinterpret_cast<volatile uint32_t *>(slot + 8);
     const Geometry g = P.g;
     uint32_t fc = 0;  // frames this worker has staged so far: ring position and mbarrier phase
     Pts z;
@@ -249,8 +259,8 @@ __global__ void __launch_bounds__(W * 64, 1) synth_kernel(const __grid_constant_
         auto refill = [&](uint32_t st, uint32_t frame_no) {
             const int tn = cur[1], ca = cur[2], cb = cur[3];
             {
-                sync.ring_e = frame_no % kFiRing;
-                const uint32_t e = smem_u32(const_cast<uint32_t *>(fi_ring)) + 4u * kRW * sync.ring_e;
+                const uint32_t ring_e = frame_no % kFiRing;
+                const uint32_t e = smem_u32(const_cast<uint32_t *>(fi_ring)) + 4u * kRW * ring_e;
                 const uint32_t *inf = reinterpret_cast<const uint32_t *>(P.info);
                 if (STEREO) {   // the whole 8-byte record: the stereo flag sits in its second word
                     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(e), "l"(inf + 2 * (size_t)ca) : "memory");
@@ -261,16 +271,17 @@ __global__ void __launch_bounds__(W * 64, 1) synth_kernel(const __grid_constant_
                 }
                 asm volatile("cp.async.commit_group;" ::: "memory");
                 if (STEREO) {
-                    sync.pair_stereo = cur[5] != 0;
-                    sync.ops_dst = smem_u32(ops_area + st);
+                    sync.put(8, ring_e);
+                    sync.put(9, smem_u32(ops_area + st));
+                    sync.put(10, cur[5] != 0 ? 1u : 0u);
                 }
             }
-            sync.dst = smem_u32(stages + st * kStageFloats);
-            sync.mbar = bars + 8 * st;
-            sync.nrows = cur[4];
-            sync.cf[0] = ca; sync.cf[1] = cb;
-            sync.rng[0] = row_range(P, (size_t)ca);
-            sync.rng[1] = row_range(P, (size_t)cb);
+            sync.put(1, smem_u32(stages + st * kStageFloats));
+            sync.put(2, bars + 8 * st);
+            sync.put(3, (uint32_t)cur[4]);
+            sync.put(4, (uint32_t)ca); sync.put(5, (uint32_t)cb);
+            sync.put(6, row_range(P, (size_t)ca));
+            sync.put(7, row_range(P, (size_t)cb));
             if (tn + 1 == g.T) { if (cur[0] + 1 < g.n_pairs) cursor_to(cur[0] + 1, 0); }
             else { cur[1] = tn + 1; cur[2] = ca + g.nc; cur[3] = cb + g.nc; }
         };
@@ -310,8 +321,11 @@ __global__ void __launch_bounds__(W * 64, 1) synth_kernel(const __grid_constant_
             if (STEREO && pr.interleaved && ((fi_ring[4 * (fc % kFiRing) + 1] >> 8) & 0xffu) != 0) io.ops = ops_area + st;
             io.dst.out0 = P.pcm + oa;
             io.dst.out1 = P.pcm + ob;
-            sync.next_valid = f + kStages < nf;
-            if (leader && sync.next_valid) refill(st, fc + kStages);
+            if (leader) {
+                const bool next_valid = f + kStages < nf;
+                sync.put(0, next_valid ? 1u : 0u);
+                if (next_valid) refill(st, fc + kStages);
+            }
             mbar_wait(bars + 8 * st, (fc / kStages) & 1u);
             worker_frame<GENERIC, STEREO>(u, sync, io, ts, P.tab, z, ov);
             cfa += g.nc; cfb += g.nc;

@@ -19,6 +19,16 @@
 #include "aacfb_core.cuh"
 #include "aacfb_geometry.h"
 
+// Tuning switches (tools/variant.sh builds variants; the defaults are the measured best).
+// AACFB_ROT must be the same for every instantiation: a long frame has to come out with the same
+// bits whichever instantiation (long-only / generic) happens to process its slice.
+#ifndef AACFB_PK
+#define AACFB_PK 1      // packed two-chain arithmetic (FFMA2) on frames of two long or two short chains
+#endif
+#ifndef AACFB_ROT
+#define AACFB_ROT 1     // MDCT twiddles of the pre- and post-twiddle derived by rotation (cs_at)
+#endif
+
 namespace aacfb {
 
 struct FrameIO {
@@ -42,12 +52,12 @@ AACFB_HD bool is_short(FrameBits fi) { return fb_seq(fi) == AACFB_EIGHT_SHORT_SE
 
 // 512-point inverse FFT of chains C0..C0+NCH-1 (fft.js:105-192 on the
 // pre-twiddled rows, mdct.js:73-79): two barriers.
-template <int C0, int NCH, bool PK, class Sync>
+template <int C0, int NCH, bool PK, bool ROT, class Sync>
 AACFB_HD void long_fft(int u, Sync &sync, const FrameIO &io, const SynthTables *ts, Pts &z) {
     const float *row[2] = {io.stage, io.stage + kRowFloats};
     float2 *bufx[2] = {reinterpret_cast<float2 *>(io.scratch), reinterpret_cast<float2 *>(io.scratch + kRowFloats)};
     float2 *bufs[2] = {reinterpret_cast<float2 *>(io.stage), reinterpret_cast<float2 *>(io.stage + kRowFloats)};
-    long_load<C0, NCH, PK>(u, row, ts->cs2048, z);
+    long_load<C0, NCH, PK, ROT>(u, row, ts->cs2048, z);
     pass_a<C0, NCH, PK>(z, ts->rootsA);
     ex1_write<C0, NCH, PK>(u, z, bufx);
     sync.barrier();  // exchange 1 complete; every thread has consumed its part of the rows
@@ -80,16 +90,16 @@ AACFB_HD void short_fft(int u, Sync &sync, const FrameIO &io, const SynthTables 
 // UNIFORM_PATH: also instantiate the specialisation for frames whose chains are all ONLY_LONG with
 // equal shapes.  The generic pass leaves it out: its code footprint (long + short paths running
 // side by side on one SM) is what the instruction cache has to hold.
-template <int NCH, bool UNIFORM_PATH, bool PK, class Sync>
+template <int NCH, bool UNIFORM_PATH, bool PK, bool ROTL, bool ROTF, class Sync>
 AACFB_HD void frame_all_long(int u, Sync &sync, const FrameIO &io, const SynthTables *ts, const SynthTables *tg,
                              Pts &z, Ovl &ov) {
-    long_fft<0, NCH, PK>(u, sync, io, ts, z);
+    long_fft<0, NCH, PK, ROTL>(u, sync, io, ts, z);
     sync.stage_free();  // exchange 2 has been read back: the stage may be refilled
     Out none;
     const bool uniform = UNIFORM_PATH && fb_seq(io.fi[0]) == AACFB_ONLY_LONG_SEQUENCE &&
                          (NCH == 1 || ((io.fi[0] ^ io.fi[1]) & 0x00ffffffu) == 0);
-    if (UNIFORM_PATH && uniform) long_finish<0, NCH, true, true, PK>(u, sync, z, ov, ts, tg, io.fi, io.dst, none);
-    else long_finish<0, NCH, false, true, PK>(u, sync, z, ov, ts, tg, io.fi, io.dst, none);
+    if (UNIFORM_PATH && uniform) long_finish<0, NCH, true, true, PK, ROTF>(u, sync, z, ov, ts, tg, io.fi, io.dst, none);
+    else long_finish<0, NCH, false, true, PK, ROTF>(u, sync, z, ov, ts, tg, io.fi, io.dst, none);
 }
 
 // A frame with at least one EIGHT_SHORT chain: results pass through registers.
@@ -122,15 +132,15 @@ AACFB_HD void frame_with_short(int u, Sync &sync, const FrameIO &io, const Synth
         return;
     }
     if (s0) {  // chain 1 long first (it only touches its own halves), then chain 0 short
-        long_fft<1, 1, false>(u, sync, io, ts, z);
-        long_finish<1, 1, false, false, false>(u, sync, z, ov, ts, tg, io.fi, d, o);
+        long_fft<1, 1, false, AACFB_ROT != 0>(u, sync, io, ts, z);
+        long_finish<1, 1, false, false, false, AACFB_ROT != 0>(u, sync, z, ov, ts, tg, io.fi, d, o);
         short_fft<0, 1, false>(u, sync, io, ts, z);
         short_products<0>(u, z, ts->cs256, ts->wshort, io.fi[0], io.stage);
         sync.barrier();
         short_finish<0>(u, io.stage, ov, d.emit, o);
     } else {
-        long_fft<0, 1, false>(u, sync, io, ts, z);
-        long_finish<0, 1, false, false, false>(u, sync, z, ov, ts, tg, io.fi, d, o);
+        long_fft<0, 1, false, AACFB_ROT != 0>(u, sync, io, ts, z);
+        long_finish<0, 1, false, false, false, AACFB_ROT != 0>(u, sync, z, ov, ts, tg, io.fi, d, o);
         short_fft<1, 1, false>(u, sync, io, ts, z);
         short_products<1>(u, z, ts->cs256, ts->wshort, io.fi[1], io.stage);
         sync.barrier();
@@ -147,10 +157,12 @@ AACFB_HD void frame_with_short(int u, Sync &sync, const FrameIO &io, const Synth
 template <bool GENERIC, bool STEREO, class Sync>
 AACFB_HD void worker_frame(int u, Sync &sync, const FrameIO &io, const SynthTables *ts, const SynthTables *tg, Pts &z,
                            Ovl &ov) {
-    // Packed two-chain arithmetic (FFMA2) where it pays: measured on B200 it is neutral to slightly
-    // negative for the plain long-only instantiation (bounded by the shared-memory pipe, not by
-    // issue slots) and +4..11 % for the generic and stereo ones (less code, no spills).
-    constexpr bool PK = GENERIC || STEREO;
+    // Packed two-chain arithmetic (FFMA2) halves the FP instruction count; on its own it is neutral
+    // for the long-only instantiation (bounded by the shared-memory pipe, not by issue slots), but
+    // it is what pays for deriving the MDCT twiddles in registers instead of loading them (cs_at):
+    // together 0.2265 -> 0.198 ms on config 2 (profiles/README.md).
+    constexpr bool PK = AACFB_PK != 0;
+    constexpr bool ROTL = AACFB_ROT != 0, ROTF = AACFB_ROT != 0;
     // M/S and intensity stereo act on the spectra before anything else (decoder.js:294-301): in place
     // on the staged rows, one op per group of 4 coefficients.  (Applying them per element while the
     // rows are read into registers was measured 6 % slower: 16 byte loads + selects per thread
@@ -163,8 +175,8 @@ AACFB_HD void worker_frame(int u, Sync &sync, const FrameIO &io, const SynthTabl
         const bool any_short = is_short(io.fi[0]) || (io.nch == 2 && is_short(io.fi[1]));
         if (any_short) { frame_with_short<PK>(u, sync, io, ts, tg, z, ov); return; }
     }
-    if (io.nch == 2) frame_all_long<2, !GENERIC, PK>(u, sync, io, ts, tg, z, ov);
-    else frame_all_long<1, !GENERIC, false>(u, sync, io, ts, tg, z, ov);
+    if (io.nch == 2) frame_all_long<2, !GENERIC, PK, ROTL, ROTF>(u, sync, io, ts, tg, z, ov);
+    else frame_all_long<1, !GENERIC, false, ROTL, ROTF>(u, sync, io, ts, tg, z, ov);
 }
 
 }  // namespace aacfb
