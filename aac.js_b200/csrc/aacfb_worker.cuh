@@ -25,6 +25,9 @@
 #ifndef AACFB_PK
 #define AACFB_PK 1      // packed two-chain arithmetic (FFMA2) on frames of two long or two short chains
 #endif
+#ifndef AACFB_GENERIC_UNIFORM
+#define AACFB_GENERIC_UNIFORM 0   // generic instantiations: also compile the uniform-ONLY_LONG finish
+#endif
 #ifndef AACFB_ROT
 #define AACFB_ROT 1     // MDCT twiddles of the pre- and post-twiddle derived by rotation (cs_at)
 #endif
@@ -175,8 +178,9 @@ AACFB_HD void worker_frame(int u, Sync &sync, const FrameIO &io, const SynthTabl
         const bool any_short = is_short(io.fi[0]) || (io.nch == 2 && is_short(io.fi[1]));
         if (any_short) { frame_with_short<PK>(u, sync, io, ts, tg, z, ov); return; }
     }
-    if (io.nch == 2) frame_all_long<2, !GENERIC, PK, ROTL, ROTF>(u, sync, io, ts, tg, z, ov);
-    else frame_all_long<1, !GENERIC, false, ROTL, ROTF>(u, sync, io, ts, tg, z, ov);
+    constexpr bool UNI = !GENERIC || AACFB_GENERIC_UNIFORM != 0;
+    if (io.nch == 2) frame_all_long<2, UNI, PK, ROTL, ROTF>(u, sync, io, ts, tg, z, ov);
+    else frame_all_long<1, UNI, false, ROTL, ROTF>(u, sync, io, ts, tg, z, ov);
 }
 
 }  // namespace aacfb
