@@ -371,7 +371,19 @@ constexpr int kTnsSmemRing = kTnsWarps * kTnsRing * kTnsTileFloats * 4;
 constexpr int kTnsSmemBytes = kTnsSmemRing + 256;      // + the band tables of one sample rate
 
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void *src) {
+#ifndef AACFB_TNS_L2_PREFETCH
+#define AACFB_TNS_L2_PREFETCH 256   // tuning switch: 0 = plain
+#endif
+#if AACFB_TNS_L2_PREFETCH == 256
+    // A tile row is one 128-byte line and the next tile of the same row is its neighbour: asking L2
+    // for the whole 256-byte block turns the DRAM access into 256-byte runs (tools/ubench/stride_copy.cu:
+    // 6.3 instead of 4.9 TB/s for this pattern) and the second tile then hits in L2.
+    asm volatile("cp.async.cg.shared.global.L2::256B [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+#elif AACFB_TNS_L2_PREFETCH == 128
+    asm volatile("cp.async.cg.shared.global.L2::128B [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+#else
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+#endif
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
