@@ -91,6 +91,10 @@ AACFB_HD F2 f_fma(F2 a, float s, F2 c) { return f_fma(a, F2{s, s}, c); }
 AACFB_HD F2 f_fma(float s, F2 a, F2 c) { return f_fma(F2{s, s}, a, c); }
 AACFB_HD F2 f_mul(F2 a, float s) { return f_mul(a, F2{s, s}); }
 
+#ifndef AACFB_SHORT_PAIRLOAD
+#define AACFB_SHORT_PAIRLOAD 1   // tuning switch: EIGHT_SHORT rows read as 8-byte pairs + one shuffle
+#endif
+
 constexpr int kWorkerThreads = 64;
 constexpr int kRowFloats = 1024;        // one channel-frame of spectrum
 constexpr int kStageFloats = 2 * 1024;  // two chains per stage
@@ -535,25 +539,49 @@ AACFB_HD void long_finish(int u, Sync &sync, const Pts &z, Ovl &ov, const SynthT
 // ----------------------------------------------------------- short transform
 // EIGHT_SHORT: thread u = 8*w + g works on window w.  Pass A' takes inputs
 // n = g + 8*j of that window, pass B' produces bins k = 8*q + g.
-template <int C0, int NCH, bool PK>
-AACFB_HD void short_load(int u, const float *const *row, const float2 *cs256, Pts &z) {
+//
+// Packed two-chain path: like the long transform's stride-2 reads, scalar loads of x[2n] and
+// x[127 - 2n] only ever touch every other bank, and here four windows of a warp land on the same
+// eight banks (4-way conflicts).  Reading 8-byte pairs (x[2n], x[2n+1]) halves that: the odd
+// element is the x[127 - 2n'] of n' = 63 - n = (7-g) + 8(7-j), i.e. what thread u ^ 7 (lane ^ 7)
+// needs for its register 7-q, so one shuffle per value replaces the second load.
+template <int C0, int NCH, bool PK, class Sync>
+AACFB_HD void short_load(int u, Sync &sync, const float *const *row, const float2 *cs256, Pts &z) {
     const int w = u >> 3, g = u & 7;
+    if constexpr (PK && NCH == 2 && AACFB_SHORT_PAIRLOAD != 0) {
+        const float2 *r0 = reinterpret_cast<const float2 *>(row[0]) + 64 * w, *r1 = reinterpret_cast<const float2 *>(row[1]) + 64 * w;
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
-        const int n = g + 8 * brev3(q);
-        const float2 cs = cs256[n];
-        if constexpr (PK && NCH == 2) {
-            const int i0 = 128 * w + 2 * n, i1 = 128 * w + 127 - 2 * n;
-            const F2 x0{row[0][i0], row[1][i0]}, x1{row[0][i1], row[1][i1]};
-            const F2 zi = f_fma(x0, cs.x, f_mul(x1, cs.y));
-            const F2 zr = f_fma(x1, cs.x, f_neg(f_mul(x0, cs.y)));
-            z.i[0][q] = zi.x; z.i[1][q] = zi.y; z.r[0][q] = zr.x; z.r[1][q] = zr.y;
-        } else {
+        for (int q = 0; q < 4; ++q) {
+            const int qa = q, qb = 7 - q;   // brev3(7 - q) = 7 - brev3(q)
+            const int na = g + 8 * brev3(qa), nb = g + 8 * brev3(qb);
+            const float2 a0 = r0[na], a1 = r1[na], b0 = r0[nb], b1 = r1[nb];
+            const F2 x1a{sync.partner7(u, b0.y), sync.partner7(u, b1.y)};
+            const F2 x1b{sync.partner7(u, a0.y), sync.partner7(u, a1.y)};
+            const F2 x0a{a0.x, a1.x}, x0b{b0.x, b1.x};
+            const float2 ca = cs256[na], cb = cs256[nb];
+            const F2 zia = f_fma(x0a, ca.x, f_mul(x1a, ca.y)), zra = f_fma(x1a, ca.x, f_neg(f_mul(x0a, ca.y)));
+            const F2 zib = f_fma(x0b, cb.x, f_mul(x1b, cb.y)), zrb = f_fma(x1b, cb.x, f_neg(f_mul(x0b, cb.y)));
+            z.i[0][qa] = zia.x; z.i[1][qa] = zia.y; z.r[0][qa] = zra.x; z.r[1][qa] = zra.y;
+            z.i[0][qb] = zib.x; z.i[1][qb] = zib.y; z.r[0][qb] = zrb.x; z.r[1][qb] = zrb.y;
+        }
+    } else {
 #pragma unroll
-            for (int c = C0; c < C0 + NCH; ++c) {
-                const float x0 = row[c][128 * w + 2 * n], x1 = row[c][128 * w + 127 - 2 * n];
-                z.i[c][q] = f_fma(x0, cs.x, f_mul(x1, cs.y));
-                z.r[c][q] = f_fma(x1, cs.x, -f_mul(x0, cs.y));
+        for (int q = 0; q < 8; ++q) {
+            const int n = g + 8 * brev3(q);
+            const float2 cs = cs256[n];
+            if constexpr (PK && NCH == 2) {
+                const int i0 = 128 * w + 2 * n, i1 = 128 * w + 127 - 2 * n;
+                const F2 x0{row[0][i0], row[1][i0]}, x1{row[0][i1], row[1][i1]};
+                const F2 zi = f_fma(x0, cs.x, f_mul(x1, cs.y));
+                const F2 zr = f_fma(x1, cs.x, f_neg(f_mul(x0, cs.y)));
+                z.i[0][q] = zi.x; z.i[1][q] = zi.y; z.r[0][q] = zr.x; z.r[1][q] = zr.y;
+            } else {
+#pragma unroll
+                for (int c = C0; c < C0 + NCH; ++c) {
+                    const float x0 = row[c][128 * w + 2 * n], x1 = row[c][128 * w + 127 - 2 * n];
+                    z.i[c][q] = f_fma(x0, cs.x, f_mul(x1, cs.y));
+                    z.r[c][q] = f_fma(x1, cs.x, -f_mul(x0, cs.y));
+                }
             }
         }
     }
@@ -606,16 +634,28 @@ AACFB_HD void exs_read(int u, float2 *const *buf, Pts &z) {
 // Index swizzle (both arrays): flipping bit 0 with bit 5 makes the consumers' stride-2 reads
 // (threads own positions 2u + const) conflict-free; flipping bit 4 with bit 7 spreads the four
 // windows a warp's producers write at once over both halves of the banks.
-AACFB_HD int short_swz(int t) { return t ^ ((t >> 5) & 1) ^ (((t >> 7) & 1) << 4); }
+// AACFB_SWZ9: bit 0 additionally flips with bit 9 (bit 2 of the window index): the four windows a
+// warp's producers write at once ({0,1,6,7} / {2,3,4,5}) then cover all 32 banks instead of 16
+// (no 2-way store conflicts), at the price of 2-way conflicts in the quarter of the consumer
+// loads whose two half-warps straddle a 512 boundary.
+#ifndef AACFB_SWZ9
+#define AACFB_SWZ9 1
+#endif
+AACFB_HD int short_swz(int t) {
+    return AACFB_SWZ9 ? t ^ (((t >> 5) ^ (t >> 9)) & 1) ^ (((t >> 7) & 1) << 4) : t ^ ((t >> 5) & 1) ^ (((t >> 7) & 1) << 4);
+}
 
-// Producer: thread u = 8w + g, bins k = 8q + g of window w.  `wshort` carries the output scale
-// (scale_windows), so the products are in output units like the overlap registers.
+// Producer: thread u = 8w + g, bins k = 8q + g of window w.  `wsp[shape][k]` = (W[pa(k)], W[pb(k)]):
+// the two window values a bin needs, as one 8-byte entry (same for every window w: a broadcast
+// load); it carries the output scale (scale_windows), so the products are in output units like
+// the overlap registers.
 template <int C>
-AACFB_HD void short_products(int u, const Pts &z, const float2 *cs256, const float (*wshort)[128], FrameBits fi,
+AACFB_HD void short_products(int u, const Pts &z, const float2 *cs256, const float2 (*wsp)[64], FrameBits fi,
                              float *buf) {
     const int w = u >> 3, g = u & 7;
-    const float *wcur = wshort[fb_shape_cur(fi)];
-    const float *wfirst = w == 0 ? wshort[fb_shape_prev(fi)] : wcur;  // filter_bank.js:153 vs :157-160
+    const float2 *wcur = wsp[fb_shape_cur(fi)];
+    const bool first_differs = fb_shape_prev(fi) != fb_shape_cur(fi);   // (uniform over the worker)
+    const float2 *wfirst = w == 0 ? wsp[fb_shape_prev(fi)] : wcur;      // filter_bank.js:153 vs :157-160
     float *p1 = buf, *p2 = buf + 1024;
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
@@ -627,8 +667,10 @@ AACFB_HD void short_products(int u, const Pts &z, const float2 *cs256, const flo
         // the two positions (one even, one odd) of this bin in either half of the window
         const int pa = q < 4 ? 64 + 2 * k : 2 * (k - 32);
         const int pb = q < 4 ? 63 - 2 * k : 191 - 2 * k;
-        const float wa = wcur[pa], wb = wcur[pb];
-        const float fa = wfirst[pa], fb = wfirst[pb];
+        const float2 wc = wcur[k];
+        float2 wf = wc;
+        if (first_differs) wf = wfirst[k];
+        const float wa = wc.x, wb = wc.y, fa = wf.x, fb = wf.y;
         const int ia = short_swz(128 * w + pa), ib = short_swz(128 * w + pb);
         if (q < 4) {  // k < 32: y[64+2k] = pr, y[63-2k] = -pr, y[192+2k] = y[191-2k] = -pi
             p1[ia] = f_mul(pr, fa);

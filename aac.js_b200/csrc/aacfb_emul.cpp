@@ -33,6 +33,13 @@ struct HostSync {
         bar->arrive_and_wait();
         return r;
     }
+    float partner7(int u, float v) {  // the kernel's __shfl_xor_sync(.., 7)
+        mailbox[u] = v;
+        bar->arrive_and_wait();
+        const float r = mailbox[u ^ 7];
+        bar->arrive_and_wait();
+        return r;
+    }
 };
 }  // namespace
 

@@ -135,6 +135,8 @@ struct DevSync {
     }
     // value of thread 63-u: lane ^ 31 of the same warp (worker_thread_index)
     __device__ __forceinline__ float partner(int, float v) { return __shfl_xor_sync(0xffffffffu, v, 31); }
+    // value of thread u ^ 7 (same window of an EIGHT_SHORT frame, mirrored position): lane ^ 7
+    __device__ __forceinline__ float partner7(int, float v) { return __shfl_xor_sync(0xffffffffu, v, 7); }
 };
 
 // aacfb_frame_info is 8 bytes: one 64-bit load, low word = FrameBits, byte 4 = tns_present

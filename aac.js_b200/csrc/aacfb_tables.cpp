@@ -131,7 +131,10 @@ void build(HostTables &T) {
     const float *wl[2] = {T.sine1024, T.kbd1024};
     const float *ws[2] = {T.sine128, T.kbd128};
     for (int sh = 0; sh < 2; ++sh) {
-        std::memcpy(S.wshort[sh], ws[sh], sizeof(float) * 128);
+        for (int k = 0; k < 64; ++k) {
+            const int pa = k < 32 ? 64 + 2 * k : 2 * (k - 32), pb = k < 32 ? 63 - 2 * k : 191 - 2 * k;
+            S.wsp[sh][k] = f2(ws[sh][pa], ws[sh][pb]);
+        }
         // effective first-half window of LONG_STOP and second-half window of
         // LONG_START, as functions of the output position n in [0,1024)
         float stop_first[1024], start_second[1024];
@@ -207,7 +210,7 @@ void scale_windows(SynthTables &S, float scale) {
             S.fwz_stop[sh][k].x *= scale; S.fwz_stop[sh][k].y *= scale;
             S.swz_start[sh][k].x *= scale; S.swz_start[sh][k].y *= scale;
         }
-        for (int i = 0; i < 128; ++i) S.wshort[sh][i] *= scale;
+        for (int k = 0; k < 64; ++k) { S.wsp[sh][k].x *= scale; S.wsp[sh][k].y *= scale; }
     }
 }
 

@@ -38,7 +38,8 @@ struct alignas(16) SynthTables {
     //       j=0: r64[4g]     j=1: r64[2g]     j=2: r64[2(8+g)]      j=3+q: r64[8q+g]
     float2 twS[64];          // 56 used
     float2 cs256[64];        // MDCT_TABLE_256 rounded to f32
-    float wshort[2][128];    // [shape][i] short windows, natural order
+    float2 wsp[2][64];       // [shape][k] = (W[pa(k)], W[pb(k)]): the two short-window values FFT bin k of a
+                             // window needs (pa = 64+2k | 2(k-32), pb = 63-2k | 191-2k; short_products)
     float2 rootsA[4];        // roots512[64k], k=0..3  (pass A stage i=4)
     float2 roots64A[4];      // roots64[8k],  k=0..3
     // window-switching variants (global memory, read only by START/STOP frames)

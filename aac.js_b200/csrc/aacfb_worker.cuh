@@ -80,7 +80,7 @@ template <int C0, int NCH, bool PK, class Sync>
 AACFB_HD void short_fft(int u, Sync &sync, const FrameIO &io, const SynthTables *ts, Pts &z) {
     const float *row[2] = {io.stage, io.stage + kRowFloats};
     float2 *bufx[2] = {reinterpret_cast<float2 *>(io.scratch), reinterpret_cast<float2 *>(io.scratch + kRowFloats)};
-    short_load<C0, NCH, PK>(u, row, ts->cs256, z);
+    short_load<C0, NCH, PK>(u, sync, row, ts->cs256, z);
     pass_a<C0, NCH, PK>(z, ts->roots64A);
     exs_write<C0, NCH, PK>(u, z, bufx);
     sync.barrier();
@@ -115,10 +115,10 @@ AACFB_HD void frame_with_short(int u, Sync &sync, const FrameIO &io, const Synth
     const bool s1 = io.nch == 2 && is_short(io.fi[1]);
     if (io.nch == 2 && s0 && s1) {
         short_fft<0, 2, PK>(u, sync, io, ts, z);
-        short_products<0>(u, z, ts->cs256, ts->wshort, io.fi[0], io.stage);    // rows are dead since the exchange barrier
+        short_products<0>(u, z, ts->cs256, ts->wsp, io.fi[0], io.stage);    // rows are dead since the exchange barrier
         sync.barrier();
         short_finish<0>(u, io.stage, ov, d.emit, o);
-        short_products<1>(u, z, ts->cs256, ts->wshort, io.fi[1], io.scratch);  // exchange data dead since the last barrier
+        short_products<1>(u, z, ts->cs256, ts->wsp, io.fi[1], io.scratch);  // exchange data dead since the last barrier
         sync.barrier();
         sync.stage_free();                                   // chain 0's IMDCT buffer has been consumed
         short_finish<1>(u, io.scratch, ov, d.emit, o);
@@ -127,7 +127,7 @@ AACFB_HD void frame_with_short(int u, Sync &sync, const FrameIO &io, const Synth
     }
     if (io.nch == 1) {
         short_fft<0, 1, false>(u, sync, io, ts, z);
-        short_products<0>(u, z, ts->cs256, ts->wshort, io.fi[0], io.stage);
+        short_products<0>(u, z, ts->cs256, ts->wsp, io.fi[0], io.stage);
         sync.barrier();
         short_finish<0>(u, io.stage, ov, d.emit, o);
         sync.stage_free();
@@ -138,14 +138,14 @@ AACFB_HD void frame_with_short(int u, Sync &sync, const FrameIO &io, const Synth
         long_fft<1, 1, false, AACFB_ROT != 0>(u, sync, io, ts, z);
         long_finish<1, 1, false, false, false, AACFB_ROT != 0>(u, sync, z, ov, ts, tg, io.fi, d, o);
         short_fft<0, 1, false>(u, sync, io, ts, z);
-        short_products<0>(u, z, ts->cs256, ts->wshort, io.fi[0], io.stage);
+        short_products<0>(u, z, ts->cs256, ts->wsp, io.fi[0], io.stage);
         sync.barrier();
         short_finish<0>(u, io.stage, ov, d.emit, o);
     } else {
         long_fft<0, 1, false, AACFB_ROT != 0>(u, sync, io, ts, z);
         long_finish<0, 1, false, false, false, AACFB_ROT != 0>(u, sync, z, ov, ts, tg, io.fi, d, o);
         short_fft<1, 1, false>(u, sync, io, ts, z);
-        short_products<1>(u, z, ts->cs256, ts->wshort, io.fi[1], io.stage);
+        short_products<1>(u, z, ts->cs256, ts->wsp, io.fi[1], io.stage);
         sync.barrier();
         short_finish<1>(u, io.stage, ov, d.emit, o);
     }

@@ -8,6 +8,13 @@ PCM -- grouped point-to-point sends/receives (NCCL has no scatter/gather primiti
 `torch.distributed.batch_isend_irecv` maps to ncclGroupStart/ncclSend/ncclRecv/End).
 No reduction of any kind exists on this path.  Backend-agnostic: NCCL on GPUs, gloo
 in the CPU tests.
+
+`share_from_root` is the fused alternative on NVLink/NVSwitch boxes: every rank maps rank 0's
+buffers through CUDA IPC and hands the *peer* addresses of its stream range straight to
+`aacfb_process_device`.  The synthesis kernel then is scatter, compute and gather in one: its
+TMA bulk copies pull the spectrum rows (and `cp.async` the side info) from rank 0's HBM over
+NVLink, and its 16-byte PCM stores land in rank 0's output buffer, row by row, overlapped with
+the arithmetic -- no staging copy, no separate collective, both link directions busy at once.
 """
 from __future__ import annotations
 
@@ -60,3 +67,20 @@ def gather_streams(local: torch.Tensor, full: torch.Tensor | None, n_streams: in
     if ops:
         for w in dist.batch_isend_irecv(ops):
             w.wait()
+
+
+def share_from_root(t: torch.Tensor | None, shape, dtype, root: int = 0) -> torch.Tensor:
+    """Every rank gets a tensor that ALIASES root's CUDA tensor `t` (CUDA IPC mapping of the same
+    allocation; peer access over NVLink).  On root this is `t` itself.  One process per GPU on one
+    box; `t` must stay alive on root while the aliases are in use."""
+    rank = dist.get_rank()
+    obj = [None]
+    if rank == root:
+        assert t.is_cuda and t.is_contiguous()
+        obj[0] = (t.untyped_storage()._share_cuda_(), t.storage_offset())
+    dist.broadcast_object_list(obj, src=root)
+    if rank == root:
+        return t
+    handle, offset = obj[0]
+    storage = torch.UntypedStorage._new_shared_cuda(*handle)
+    return torch.empty(0, dtype=dtype, device=storage.device).set_(storage, offset, tuple(shape))

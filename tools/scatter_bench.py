@@ -10,6 +10,10 @@ Reports, as one JSON line from rank 0 (max over ranks, CUDA events):
   e2e_ms     : scatter + synthesis + gather from/to rank 0 -- bounded by rank 0's NVLink
                egress/ingress (~770 GB/s measured per direction), an order of magnitude below the
                kernel's HBM rate, so the two are reported separately.
+  p2p_ms     : the fused path (sharding.share_from_root): every rank runs the synthesis kernel
+               directly on rank 0's buffers mapped through CUDA IPC -- TMA row loads and PCM stores
+               go over NVLink inside the kernel, both directions at once, no staging, no collective.
+               Checked on rank 0 against a local run of a stream that another rank produced.
 """
 import argparse
 import json
@@ -32,6 +36,7 @@ def main():
     ap.add_argument("--streams", type=int, default=1024)
     ap.add_argument("--frames", type=int, default=256)
     ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--no-p2p", action="store_true", help="skip the fused peer-memory path")
     args = ap.parse_args()
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
@@ -79,11 +84,44 @@ def main():
 
     e2e_ms = timed(e2e)
     kernel_ms = timed(kernel)
+
+    # ---- fused: the kernel reads from / writes to rank 0's buffers over NVLink -----------------
+    p2p_ms = p2p_err = None
+    if not args.no_p2p:
+        r_spec = sharding.share_from_root(full_spec, (S, T, C, 1024), torch.float32)
+        r_info = sharding.share_from_root(full_info, (S, T, C, 8), torch.uint8)
+        r_pcm = sharding.share_from_root(full_pcm, (S, T, 1024, C), torch.float32)
+        ctx2 = A.Context(n, C, 4, 0, device=local)
+
+        def p2p():
+            ctx2.process_device(r_spec[lo:hi].data_ptr(), r_info[lo:hi].data_ptr(), r_pcm[lo:hi].data_ptr(), T,
+                                st.cuda_stream)
+
+        if rank == 0:
+            full_pcm.zero_()
+        torch.cuda.synchronize()
+        dist.barrier()
+        p2p()                                   # first step from a zero overlap: the one that is checked
+        torch.cuda.synchronize()
+        dist.barrier()
+        if rank == 0:                           # stream S-1 was produced by the last rank
+            chk = A.Context(1, C, 4, 0, device=local)
+            ref = torch.empty((1, T, 1024, C), device=dev)
+            chk.process_device(full_spec[S - 1:].data_ptr(), full_info[S - 1:].data_ptr(), ref.data_ptr(), T, st.cuda_stream)
+            torch.cuda.synchronize()
+            p2p_err = float((ref[0] - full_pcm[S - 1]).abs().max())
+            assert p2p_err == 0.0 and float(full_pcm[S - 1].abs().max()) > 0, p2p_err
+            chk.close()
+        p2p_ms = timed(p2p)
+        ctx2.close()
     if rank == 0:
         moved = (S - (hi - lo)) * T * C * 4096
         print(json.dumps({"workload": f"config5 mixed long/short, {S} streams x {T} frames stereo, root scatter/gather",
                           "n_gpus": world, "kernel_ms": kernel_ms, "e2e_ms": e2e_ms,
                           "kernel_frames_per_s": S * T / kernel_ms * 1e3, "e2e_frames_per_s": S * T / e2e_ms * 1e3,
+                          "p2p_ms": p2p_ms, "p2p_frames_per_s": S * T / p2p_ms * 1e3 if p2p_ms else None,
+                          "p2p_max_abs_diff_vs_local_run": p2p_err,
+                          "p2p_nvlink_gbs_each_way": moved / (p2p_ms * 1e-3) / 1e9 if p2p_ms else None,
                           "nvlink_bytes_each_way": moved,
                           "nvlink_gbs_each_way": moved / ((e2e_ms - kernel_ms) / 2 * 1e-3) / 1e9 if e2e_ms > kernel_ms else None}))
     ctx.close()
