@@ -69,18 +69,40 @@ def gather_streams(local: torch.Tensor, full: torch.Tensor | None, n_streams: in
             w.wait()
 
 
-def share_from_root(t: torch.Tensor | None, shape, dtype, root: int = 0) -> torch.Tensor:
-    """Every rank gets a tensor that ALIASES root's CUDA tensor `t` (CUDA IPC mapping of the same
-    allocation; peer access over NVLink).  On root this is `t` itself.  One process per GPU on one
-    box; `t` must stay alive on root while the aliases are in use."""
+_ipc_open: dict = {}   # IPC handle bytes -> device pointer of the mapping in this process
+
+
+def share_from_root(t: torch.Tensor | None, root: int = 0) -> int:
+    """Every rank gets the ADDRESS of root's CUDA tensor `t` as seen from its own GPU: the
+    allocation is exported with cudaIpcGetMemHandle on root and opened on every other rank with
+    ITS device current (cudaIpcOpenMemHandle maps into the current device's address space and
+    enables peer access, i.e. NVLink loads/stores from kernels running there).  On root this is
+    `t.data_ptr()`.  One process per GPU on one box; `t` must stay alive on root while in use.
+    (torch's own CUDA-IPC tensor sharing opens the handle with the EXPORTING device current, which
+    makes the alias usable for copies but not for kernels running on another GPU.)"""
+    from cuda.bindings import driver as drv
+    from cuda.bindings import runtime as rt
+
+    def ok(res):
+        err, *out = res
+        if int(err) != 0:
+            raise RuntimeError(f"CUDA error {err}")
+        return out[0] if len(out) == 1 else out
+
     rank = dist.get_rank()
     obj = [None]
     if rank == root:
         assert t.is_cuda and t.is_contiguous()
-        obj[0] = (t.untyped_storage()._share_cuda_(), t.storage_offset())
+        base, _size = ok(drv.cuMemGetAddressRange(t.data_ptr()))
+        handle = ok(rt.cudaIpcGetMemHandle(int(base)))
+        obj[0] = (bytes(handle.reserved), t.data_ptr() - int(base))
     dist.broadcast_object_list(obj, src=root)
     if rank == root:
-        return t
-    handle, offset = obj[0]
-    storage = torch.UntypedStorage._new_shared_cuda(*handle)
-    return torch.empty(0, dtype=dtype, device=storage.device).set_(storage, offset, tuple(shape))
+        return t.data_ptr()
+    raw, offset = obj[0]
+    if raw not in _ipc_open:
+        ok(rt.cudaSetDevice(torch.cuda.current_device()))
+        h = rt.cudaIpcMemHandle_t()
+        h.reserved = raw
+        _ipc_open[raw] = int(ok(rt.cudaIpcOpenMemHandle(h, rt.cudaIpcMemLazyEnablePeerAccess)))
+    return _ipc_open[raw] + offset

@@ -13,7 +13,9 @@ Reports, as one JSON line from rank 0 (max over ranks, CUDA events):
   p2p_ms     : the fused path (sharding.share_from_root): every rank runs the synthesis kernel
                directly on rank 0's buffers mapped through CUDA IPC -- TMA row loads and PCM stores
                go over NVLink inside the kernel, both directions at once, no staging, no collective.
-               Checked on rank 0 against a local run of a stream that another rank produced.
+               Checked twice: every rank reads back over NVLink what its kernel left in rank 0's
+               buffer and compares it bit for bit with its own local run; rank 0 compares the whole
+               buffer with the PCM gathered through NCCL.
 """
 import argparse
 import json
@@ -88,30 +90,60 @@ def main():
     # ---- fused: the kernel reads from / writes to rank 0's buffers over NVLink -----------------
     p2p_ms = p2p_err = None
     if not args.no_p2p:
-        r_spec = sharding.share_from_root(full_spec, (S, T, C, 1024), torch.float32)
-        r_info = sharding.share_from_root(full_info, (S, T, C, 8), torch.uint8)
-        r_pcm = sharding.share_from_root(full_pcm, (S, T, 1024, C), torch.float32)
+        # addresses of rank 0's buffers as seen from this rank's GPU (CUDA IPC, peer access over NVLink)
+        a_spec = sharding.share_from_root(full_spec)
+        a_info = sharding.share_from_root(full_info)
+        a_pcm = sharding.share_from_root(full_pcm)
+        row = T * C * 4096                      # bytes of spectra (= of PCM) per stream
         ctx2 = A.Context(n, C, 4, 0, device=local)
 
         def p2p():
-            ctx2.process_device(r_spec[lo:hi].data_ptr(), r_info[lo:hi].data_ptr(), r_pcm[lo:hi].data_ptr(), T,
-                                st.cuda_stream)
+            ctx2.process_device(a_spec + lo * row, a_info + lo * T * C * 8, a_pcm + lo * row, T, st.cuda_stream)
 
+        # -- check, every rank: (1) local rows -> local PCM (what the scatter path computes),
+        #    (2) rank 0's rows read over NVLink -> local PCM, (3) rank 0's rows -> rank 0's PCM buffer;
+        #    rank 0 then gathers (1) and compares all S streams with what (3) left in full_pcm.
+        def fresh(run_in_spec, run_in_info, run_out):
+            c = A.Context(n, C, 4, 0, device=local)
+            c.process_device(run_in_spec, run_in_info, run_out, T, st.cuda_stream)
+            torch.cuda.synchronize()
+            c.close()
+
+        pcm_b = torch.empty_like(pcm)
         if rank == 0:
             full_pcm.zero_()
         torch.cuda.synchronize()
         dist.barrier()
-        p2p()                                   # first step from a zero overlap: the one that is checked
+        fresh(spec.data_ptr(), info.data_ptr(), pcm.data_ptr())
+        fresh(a_spec + lo * row, a_info + lo * T * C * 8, pcm_b.data_ptr())
+        reads_ok = bool(torch.equal(pcm, pcm_b))
+        p2p()                                   # first step of ctx2 (zero overlap) -> rank 0's buffer
         torch.cuda.synchronize()
         dist.barrier()
-        if rank == 0:                           # stream S-1 was produced by the last rank
-            chk = A.Context(1, C, 4, 0, device=local)
-            ref = torch.empty((1, T, 1024, C), device=dev)
-            chk.process_device(full_spec[S - 1:].data_ptr(), full_info[S - 1:].data_ptr(), ref.data_ptr(), T, st.cuda_stream)
-            torch.cuda.synchronize()
-            p2p_err = float((ref[0] - full_pcm[S - 1]).abs().max())
-            assert p2p_err == 0.0 and float(full_pcm[S - 1].abs().max()) > 0, p2p_err
-            chk.close()
+        # what this rank's kernel left in rank 0's buffer, read back over NVLink by this rank itself
+        from cuda.bindings import runtime as rt
+        back = torch.empty_like(pcm)
+        rt.cudaMemcpy(back.data_ptr(), a_pcm + lo * row, back.numel() * 4, rt.cudaMemcpyKind.cudaMemcpyDefault)
+        torch.cuda.synchronize()
+        own_bad = (back != pcm).reshape(n, -1).any(dim=1)
+        own = torch.tensor([int(own_bad.sum()), int(((back == 0) & (pcm != 0)).sum())], device=dev)
+        own_all = [torch.zeros_like(own) for _ in range(world)]
+        dist.all_gather(own_all, own)
+        del back
+        full_ref = torch.empty_like(full_pcm) if rank == 0 else None
+        sharding.gather_streams(pcm, full_ref, S)
+        flags = torch.tensor([int(reads_ok)], device=dev)
+        dist.all_reduce(flags, op=dist.ReduceOp.MIN)
+        if rank == 0:
+            bad = (full_ref != full_pcm).reshape(S, -1).any(dim=1)
+            p2p_err = {"peer_reads_bit_identical_on_every_rank": bool(flags.item()),
+                       "streams_differing_in_root_buffer": int(bad.sum()),
+                       "per_rank_readback_[streams_differing, samples_left_zero]": [t.tolist() for t in own_all],
+                       "differing_streams_by_rank_region": [int(bad[slice(*sharding.stream_range(S, world, r))].sum()) for r in range(world)],
+                       "max_abs_diff": float((full_ref - full_pcm).abs().max()), "max_abs_pcm": float(full_ref.abs().max())}
+            del full_ref
+        del pcm_b
+        dist.barrier()   # nobody starts overwriting rank 0's buffer (the timing loop) while rank 0 still compares
         p2p_ms = timed(p2p)
         ctx2.close()
     if rank == 0:
@@ -120,7 +152,7 @@ def main():
                           "n_gpus": world, "kernel_ms": kernel_ms, "e2e_ms": e2e_ms,
                           "kernel_frames_per_s": S * T / kernel_ms * 1e3, "e2e_frames_per_s": S * T / e2e_ms * 1e3,
                           "p2p_ms": p2p_ms, "p2p_frames_per_s": S * T / p2p_ms * 1e3 if p2p_ms else None,
-                          "p2p_max_abs_diff_vs_local_run": p2p_err,
+                          "p2p_check": p2p_err,
                           "p2p_nvlink_gbs_each_way": moved / (p2p_ms * 1e-3) / 1e9 if p2p_ms else None,
                           "nvlink_bytes_each_way": moved,
                           "nvlink_gbs_each_way": moved / ((e2e_ms - kernel_ms) / 2 * 1e-3) / 1e9 if e2e_ms > kernel_ms else None}))
