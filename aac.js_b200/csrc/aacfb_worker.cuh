@@ -28,6 +28,11 @@
 #ifndef AACFB_GENERIC_UNIFORM
 #define AACFB_GENERIC_UNIFORM 0   // generic instantiations: also compile the uniform-ONLY_LONG finish
 #endif
+#ifndef AACFB_TW_SYM
+#define AACFB_TW_SYM 0   // EXPERIMENT (off): derive 3 of the 7 FFT twiddles of a 3-stage pass as i * another one
+                         // (roots[k + L/4] = i roots[k] ideally; the reference's recurrence-built table deviates
+                         // by up to 1.8e-6 from that, which is why this is not free for parity -- see load_tw)
+#endif
 #ifndef AACFB_ROT
 #define AACFB_ROT 1     // MDCT twiddles of the pre- and post-twiddle derived by rotation (cs_at)
 #endif
@@ -53,6 +58,15 @@ AACFB_HD bool is_short(FrameBits fi) { return fb_seq(fi) == AACFB_EIGHT_SHORT_SE
 //   long:   rows S -> regs -> X (exchange 1) -> regs -> S (exchange 2) -> regs -> global
 //   short:  rows S -> regs -> X (exchange)   -> regs -> IMDCT buffers S / X -> regs -> global
 
+// The seven twiddles of a 3-stage pass, tw[j] at p[j * stride]: tw[2] = roots[a + L/4], tw[5] = roots[b + L/4],
+// tw[6] = roots[c + L/4] where tw[1] = roots[a], tw[3] = roots[b], tw[4] = roots[c] (tables.h).
+AACFB_HD void load_tw(const float2 *p, int stride, float2 *tw) {
+    tw[0] = p[0]; tw[1] = p[stride]; tw[3] = p[3 * stride]; tw[4] = p[4 * stride];
+    tw[2].x = -tw[1].y; tw[2].y = tw[1].x;
+    tw[5].x = -tw[3].y; tw[5].y = tw[3].x;
+    tw[6].x = -tw[4].y; tw[6].y = tw[4].x;
+}
+
 // 512-point inverse FFT of chains C0..C0+NCH-1 (fft.js:105-192 on the
 // pre-twiddled rows, mdct.js:73-79): two barriers.
 template <int C0, int NCH, bool PK, bool ROT, class Sync>
@@ -65,13 +79,23 @@ AACFB_HD void long_fft(int u, Sync &sync, const FrameIO &io, const SynthTables *
     ex1_write<C0, NCH, PK>(u, z, bufx);
     sync.barrier();  // exchange 1 complete; every thread has consumed its part of the rows
     ex1_read<C0, NCH, PK>(u, bufx, z);
+#if AACFB_TW_SYM
+    float2 twb[7];
+    load_tw(ts->twB + 7 * passb_blo(u), 1, twb);
+    pass_3stage<C0, NCH, PK>(z, twb);
+#else
     pass_3stage<C0, NCH, PK>(z, ts->twB + 7 * passb_blo(u));
+#endif
     ex2_write<C0, NCH, PK>(u, z, bufs);
     sync.barrier();  // exchange 2 complete; exchange-1 data is dead
     ex2_read<C0, NCH, PK>(u, bufs, z);
     float2 twc[7];
+#if AACFB_TW_SYM
+    load_tw(&ts->twC[0][u], 64, twc);
+#else
 #pragma unroll
     for (int j = 0; j < 7; ++j) twc[j] = ts->twC[j][u];
+#endif
     pass_3stage<C0, NCH, PK>(z, twc);
 }
 
@@ -85,7 +109,13 @@ AACFB_HD void short_fft(int u, Sync &sync, const FrameIO &io, const SynthTables 
     exs_write<C0, NCH, PK>(u, z, bufx);
     sync.barrier();
     exs_read<C0, NCH, PK>(u, bufx, z);
+#if AACFB_TW_SYM
+    float2 tws[7];
+    load_tw(ts->twS + 7 * (u & 7), 1, tws);
+    pass_3stage<C0, NCH, PK>(z, tws);
+#else
     pass_3stage<C0, NCH, PK>(z, ts->twS + 7 * (u & 7));
+#endif
 }
 
 // A frame whose chains are all long transforms: two blocking barriers; the PCM
