@@ -290,7 +290,7 @@ def run_ours(args):
         h_pcm = torch.empty((S, T, 1024, C), dtype=torch.float32, pin_memory=True)
         spec_np, pcm_np = h_spec.numpy(), h_pcm.numpy()
         ctx2 = A.Context(S, C, side["sample_index"], side["flags"], device=local)
-        e2e_steps = args.e2e_steps or max(2, min(args.steps, 5))
+        e2e_steps = args.e2e_steps or max(2, min(args.steps, 20))
         for _ in range(2):
             ctx2.process(spec_np, info_np, side["tns_blob"], side["tns_offsets"], out=pcm_np, stereo_ops=ops_np)
         barrier()
@@ -383,7 +383,7 @@ def main():
     ap.add_argument("--frames", type=int, default=0)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--e2e-steps", type=int, default=0, help="timed steps of the e2e leg (default min(steps, 5))")
+    ap.add_argument("--e2e-steps", type=int, default=0, help="timed steps of the e2e leg (default min(steps, 20))")
     ap.add_argument("--no-numa", action="store_true", help="do not bind the process to the GPU's NUMA node")
     args = ap.parse_args()
     if args.impl == "reference":
