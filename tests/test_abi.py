@@ -39,6 +39,8 @@ def test_library_carries_sm100a_code_and_tma():
     assert "sm_100a" in r.stdout
     assert "UBLKCP" in r.stdout and "SYNCS" in r.stdout
     assert "synth_kernel" in r.stdout and "tns_kernel" in r.stdout
+    # the two-chain arithmetic is packed FP32 (fma/mul/add.rn.f32x2), DESIGN.md section 4.1
+    assert "FFMA2" in r.stdout and "FMUL2" in r.stdout and "FADD2" in r.stdout
 
 
 def test_oracle_is_not_linked_into_the_product():
@@ -93,5 +95,6 @@ def test_napi_addon_source_compiles_against_the_header():
     assert r.returncode == 0, r.stderr
     text = open(src).read()
     for sym in ("aacfb_create", "aacfb_process", "aacfb_filterbank_process", "aacfb_tns_process", "aacfb_reset",
-                "aacfb_get_overlap", "aacfb_set_overlap", "aacfb_destroy", "aacfb_last_error"):
+                "aacfb_get_overlap", "aacfb_set_overlap", "aacfb_destroy", "aacfb_last_error", "aacfb_process_stereo",
+                "aacfb_get_swb_offsets"):
         assert sym in text
