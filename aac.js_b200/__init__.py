@@ -37,13 +37,17 @@ INFO_DTYPE = np.dtype(
      ("max_sfb", "u1"), ("tns_present", "u1"), ("stereo_present", "u1"), ("reserved", "u1", (2,))])
 
 ERRORS = {-1: "AACFB_ERR_ARG", -2: "AACFB_ERR_SMALL", -3: "AACFB_ERR_SEQUENCE", -4: "AACFB_ERR_TNS",
-          -5: "AACFB_ERR_CUDA", -6: "AACFB_ERR_NOMEM"}
+          -5: "AACFB_ERR_CUDA", -6: "AACFB_ERR_NOMEM", -7: "AACFB_ERR_ADTS"}
 
 # every symbol include/aacfb.h declares
 ABI_SYMBOLS = ["aacfb_create", "aacfb_destroy", "aacfb_reset", "aacfb_process", "aacfb_process_device",
                "aacfb_filterbank_process", "aacfb_tns_process", "aacfb_get_overlap", "aacfb_set_overlap",
                "aacfb_last_error", "aacfb_version", "aacfb_launch_count", "aacfb_get_table",
-               "aacfb_process_stereo", "aacfb_process_device_stereo", "aacfb_get_swb_offsets"]
+               "aacfb_process_stereo", "aacfb_process_device_stereo", "aacfb_get_swb_offsets", "aacfb_adts_index"]
+
+ADTS_FRAME_DTYPE = np.dtype([("offset", "u8"), ("frame_length", "u4"), ("header_bytes", "u1"), ("profile", "u1"),
+                             ("sampling_index", "u1"), ("chan_config", "u1"), ("num_frames", "u1"), ("reserved", "u1", (7,))])
+assert ADTS_FRAME_DTYPE.itemsize == 24
 
 # aacfb_stereo_ops: what to do to each group of 4 coefficients of a channel pair (include/aacfb.h)
 STEREO_DTYPE = np.dtype([("op", "u1", (256,)), ("scale", "f4", (128,))])
@@ -89,6 +93,8 @@ def lib():
             L.aacfb_process_stereo.argtypes = [vp, vp, vp, vp, vp, vp, vp, ci]
             L.aacfb_process_device_stereo.argtypes = [vp, vp, vp, vp, vp, vp, C.c_size_t, vp, ci, vp]
             L.aacfb_get_swb_offsets.argtypes = [ci, ci, vp, ci]
+        if hasattr(L, "aacfb_adts_index"):
+            L.aacfb_adts_index.argtypes = [vp, C.c_size_t, vp, ci, C.POINTER(C.c_size_t)]
         _lib = L
     return _lib
 
@@ -112,6 +118,24 @@ def swb_offsets(sample_index: int, is_short: bool) -> np.ndarray:
     if n < 0:
         raise AacfbError(n, "bad sample index")
     return out[:n + 1].copy()
+
+
+def adts_index(data, capacity: int | None = None):
+    """Locate the access units of an ADTS byte buffer from their headers alone (the reference's
+    ADTSDemuxer.readHeader, adts_demuxer.js:28-52, hopping by frameLength): returns
+    (frames [n] ADTS_FRAME_DTYPE, consumed) -- `consumed` is where the first incomplete frame
+    starts.  Raises like the reference on a bad syncword ('Invalid ADTS header.')."""
+    buf = np.frombuffer(bytes(data), np.uint8) if not isinstance(data, np.ndarray) else np.ascontiguousarray(data, np.uint8)
+    consumed = C.c_size_t(0)
+    if capacity is None:
+        capacity = lib().aacfb_adts_index(_ptr(buf) if buf.size else None, buf.size, None, 0, C.byref(consumed))
+        if capacity < 0:
+            raise AacfbError(capacity, lib().aacfb_last_error(None).decode())
+    frames = np.zeros(max(capacity, 1), ADTS_FRAME_DTYPE)
+    n = lib().aacfb_adts_index(_ptr(buf) if buf.size else None, buf.size, _ptr(frames), capacity, C.byref(consumed))
+    if n < 0:
+        raise AacfbError(n, lib().aacfb_last_error(None).decode())
+    return frames[:n], int(consumed.value)
 
 
 class Context:

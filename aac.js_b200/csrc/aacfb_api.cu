@@ -285,6 +285,43 @@ API int aacfb_get_swb_offsets(int sample_index, int is_short, uint16_t *dst, int
     return n;
 }
 
+// adts_demuxer.js:28-52 without a bit reader: the header is 7 (or 9) whole bytes.
+static_assert(sizeof(aacfb_adts_frame) == 24, "aacfb_adts_frame layout");
+API int aacfb_adts_index(const uint8_t *data, size_t size, aacfb_adts_frame *frames, int capacity, size_t *consumed) {
+    if (!data && size) return fail(nullptr, AACFB_ERR_ARG, "null buffer");
+    if (capacity < 0) return fail(nullptr, AACFB_ERR_ARG, "negative capacity");
+    size_t p = 0;
+    int n = 0;
+    while (size - p >= 7 && (!frames || n < capacity)) {
+        const uint8_t *h = data + p;
+        if (h[0] != 0xff || (h[1] & 0xf0) != 0xf0) {
+            if (consumed) *consumed = p;
+            return fail(nullptr, AACFB_ERR_ADTS, "Invalid ADTS header.");   // adts_demuxer.js:30
+        }
+        const bool protection_absent = (h[1] & 1) != 0;
+        const uint32_t frame_length = ((uint32_t)(h[3] & 3) << 11) | ((uint32_t)h[4] << 3) | (h[5] >> 5);
+        const uint32_t header_bytes = protection_absent ? 7 : 9;
+        if (frame_length < header_bytes) {
+            if (consumed) *consumed = p;
+            return fail(nullptr, AACFB_ERR_ADTS, "ADTS frame at offset %zu is shorter than its header", p);
+        }
+        if (frame_length > size - p) break;   // incomplete: the next buffer starts here
+        if (frames) {
+            aacfb_adts_frame f{};
+            f.offset = p; f.frame_length = frame_length; f.header_bytes = (uint8_t)header_bytes;
+            f.profile = (uint8_t)(((h[2] >> 6) & 3) + 1);
+            f.sampling_index = (uint8_t)((h[2] >> 2) & 15);
+            f.chan_config = (uint8_t)(((h[2] & 1) << 2) | (h[3] >> 6));
+            f.num_frames = (uint8_t)((h[6] & 3) + 1);
+            frames[n] = f;
+        }
+        ++n;
+        p += frame_length;
+    }
+    if (consumed) *consumed = p;
+    return n;
+}
+
 API int aacfb_create(aacfb_ctx **out, int device, int n_streams, int channels, int sample_index, int small_frames,
                      uint32_t flags) {
     if (!out) return fail(nullptr, AACFB_ERR_ARG, "null out pointer");

@@ -99,6 +99,38 @@ static napi_value js_swb_offsets(napi_env env, napi_callback_info info) {
     return out;
 }
 
+/* adtsIndex(bytes u8, out u32 (3 words per frame: offset, frameLength, headerBytes)) -> number of complete
+ * frames found; out[3n] receives the offset of the first incomplete frame (the rewind point).
+ * ADTSDemuxer.readHeader (adts_demuxer.js:28-52) for every access unit of the buffer at once. */
+static napi_value js_adts_index(napi_env env, napi_callback_info info) {
+    size_t argc = 2; napi_value a[2];
+    NAPI_OK(env, napi_get_cb_info(env, info, &argc, a, NULL, NULL));
+    size_t nbytes = 0, obytes = 0;
+    const uint8_t *data = (const uint8_t *)typed(env, a[0], &nbytes);
+    uint32_t *out = (uint32_t *)typed(env, a[1], &obytes);
+    int cap = (int)(obytes / 12);
+    if (cap > 0) cap -= 1;                     /* the last triple holds the rewind point */
+    aacfb_adts_frame fr[256];
+    size_t pos = 0, consumed = 0;
+    int total = 0;
+    while (total < cap) {
+        int want = cap - total < 256 ? cap - total : 256;
+        int n = aacfb_adts_index(data + pos, nbytes - pos, fr, want, &consumed);
+        if (n < 0) return fail(env, NULL, n);
+        for (int i = 0; i < n; i++) {
+            out[3 * (total + i)] = (uint32_t)(pos + fr[i].offset);
+            out[3 * (total + i) + 1] = fr[i].frame_length;
+            out[3 * (total + i) + 2] = fr[i].header_bytes;
+        }
+        total += n; pos += consumed;
+        if (n < want) break;
+    }
+    if (obytes >= 12) out[3 * total] = (uint32_t)pos;
+    napi_value r;
+    NAPI_OK(env, napi_create_int32(env, total, &r));
+    return r;
+}
+
 /* filterbankProcess(handle, stream, channel, info u8[8], input f32[1024], output f32[1024]) */
 static napi_value js_filterbank(napi_env env, napi_callback_info info) {
     size_t argc = 6; napi_value a[6];
@@ -156,6 +188,7 @@ static napi_value init(napi_env env, napi_value exports) {
         {"process", NULL, js_process, NULL, NULL, NULL, napi_default, NULL},
         {"processStereo", NULL, js_process_stereo, NULL, NULL, NULL, napi_default, NULL},
         {"swbOffsets", NULL, js_swb_offsets, NULL, NULL, NULL, napi_default, NULL},
+        {"adtsIndex", NULL, js_adts_index, NULL, NULL, NULL, napi_default, NULL},
         {"filterbankProcess", NULL, js_filterbank, NULL, NULL, NULL, napi_default, NULL},
         {"tnsProcess", NULL, js_tns, NULL, NULL, NULL, napi_default, NULL},
         {"reset", NULL, js_reset, NULL, NULL, NULL, napi_default, NULL},

@@ -59,7 +59,8 @@ enum {
     AACFB_ERR_SEQUENCE  = -3,  /* window_sequence > 3                           */
     AACFB_ERR_TNS       = -4,  /* TNS order > 20 (tns.js:84-85) or bad blob     */
     AACFB_ERR_CUDA      = -5,  /* CUDA runtime failure / no usable device       */
-    AACFB_ERR_NOMEM     = -6
+    AACFB_ERR_NOMEM     = -6,
+    AACFB_ERR_ADTS      = -7   /* "Invalid ADTS header." adts_demuxer.js:29-30  */
 };
 
 /* create() flags ---------------------------------------------------------- */
@@ -211,6 +212,34 @@ int aacfb_get_table(int which, float *dst, int capacity);
  * sample rate: is_short = 0 -> SWB_OFFSET_1024[sample_index], 1 -> SWB_OFFSET_128.
  * Returns the number of bands (swbCount); dst receives swbCount + 1 offsets. */
 int aacfb_get_swb_offsets(int sample_index, int is_short, uint16_t *dst, int capacity);
+
+/* ADTS frame index (host-side, no device work) -- SURVEY section 8(f) row 3.
+ * The reference reads one ADTS header per access unit inside the serial decode
+ * loop (decoder.js:129-130 -> ADTSDemuxer.readHeader, adts_demuxer.js:28-52), but
+ * the header alone says where the next access unit starts (frameLength), so a
+ * host can locate every frame of a buffer WITHOUT entropy decoding and parse the
+ * frames of a batch independently (one parser per core) before one aacfb_process
+ * call.  Field for field what readHeader returns, plus the byte offset:
+ *     12 bits 0xfff | 3 skipped | protectionAbsent | profile-1 (2) | samplingIndex (4)
+ *     | 1 skipped | chanConfig (3) | 4 skipped | frameLength (13) | 11 skipped
+ *     | numFrames-1 (2) | 16 more bits (CRC) if !protectionAbsent                    */
+typedef struct aacfb_adts_frame {
+    uint64_t offset;          /* byte offset of the syncword in `data`             */
+    uint32_t frame_length;    /* ret.frameLength: bytes to the next syncword        */
+    uint8_t  header_bytes;    /* 7, or 9 with CRC (what readHeader consumes)        */
+    uint8_t  profile;         /* ret.profile = field + 1                            */
+    uint8_t  sampling_index;  /* ret.samplingIndex                                  */
+    uint8_t  chan_config;     /* ret.chanConfig                                     */
+    uint8_t  num_frames;      /* ret.numFrames = field + 1                          */
+    uint8_t  reserved[7];     /* sizeof == 24                                       */
+} aacfb_adts_frame;
+/* Walks data[0, size) from a syncword at offset 0.  Fills up to `capacity` frames
+ * (frames may be NULL to count only) and stops at the first frame that is not
+ * completely inside the buffer; *consumed (may be NULL) = offset of that frame =
+ * where the next buffer has to start (the batching decoder's rewind point).
+ * Returns the number of complete frames, or AACFB_ERR_ADTS when a header does not
+ * start with 0xfff or announces a frame shorter than its own header. */
+int aacfb_adts_index(const uint8_t *data, size_t size, aacfb_adts_frame *frames, int capacity, size_t *consumed);
 
 #ifdef __cplusplus
 }

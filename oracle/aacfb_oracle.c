@@ -498,6 +498,38 @@ void aacfb_oracle_stereo(const oracle_cpe *e, int sample_index, float *left, flo
     process_is(e, sample_index, left, right);
 }
 
+/* ------------------------------------------------------------- ADTS header */
+
+/* AV.Bitstream as readHeader uses it: read(n) MSB first, advance(n). */
+typedef struct { const uint8_t *p; size_t bit, bits; } obits;
+static uint32_t ob_read(obits *b, int n) {
+    uint32_t v = 0;
+    for (int i = 0; i < n; i++, b->bit++) v = (v << 1) | (b->bit < b->bits ? (b->p[b->bit >> 3] >> (7 - (b->bit & 7))) & 1u : 0u);
+    return v;
+}
+static void ob_advance(obits *b, int n) { b->bit += (size_t)n; }
+
+/* adts_demuxer.js:28-52, statement by statement.  out[0..5] = profile, samplingIndex, chanConfig,
+ * frameLength, numFrames, bits consumed.  Returns 0, or -1 for 'Invalid ADTS header.' */
+__attribute__((visibility("default")))
+int aacfb_oracle_adts_header(const uint8_t *data, size_t size, uint32_t *out) {
+    obits st = {data, 0, size * 8};
+    if (ob_read(&st, 12) != 0xfff) return -1;                 /* :29-30 */
+    ob_advance(&st, 3);                                       /* :33 mpeg version and layer */
+    const int protectionAbsent = ob_read(&st, 1) != 0;        /* :34 */
+    out[0] = ob_read(&st, 2) + 1;                             /* :36 profile */
+    out[1] = ob_read(&st, 4);                                 /* :37 samplingIndex */
+    ob_advance(&st, 1);                                       /* :39 private */
+    out[2] = ob_read(&st, 3);                                 /* :40 chanConfig */
+    ob_advance(&st, 4);                                       /* :41 */
+    out[3] = ob_read(&st, 13);                                /* :43 frameLength */
+    ob_advance(&st, 11);                                      /* :44 fullness */
+    out[4] = ob_read(&st, 2) + 1;                             /* :46 numFrames */
+    if (!protectionAbsent) ob_advance(&st, 16);               /* :48-49 */
+    out[5] = (uint32_t)st.bit;
+    return 0;
+}
+
 /* --------------------------------------------------------- exported entry */
 
 #define API __attribute__((visibility("default")))

@@ -54,6 +54,8 @@ def lib():
         L.aacfb_oracle_process.restype = C.c_int
         L.aacfb_oracle_stereo.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.aacfb_oracle_stereo.restype = None
+        L.aacfb_oracle_adts_header.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p]
+        L.aacfb_oracle_adts_header.restype = C.c_int
         L.aacfb_oracle_init()
         _lib = L
     return _lib
@@ -158,3 +160,14 @@ def stereo(cpe: np.ndarray, sample_index: int, left: np.ndarray, right: np.ndarr
     r = np.ascontiguousarray(right, np.float32).copy()
     lib().aacfb_oracle_stereo(_p(cpe), sample_index, _p(l), _p(r))
     return l, r
+
+
+def adts_header(data: bytes):
+    """ADTSDemuxer.readHeader (adts_demuxer.js:28-52) on the bytes at the start of `data`:
+    dict(profile, samplingIndex, chanConfig, frameLength, numFrames, bits) or None for
+    'Invalid ADTS header.'"""
+    buf = np.frombuffer(bytes(data), np.uint8)
+    out = np.zeros(6, np.uint32)
+    if lib().aacfb_oracle_adts_header(_p(buf), buf.size, _p(out)) != 0:
+        return None
+    return dict(zip(("profile", "samplingIndex", "chanConfig", "frameLength", "numFrames", "bits"), (int(v) for v in out)))

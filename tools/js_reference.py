@@ -28,6 +28,42 @@ from tools import workloads as W  # noqa: E402
 REF_SRC = "/root/reference/src"
 
 
+class AdtsReference:
+    """ADTSDemuxer.readHeader (adts_demuxer.js:28-52) cut out of the file -- the module itself needs
+    the `av` peer dependency -- and run by the interpreter on a Python-side bit reader that offers
+    the two AV.Bitstream methods it calls (read(n) MSB first, advance(n))."""
+
+    def __init__(self, src_dir=REF_SRC):
+        text = open(os.path.join(src_dir, "adts_demuxer.js")).read()
+        m = re.search(r"this\.readHeader = (function\(stream\) \{\n.*?\n    \});", text, re.S)
+        assert m, "adts_demuxer.js readHeader not found"
+        self.fn = J.Runtime(src_dir).run("var readHeader = %s;\n" % m.group(1))["readHeader"]
+
+    def read_header(self, data: bytes):
+        pos = [0]
+
+        def read(this, args):
+            n, v = int(J.to_number(args[0])), 0
+            for _ in range(n):
+                byte = data[pos[0] >> 3] if (pos[0] >> 3) < len(data) else 0
+                v = (v << 1) | ((byte >> (7 - (pos[0] & 7))) & 1)
+                pos[0] += 1
+            return float(v)
+
+        def advance(this, args):
+            pos[0] += int(J.to_number(args[0]))
+            return J.UNDEF
+
+        stream = J.obj(read=J.native(read), advance=J.native(advance))
+        try:
+            ret = self.fn.call(J.UNDEF, [stream])
+        except J.JSThrow as e:   # `throw new Error('Invalid ADTS header.')`
+            return None, str(e)   # JSThrow carries the Error's message
+        out = {k: int(J.to_number(ret.get(k))) for k in ("profile", "samplingIndex", "chanConfig", "frameLength", "numFrames")}
+        out["bits"] = pos[0]
+        return out, None
+
+
 class Reference:
     def __init__(self, src_dir=REF_SRC, fix_tns=False):
         self.rt = J.Runtime(src_dir)
@@ -228,5 +264,22 @@ def main_stereo():
     print("stereo", ol.shape, pcm.shape, int((ol != left).any(axis=1).sum()), int((orr != right).any(axis=1).sum()))
 
 
+def main_adts():
+    """ADTSDemuxer.readHeader run by the interpreter on every frame of a seeded synthetic ADTS stream."""
+    out_dir = os.path.join(ROOT, "tests", "golden", "adts")
+    os.makedirs(out_dir, exist_ok=True)
+    data, _ = W.adts_stream(np.random.default_rng(90), 64)
+    ref, p, rows = AdtsReference(), 0, []
+    while p + 7 <= len(data):
+        h, err = ref.read_header(data[p:])
+        assert err is None
+        rows.append([p, h["frameLength"], h["bits"], h["profile"], h["samplingIndex"], h["chanConfig"], h["numFrames"]])
+        p += h["frameLength"]
+    _, msg = ref.read_header(b"\xff\xe1" + bytes(8))
+    np.savez_compressed(os.path.join(out_dir, "jsref_adts.npz"), headers=np.asarray(rows, np.int64),
+                        meta=np.array([90, 64]), error=np.frombuffer(msg.encode(), np.uint8))
+    print("adts", len(rows), "frames;", msg)
+
+
 if __name__ == "__main__":
-    main_stereo() if sys.argv[1:] == ["stereo"] else main()
+    {"stereo": main_stereo, "adts": main_adts}.get((sys.argv[1:] or [""])[0], main)()

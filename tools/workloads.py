@@ -242,3 +242,26 @@ def joint_stereo_ops(S, T, seed=0):
         ops["op"][..., edges[k] // 4: edges[k + 1] // 4] = 2 + k
     ops["scale"][..., :6] = (0.5 ** (rng.integers(-8, 8, (S, T, 1, 6)) / 4.0)).astype(np.float32)
     return ops
+
+
+def adts_stream(rng, n_frames, crc_every=3, sampling_index=4, chan_config=2):
+    """A synthetic ADTS byte stream: n_frames access units with random payload sizes; every
+    `crc_every`-th header carries the 16-bit CRC field (protection_absent = 0).  Returns
+    (bytes, [(offset, frame_length, header_bytes, profile, num_frames)])."""
+    out, meta = bytearray(), []
+    for i in range(n_frames):
+        prot_absent = 0 if (crc_every and i % crc_every == crc_every - 1) else 1
+        hdr = 7 if prot_absent else 9
+        length = hdr + int(rng.integers(0, 1500))
+        profile_field, nf_field = int(rng.integers(0, 4)), int(rng.integers(0, 4))
+        bits = 0
+        def put(v, n):
+            nonlocal bits
+            bits = (bits << n) | (v & ((1 << n) - 1))
+        put(0xfff, 12); put(int(rng.integers(0, 8)), 3); put(prot_absent, 1)
+        put(profile_field, 2); put(sampling_index, 4); put(int(rng.integers(0, 2)), 1); put(chan_config, 3)
+        put(int(rng.integers(0, 16)), 4); put(length, 13); put(int(rng.integers(0, 2048)), 11); put(nf_field, 2)
+        h = bits.to_bytes(7, "big")
+        meta.append((len(out), length, hdr, profile_field + 1, nf_field + 1))
+        out += h + bytes(rng.integers(0, 256, length - 7, dtype=np.uint8))
+    return bytes(out), meta
