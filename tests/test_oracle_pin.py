@@ -122,3 +122,28 @@ def test_reference_tables_through_the_interpreter():
         assert np.array_equal(js.view(np.uint32), O.table(which).view(np.uint32))
     with pytest.raises(J.JSThrow, match="No small frames allowed"):
         rt.require("./filter_bank").construct([True, 2.0])
+
+
+def test_jsmini_host_side_features():
+    """What the JS host files under aac.js_b200/js need beyond the reference's own sources:
+    ArrayBuffer + typed-array views + DataView, TypedArray.set, try / catch / finally with
+    instanceof dispatch, Function.prototype.call / apply, Array.prototype.push."""
+    s = run("""
+        var buf = new ArrayBuffer(32), b = new Uint8Array(buf), v = new DataView(buf);
+        v.setFloat32(4, 1.5, true); v.setUint16(0, 0x1234, false); b[2] = 7;
+        var f = new Float32Array(buf, 4, 2), x = f[0]; f[1] = 2.25;
+        var g = v.getFloat32(8, true), n = buf.byteLength, b0 = b[0], b1 = b[1];
+        var big = new Float32Array(8); big.set(f, 3); var y = big[4];
+        function E1() {} function E2() {}
+        var log = [];
+        function t(k) { try { if (k == 1) throw new E1(); if (k == 2) throw new E2(); log.push('ok'); return 1; }
+                        catch (err) { if (!(err instanceof E1)) throw err; log.push('caught'); return 2; }
+                        finally { log.push('fin'); } }
+        var r0 = t(0), r1 = t(1), r2;
+        try { t(2); } catch (e) { r2 = e instanceof E2; }
+        function who(a, b) { return this.tag + a + b; }
+        var c1 = who.call({tag: 10}, 1, 2), c2 = who.apply({tag: 20}, [3, 4]);
+    """)
+    assert (s["x"], s["g"], s["n"], s["y"], s["b0"], s["b1"]) == (1.5, 2.25, 32.0, 2.25, 0x12, 0x34)
+    assert (s["r0"], s["r1"], s["r2"], s["c1"], s["c2"]) == (1.0, 2.0, True, 13.0, 27.0)
+    assert [J.to_string(v) for v in s["log"].items] == ["ok", "fin", "caught", "fin", "fin"]

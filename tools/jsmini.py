@@ -133,6 +133,11 @@ class JSTyped(JSObject):
         super().__init__(OBJECT_PROTO, kind)
         self.kind, self.a = kind, a
 
+    def get(self, key):
+        if key == "set" and "set" not in self.props:
+            return native(typed_set)
+        return super().get(key)
+
 
 OBJECT_PROTO = JSObject(None)
 FUNCTION_PROTO = JSObject(OBJECT_PROTO)
@@ -319,7 +324,8 @@ TOKEN_RE = re.compile(r"""
 """, re.S | re.X)
 
 KEYWORDS = {"var", "const", "function", "return", "if", "else", "for", "while", "do", "break", "continue", "switch",
-            "case", "default", "new", "this", "throw", "typeof", "null", "true", "false", "instanceof", "undefined"}
+            "case", "default", "new", "this", "throw", "typeof", "null", "true", "false", "instanceof", "undefined",
+            "try", "catch", "finally"}
 
 
 def tokenize(src):
@@ -468,6 +474,17 @@ class Parser:
                 e = self.expression()
                 self.semi()
                 return ("throw", e)
+            if v == "try":
+                self.next()
+                body, name, handler, final = self.block(), None, None, None
+                if self.eat("kw", "catch"):
+                    self.expect("op", "(")
+                    name = self.expect("id")[1]
+                    self.expect("op", ")")
+                    handler = self.block()
+                if self.eat("kw", "finally"):
+                    final = self.block()
+                return ("try", body, name, handler, final)
             if v == "switch":
                 self.next()
                 self.expect("op", "(")
@@ -1014,6 +1031,24 @@ def compile_node(n):  # noqa: C901  (a flat dispatcher)
         def f_throw(env):
             raise JSThrow(fe(env))
         return f_throw
+    if tag == "try":
+        fb = compile_node(n[1])
+        name = n[2]
+        fh = compile_node(n[3]) if n[3] is not None else None
+        ff = compile_node(n[4]) if n[4] is not None else None
+
+        def f_try(env):
+            try:
+                try:
+                    fb(env)
+                except JSThrow as t:
+                    if fh is None:
+                        raise
+                    fh(({name: t.value}, env))   # the catch parameter lives in its own scope
+            finally:
+                if ff is not None:
+                    ff(env)
+        return f_try
     if tag == "switch":
         fd = compile_node(n[1])
         cases = [(compile_node(t) if t is not None else None, [compile_node(s) for s in body]) for t, body in n[2]]
@@ -1047,6 +1082,25 @@ def native(fn):
     return JSFunction(native=lambda this, args, new=False: fn(this, args))
 
 
+def _fn_call(this, args):      # Function.prototype.call(thisArg, ...args)
+    return this.call(args[0] if args else UNDEF, list(args[1:]))
+
+
+def _fn_apply(this, args):     # Function.prototype.apply(thisArg, argsArray)
+    arr = args[1] if len(args) > 1 else UNDEF
+    return this.call(args[0] if args else UNDEF, list(arr.items) if isinstance(arr, JSArray) else [])
+
+
+def _array_push(this, args):   # Array.prototype.push
+    this.items.extend(args)
+    return float(len(this.items))
+
+
+ARRAY_PROTO.props["push"] = native(_array_push)
+FUNCTION_PROTO.props["call"] = native(_fn_call)
+FUNCTION_PROTO.props["apply"] = native(_fn_apply)
+
+
 def js_max(this, args):
     r = -math.inf
     for a in args:
@@ -1075,11 +1129,76 @@ def js_pow(this, args):
         return math.nan
 
 
+class JSArrayBuffer(JSObject):
+    """ArrayBuffer: raw bytes; typed-array views and DataViews alias it (numpy views)."""
+    __slots__ = ("b",)
+
+    def __init__(self, nbytes):
+        super().__init__(OBJECT_PROTO, "ArrayBuffer")
+        self.b = np.zeros(int(nbytes), np.uint8)
+        self.props["byteLength"] = float(int(nbytes))
+
+
+def arraybuffer_ctor(this, args, new=False):
+    return JSArrayBuffer(to_number(args[0]) if args else 0)
+
+
+def dataview_ctor(this, args, new=False):
+    buf = args[0]
+    assert isinstance(buf, JSArrayBuffer), "DataView needs an ArrayBuffer"
+    base = int(to_number(args[1])) if len(args) > 1 and args[1] is not UNDEF else 0
+    view = JSObject(OBJECT_PROTO, "DataView")
+    view.props["buffer"] = buf
+
+    def accessor(fmt, size, setter):
+        def fn(this_, a):
+            import struct
+
+            at = base + int(to_number(a[0]))
+            little = to_bool(a[2 if setter else 1]) if len(a) > (2 if setter else 1) else False
+            code = ("<" if little else ">") + fmt
+            if setter:
+                v = to_number(a[1])
+                if fmt in "bBhHiI":
+                    v = to_int32(v) & ((1 << (8 * size)) - 1) if fmt in "BHI" else int(np.array(to_int32(v)).astype(
+                        {1: np.int8, 2: np.int16, 4: np.int32}[size]))
+                buf.b[at:at + size] = np.frombuffer(struct.pack(code, v), np.uint8)
+                return UNDEF
+            return float(struct.unpack(code, bytes(buf.b[at:at + size]))[0])
+        return native(fn)
+
+    for name, fmt, size in (("Float32", "f", 4), ("Float64", "d", 8), ("Uint8", "B", 1), ("Int8", "b", 1), ("Uint16", "H", 2),
+                            ("Int16", "h", 2), ("Uint32", "I", 4), ("Int32", "i", 4)):
+        view.props["set" + name] = accessor(fmt, size, True)
+        view.props["get" + name] = accessor(fmt, size, False)
+    return view
+
+
+def typed_set(this, args):
+    """TypedArray.prototype.set(source[, offset])"""
+    src, off = args[0], int(to_number(args[1])) if len(args) > 1 and args[1] is not UNDEF else 0
+    if isinstance(src, JSTyped):
+        this.a[off:off + src.a.size] = src.a.astype(this.a.dtype)
+    else:
+        for i, v in enumerate(src.items):
+            set_member(this, float(off + i), v)
+    return UNDEF
+
+
 def make_typed_ctor(kind):
     dt = TYPED[kind]
 
     def ctor(this, args, new=False):
         a0 = args[0] if args else 0.0
+        if isinstance(a0, JSArrayBuffer):   # a view: new T(buffer[, byteOffset[, length]])
+            off = int(to_number(args[1])) if len(args) > 1 and args[1] is not UNDEF else 0
+            isz = np.dtype(dt).itemsize
+            n = int(to_number(args[2])) if len(args) > 2 and args[2] is not UNDEF else (a0.b.size - off) // isz
+            assert off % isz == 0, "typed-array view must be aligned"
+            t = JSTyped(kind, a0.b[off:off + n * isz].view(dt))
+            t.props["buffer"] = a0
+            t.props["set"] = native(typed_set)
+            return t
         if isinstance(a0, JSArray):
             t = JSTyped(kind, np.zeros(len(a0.items), dt))
             for i, v in enumerate(a0.items):
@@ -1116,6 +1235,8 @@ def make_globals():
     for kind in TYPED:
         g[kind] = make_typed_ctor(kind)
     g["Array"] = JSFunction(native=array_ctor)
+    g["ArrayBuffer"] = JSFunction(native=arraybuffer_ctor)
+    g["DataView"] = JSFunction(native=dataview_ctor)
     g["Error"] = JSFunction(native=error_ctor)
     g["Error"].props["prototype"] = ERROR_PROTO
     g["NaN"], g["Infinity"], g["undefined"] = math.nan, math.inf, UNDEF
