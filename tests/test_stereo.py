@@ -219,3 +219,57 @@ def test_gpu_stereo_records_without_flag_are_ignored_and_bad_ops_rejected():
     with pytest.raises(A.AacfbError):
         ctx.process(case["spectra"], wrong, stereo_ops=ops)
     ctx.close()
+
+
+# ------------------------------------------------- the reference's own decoder.process as the driver
+DEC_GOLD = os.path.join(os.path.dirname(__file__), "golden", "stereo", "jsref_decoder_process.npz")
+
+
+def decoder_fixture():
+    from tools.js_reference import decoder_case
+
+    z = np.load(DEC_GOLD)
+    seed, T, mseed, mT = (int(v) for v in z["meta"])
+    return z, decoder_case(seed, T), W.make(5, 1, mT, 1, seed=mseed, shape_prev_mode="carried")
+
+
+def test_oracle_equals_unmodified_decoder_process_bit_for_bit():
+    """tests/golden/stereo/jsref_decoder_process.npz was produced by the reference's UNMODIFIED decoder.js
+    (AACDecoder.prototype.process: processPair / processSingle -> processMS, processIS, tns.process,
+    filter_bank.process, then the interleave of readChunk) on elements built with the reference's own
+    ICStream / CPEElement constructors (tools/js_reference.DecoderReference).  The oracle's restatement
+    composed the same way reproduces every bit of PCM and overlap, stereo and mono."""
+    z, case, mono = decoder_fixture()
+    pcm, ovl = O.process(oracle_stereo_spectra(case), case["info"], sample_index=4)
+    assert np.array_equal(bits(pcm[0]), bits(z["pcm"])) and np.array_equal(bits(ovl[0]), bits(z["overlap"]))
+    mp, mo = O.process(mono["spectra"], mono["info"], sample_index=4)
+    assert np.array_equal(bits(mp[0]), bits(z["mono_pcm"])) and np.array_equal(bits(mo[0]), bits(z["mono_overlap"]))
+    assert float(np.abs(z["pcm"]).max()) > 0.1
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="/root/reference is not on this machine")
+def test_oracle_equals_decoder_process_live():
+    from tools.js_reference import DecoderReference, decoder_case
+
+    case = decoder_case(seed=4242, T=6)
+    jp, jo = DecoderReference(2).run_stereo_stream(case["spectra"][0], case["info"][0], case["cpe"][0])
+    pcm, ovl = O.process(oracle_stereo_spectra(case), case["info"], sample_index=4)
+    assert np.array_equal(bits(pcm[0]), bits(jp)) and np.array_equal(bits(ovl[0]), bits(jo))
+
+
+@pytest.mark.gpu
+def test_gpu_equals_unmodified_decoder_process():
+    """The CUDA path (stereo tools on the device) against the reference's own decoder.process output."""
+    z, case, mono = decoder_fixture()
+    info, ops = pack_case(case)
+    ctx = A.Context(1, 2, 4, 0)
+    got = ctx.process(case["spectra"], info, stereo_ops=ops)
+    gov = ctx.get_overlap()
+    ctx.close()
+    scale = max(1.0, float(np.abs(z["pcm"]).max()))
+    assert np.abs(got[0].astype(np.float64) - z["pcm"]).max() <= TOL * scale
+    assert np.abs(gov[0] - z["overlap"]).max() / 32768 <= TOL * scale
+    ctx = A.Context(1, 1, 4, 0)
+    got = ctx.process(mono["spectra"], mono["info"])
+    ctx.close()
+    assert np.abs(got[0].astype(np.float64) - z["mono_pcm"]).max() <= TOL * max(1.0, float(np.abs(z["mono_pcm"]).max()))

@@ -28,6 +28,109 @@ from tools import workloads as W  # noqa: E402
 REF_SRC = "/root/reference/src"
 
 
+AV_STUB = """
+function Base() {}
+function makeExtend(Parent) {           // Aurora's class helper: Base.extend(function() { this.prototype.x = ... })
+    return function(init) {
+        function K() {}
+        function P() {}
+        P.prototype = Parent.prototype;
+        K.prototype = new P();
+        K.extend = makeExtend(K);
+        K.register = function() {};
+        init.call(K);
+        return K;
+    };
+}
+var AV = {Decoder: {extend: makeExtend(Base), register: function() {}},
+          Demuxer: {extend: makeExtend(Base), register: function() {}}};
+"""
+
+
+class DecoderReference:
+    """The reference's UNMODIFIED src/decoder.js (and everything it requires) loaded on a stand-in
+    for its one missing dependency, the `av` peer package (only `AV.Decoder.extend/register` and
+    `AV.Demuxer.extend/register` are needed to load the modules).  Elements are built with the
+    reference's own constructors (`new ICStream(config)`, `new CPEElement(config)`), filled with what
+    the bit parse would have left behind, and handed to `AACDecoder.prototype.process` -- processPair
+    / processSingle, processMS, processIS, tns.process, filter_bank.process exactly as decoder.js
+    :218-334 chains them -- followed by the interleave lines of readChunk (:204-213)."""
+
+    def __init__(self, channels, sample_index=4, src_dir=REF_SRC):
+        self.rt = J.Runtime(src_dir)
+        self.rt.stubs["av"] = self.rt.run(AV_STUB)["AV"]
+        self.Decoder = self.rt.require("./decoder")
+        self.ICStream = self.rt.require("./ics")
+        self.CPEElement = self.rt.require("./cpe")
+        self.FilterBank = self.rt.require("./filter_bank")
+        self.tables = self.rt.require("./tables")
+        self.sample_index, self.channels = sample_index, channels
+        self.config = J.obj(profile=2, chanConfig=channels, frameLength=1024, sampleIndex=sample_index)  # AOT_AAC_LC
+        self.dec = self.Decoder.construct([])
+        self.dec.put("config", self.config)
+        self.dec.put("filter_bank", self.FilterBank.construct([False, float(channels)]))   # decoder.js:112
+        self.dec.put("cces", J.JSArray([]))
+        text = open(os.path.join(src_dir, "decoder.js")).read()
+        m = re.search(r"// Interleave channels\n(.*?)\n\s*return output;", text, re.S)
+        self.interleave_src = m.group(1)
+
+    def ics(self, fi, data, cpe=None, c=0):
+        """An ICStream as ICStream.decode would leave it (ics.js:56-81) for one channel-frame."""
+        s = self.ICStream.construct([self.config])
+        info = s.get("info")
+        seq = int(fi["window_sequence"])
+        short = seq == 2
+        info.put("windowSequence", float(seq))
+        info.get("windowShape").a[:] = [int(fi["shape_prev"]), int(fi["shape_cur"])]
+        which = ("SWB_OFFSET_128", "SWB_SHORT_WINDOW_COUNT") if short else ("SWB_OFFSET_1024", "SWB_LONG_WINDOW_COUNT")
+        info.put("swbOffsets", J.get_member(self.tables.get(which[0]), float(self.sample_index)))
+        info.put("swbCount", J.get_member(self.tables.get(which[1]), float(self.sample_index)))
+        info.put("windowCount", 8.0 if short else 1.0)
+        if cpe is not None:
+            info.put("groupCount", float(cpe["group_count"][c]))
+            info.get("groupLength").a[:8] = cpe["group_length"][c]
+            info.put("maxSFB", float(cpe["max_sfb"][c]))
+            s.get("bandTypes").a[:120] = cpe["band_types"][c]
+            s.get("sectEnd").a[:120] = cpe["sect_end"][c]
+            s.get("scaleFactors").a[:120] = cpe["scale_factors"][c]
+        else:
+            info.put("groupCount", 1.0)
+            info.put("maxSFB", float(fi["max_sfb"]))
+        s.get("data").a[:] = data
+        s.put("tnsPresent", False)
+        return s
+
+    def process_frame(self, elements):
+        self.dec.get("process").call(self.dec, [J.JSArray(elements)])
+        scope = self.rt.run(self.interleave_src, {"this": self.dec, "frameLength": 1024.0})
+        return scope["output"].a.copy()
+
+    def run_stereo_stream(self, spectra, info, cpe):
+        """[T][2][1024] spectra before the stereo tools -> (pcm [T][1024][2], overlaps [2][1024])."""
+        T = spectra.shape[0]
+        pcm = np.empty((T, 1024, 2), np.float32)
+        for t in range(T):
+            e = self.CPEElement.construct([self.config])
+            left = self.ics(info[t, 0], spectra[t, 0], cpe[t], 0)
+            right = self.ics(info[t, 1], spectra[t, 1], cpe[t], 1)
+            if cpe[t]["common_window"]:
+                right.put("info", left.get("info"))     # cpe.js:41
+            e.put("left", left); e.put("right", right)
+            e.put("commonWindow", bool(cpe[t]["common_window"]))
+            e.put("maskPresent", bool(cpe[t]["mask_present"]))
+            e.put("ms_used", J.JSArray([bool(v) for v in cpe[t]["ms_used"]]))
+            pcm[t] = self.process_frame([e]).reshape(1024, 2)
+        ovl = np.stack([o.a.copy() for o in self.dec.get("filter_bank").get("overlaps").items])
+        return pcm, ovl
+
+    def run_mono_stream(self, spectra, info):
+        T = spectra.shape[0]
+        pcm = np.empty((T, 1024, 1), np.float32)
+        for t in range(T):
+            pcm[t] = self.process_frame([self.ics(info[t, 0], spectra[t, 0])]).reshape(1024, 1)
+        return pcm, np.stack([o.a.copy() for o in self.dec.get("filter_bank").get("overlaps").items])
+
+
 class AdtsReference:
     """ADTSDemuxer.readHeader (adts_demuxer.js:28-52) cut out of the file -- the module itself needs
     the `av` peer dependency -- and run by the interpreter on a Python-side bit reader that offers
@@ -264,6 +367,29 @@ def main_stereo():
     print("stereo", ol.shape, pcm.shape, int((ol != left).any(axis=1).sum()), int((orr != right).any(axis=1).sum()))
 
 
+def decoder_case(seed=81, T=10):
+    """The seeded stereo stream of tests/golden/stereo/jsref_decoder_process.npz: common-window pairs keep
+    one window sequence/shape for both channels (cpe.js:40-42: right.info IS left.info)."""
+    case = W.random_stereo_case(1, T, np.random.default_rng(seed), sigma=2e4)
+    for t in range(T):
+        if case["cpe"][0, t]["common_window"]:
+            case["info"][0, t, 1] = case["info"][0, t, 0]
+    return case
+
+
+def main_decoder():
+    """AACDecoder.process + interleave of the unmodified decoder.js on a stereo and a mono stream."""
+    out_dir = os.path.join(ROOT, "tests", "golden", "stereo")
+    os.makedirs(out_dir, exist_ok=True)
+    case = decoder_case()
+    pcm, ovl = DecoderReference(2).run_stereo_stream(case["spectra"][0], case["info"][0], case["cpe"][0])
+    mono = W.make(5, 1, 18, 1, seed=82, shape_prev_mode="carried")
+    mpcm, movl = DecoderReference(1).run_mono_stream(mono["spectra"][0], mono["info"][0])
+    np.savez_compressed(os.path.join(out_dir, "jsref_decoder_process.npz"), pcm=pcm, overlap=ovl, mono_pcm=mpcm,
+                        mono_overlap=movl, meta=np.array([81, 10, 82, 18]))
+    print("decoder.process", pcm.shape, float(np.abs(pcm).max()), mpcm.shape)
+
+
 def main_adts():
     """ADTSDemuxer.readHeader run by the interpreter on every frame of a seeded synthetic ADTS stream."""
     out_dir = os.path.join(ROOT, "tests", "golden", "adts")
@@ -282,4 +408,4 @@ def main_adts():
 
 
 if __name__ == "__main__":
-    {"stereo": main_stereo, "adts": main_adts}.get((sys.argv[1:] or [""])[0], main)()
+    {"stereo": main_stereo, "adts": main_adts, "decoder": main_decoder}.get((sys.argv[1:] or [""])[0], main)()
