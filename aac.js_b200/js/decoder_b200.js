@@ -11,8 +11,9 @@
  * tns.process + filter_bank.process + the interleave per frame in JS, readChunk
  * parses up to K frames ahead, stages their spectra and side info into typed
  * arrays and makes ONE aacfb_process call; it returns K*1024*channels samples.
- * K = 1 is the PR-1 style correctness path.  Streams with coupling elements fall
- * back to the stock decoder for the whole frame (outside the accelerated path).
+ * K = 1 is the PR-1 style correctness path.  Coupling elements are outside the accelerated path
+ * (stage() throws).  The reference is used unmodified: the parse of each access unit is its own
+ * readChunk with `process` intercepted (parseElements below).
  */
 var AV = require('av');
 var AACDecoder = require('aac/src/decoder');      // the unmodified reference
@@ -81,6 +82,19 @@ var B200Decoder = AACDecoder.extend(function() {
         }
     };
 
+    // The bit parse of ONE access unit, done by the reference itself: its readChunk (decoder.js:125-216)
+    // reads the ADTS header, parses the elements, aligns, and then calls this.process(elements) --
+    // which is intercepted here to capture the parsed elements instead of running TNS / filterbank on
+    // the CPU; the interleave that follows finds no channel data and returns an empty array.  Nothing
+    // in the reference has to be modified or refactored for this.
+    var referenceReadChunk = AACDecoder.prototype.readChunk;
+    this.prototype.parseElements = function() {
+        var captured = null, self = this, own = this.process;
+        this.process = function(elements) { captured = elements; self.data = []; };
+        try { referenceReadChunk.call(this); } finally { this.process = own; }
+        return captured;
+    };
+
     this.prototype.readChunk = function() {
         var C = this.config.chanConfig, K = this.framesPerChunk, t = 0, stream = this.bitstream;
         this.tnsLen = 0;
@@ -88,7 +102,7 @@ var B200Decoder = AACDecoder.extend(function() {
         while (t < K) {
             var mark = stream.offset();
             try {
-                var elements = this.parseElements();   // decoder.js:129-200 up to stream.align(), factored out
+                var elements = this.parseElements();   // the reference's own parse (decoder.js:129-200)
                 this.stage(elements, t++);
             } catch (err) {
                 if (!(err instanceof AV.UnderflowError) || t === 0) throw err;

@@ -1,0 +1,108 @@
+"""End to end at the plugin surface: an AAC-LC ADTS byte stream -> interleaved Float32 PCM.
+
+tests/golden/stream/jsref_stream_*.npz (made by `python tools/js_reference.py stream`, where
+/root/reference exists) hold, for a stereo and a mono synthetic stream (tools/aac_bitstream.py: valid
+raw_data_block syntax -- channel pair / single channel elements, M/S masks, intensity stereo, section
+and scalefactor data, TNS data, all eleven spectral Huffman codebooks with escapes, window switching --
+written with the reference's own code tables):
+
+  * `pcm`: what the reference's UNMODIFIED decoder produced -- setCookie, then readChunk per access unit:
+    ADTS header, the whole bit parse, process, interleave -- run by tools/jsmini.py on a stand-in for
+    the `av` peer package;
+  * per addon call, the typed arrays that aac.js_b200/js/decoder_b200.js -- running on top of that same
+    unmodified decoder, its parse intercepted -- staged for aacfb_process / aacfb_process_stereo.
+
+Replaying the staged calls through the library must give the reference's PCM: bit for bit with the
+oracle standing in for the library (CPU), within 1e-5 with the CUDA library (GPU).  Where the
+reference tree is present the whole thing is also run live on a fresh stream."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+import aacjs_b200 as A
+from tools import workloads as W
+
+GOLD = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "stream", "jsref_stream_*.npz")))
+HAVE_REF = os.path.isdir("/root/reference/src")
+TOL = 1e-5
+
+
+def load(path):
+    z = np.load(path)
+    C, n, seed, K, n_calls = (int(v) for v in z["meta"])
+    calls = []
+    for i in range(n_calls):
+        sp = z[f"c{i}_spectra"]
+        T = sp.shape[0]
+        calls.append({"spectra": sp, "info": z[f"c{i}_info"].view(W.INFO_DTYPE).reshape(T, C),
+                      "stereo_ops": z[f"c{i}_stereo"] if z[f"c{i}_stereo"].size else None,
+                      "tns_blob": z[f"c{i}_tns_blob"] if z[f"c{i}_tns_blob"].size else None,
+                      "tns_offsets": z[f"c{i}_tns_offsets"] if z[f"c{i}_tns_offsets"].size else None})
+    return z, C, n, calls
+
+
+def test_fixtures_cover_both_layouts():
+    assert [os.path.basename(p) for p in GOLD] == ["jsref_stream_mono.npz", "jsref_stream_stereo.npz"]
+
+
+@pytest.mark.parametrize("path", GOLD, ids=os.path.basename)
+def test_adts_index_finds_every_access_unit_of_the_stream(path):
+    z, C, n, calls = load(path)
+    frames, consumed = A.adts_index(z["adts"])
+    assert len(frames) == n and consumed == z["adts"].size
+    assert sum(c["spectra"].shape[0] for c in calls) == n          # the JS batched all of them
+    assert set(int(v) for v in frames["chan_config"]) == {C} and set(int(v) for v in frames["profile"]) == {2}
+
+
+@pytest.mark.parametrize("path", GOLD, ids=os.path.basename)
+def test_oracle_replay_of_the_staged_calls_equals_the_reference_decoder(path):
+    from tools.js_reference import OracleLibrary
+
+    z, C, n, calls = load(path)
+    lib = OracleLibrary(C)
+    pcm = np.concatenate([lib(c).reshape(-1) for c in calls])
+    assert pcm.size == n * 1024 * C
+    assert np.array_equal(pcm.view(np.uint32), z["pcm"].view(np.uint32))
+    if C == 2:   # the stream does exercise the stereo tools and TNS side info
+        assert any(c["stereo_ops"] is not None and c["info"]["stereo_present"].any() for c in calls)
+        assert any(c["tns_blob"] is not None for c in calls)
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="/root/reference is not on this machine")
+@pytest.mark.parametrize("channels,stereo_on_device", [(2, True), (2, False), (1, True)])
+def test_batching_decoder_equals_stock_decoder_live(channels, stereo_on_device):
+    """decoder_b200.js on top of the unmodified reference == the unmodified reference, sample for sample,
+    for any chunking (frames per chunk 1, 3, 64) and with the stereo tools on either side."""
+    from tools import aac_bitstream as B
+    from tools.js_reference import B200DecoderHarness, OracleLibrary, StreamReference
+
+    data = B.write_adts_stream(B.random_frames(np.random.default_rng(500 + channels), 7, channels=channels),
+                               B.codebooks(), channels=channels)
+    ref = StreamReference(data, channels=channels).decode_all()
+    assert ref.size == 7 * 1024 * channels and np.isfinite(ref).all() and np.abs(ref).max() > 0.01
+    for K in (1, 3, 64):
+        h = B200DecoderHarness(data, OracleLibrary(channels), channels=channels, frames_per_chunk=K,
+                               stereo_on_device=stereo_on_device)
+        got = h.decode_all()
+        assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))
+        assert len(h.calls) == -(-7 // K)
+        assert all((c["entry"] == "aacfb_process_stereo") <= stereo_on_device for c in h.calls)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", GOLD, ids=os.path.basename)
+def test_gpu_replay_of_the_staged_calls_equals_the_reference_decoder(path):
+    z, C, n, calls = load(path)
+    ctx = A.Context(1, C, 4, A.TNS_AS_SHIPPED)
+    out = []
+    for c in calls:
+        T = c["spectra"].shape[0]
+        ops = c["stereo_ops"].view(A.STEREO_DTYPE).reshape(1, T, 1) if c["stereo_ops"] is not None else None
+        out.append(ctx.process(c["spectra"][None], c["info"][None], c["tns_blob"], c["tns_offsets"], stereo_ops=ops).reshape(-1))
+    assert ctx.launches >= 2 * len(calls)
+    ctx.close()
+    pcm = np.concatenate(out)
+    ref = z["pcm"]
+    assert np.abs(pcm.astype(np.float64) - ref).max() <= TOL * max(1.0, float(np.abs(ref).max()))

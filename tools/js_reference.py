@@ -131,6 +131,171 @@ class DecoderReference:
         return pcm, np.stack([o.a.copy() for o in self.dec.get("filter_bank").get("overlaps").items])
 
 
+class PyBitstream:
+    """What the reference needs of AV.Bitstream (read / peek / advance / align, plus offset / seek /
+    available for hosts), over a bytes object, MSB first.  Reading past the end throws the
+    `UnderflowError` of the AV stand-in, as Aurora's bitstream does."""
+
+    def __init__(self, data: bytes, underflow_ctor):
+        self.data, self.pos, self.underflow = data, 0, underflow_ctor
+
+    def _bits(self, n, at):
+        if at + n > 8 * len(self.data):
+            raise J.JSThrow(self.underflow.construct([]))
+        v = 0
+        for i in range(at, at + n):
+            v = (v << 1) | ((self.data[i >> 3] >> (7 - (i & 7))) & 1)
+        return v
+
+    def js(self):
+        def read(this, a):
+            n = int(J.to_number(a[0]))
+            v = self._bits(n, self.pos)
+            self.pos += n
+            return float(v)
+
+        def peek(this, a):
+            return float(self._bits(int(J.to_number(a[0])), self.pos))
+
+        def advance(this, a):
+            self.pos += int(J.to_number(a[0]))
+            return J.UNDEF
+
+        def align(this, a):
+            self.pos += -self.pos % 8
+            return J.UNDEF
+
+        def seek(this, a):
+            self.pos = int(J.to_number(a[0]))
+            return J.UNDEF
+
+        return J.obj(read=J.native(read), peek=J.native(peek), advance=J.native(advance), align=J.native(align),
+                     seek=J.native(seek), offset=J.native(lambda this, a: float(self.pos)),
+                     available=J.native(lambda this, a: self.pos + int(J.to_number(a[0])) <= 8 * len(self.data)))
+
+
+STREAM_AV_STUB = AV_STUB + """
+function UnderflowError() {}
+AV.UnderflowError = UnderflowError;
+AV.Stream = {fromBuffer: function(b) { return b; }};
+"""
+
+
+class StreamReference:
+    """The reference's unmodified decoder.js end to end: setCookie on the 2-byte AudioSpecificConfig the
+    ADTS demuxer makes (adts_demuxer.js:66-69), then readChunk -- ADTS header, the whole bit parse
+    (ics.js, cpe.js, tns.js, huffman.js), process, interleave -- per access unit of a byte stream."""
+
+    def __init__(self, data: bytes, profile=2, sample_index=4, channels=2, src_dir=REF_SRC, decoder_module="./decoder"):
+        self.rt = J.Runtime(src_dir)
+        self.av = self.rt.run(STREAM_AV_STUB)["AV"]
+        self.stream = PyBitstream(data, self.av.get("UnderflowError"))
+        js_stream = self.stream.js()
+        self.av.put("Bitstream", J.JSFunction(native=lambda this, args, new=False: args[0]))   # new AV.Bitstream(x) -> x
+        self.rt.stubs["av"] = self.av
+        self.Decoder = self.rt.require(decoder_module)
+        self.dec = self.Decoder.construct([])
+        self.dec.put("format", J.obj())
+        cookie = bytes([(profile << 3) | ((sample_index >> 1) & 7), ((sample_index & 1) << 7) | (channels << 3), 0])
+        self.Decoder.get("prototype").get("setCookie").call(self.dec, [PyBitstream(cookie, self.av.get("UnderflowError")).js()])
+        self.dec.put("bitstream", js_stream)
+
+    def read_chunk(self):
+        return self.Decoder.get("prototype").get("readChunk").call(self.dec, []).a.copy()
+
+    def decode_all(self):
+        out = []
+        while self.stream.pos + 56 <= 8 * len(self.stream.data):
+            out.append(self.read_chunk())
+        return np.concatenate(out) if out else np.zeros(0, np.float32)
+
+
+class B200DecoderHarness:
+    """aac.js_b200/js/decoder_b200.js -- the batching decoder a Node host registers instead of the
+    reference's -- run by the interpreter ON TOP OF the unmodified reference (its base class is the
+    real src/decoder.js; ICStream / CPEElement are the reference's) with a stand-in for the N-API addon.
+    `compute(call)` plays the library: it receives what the JS staged for one aacfb_process[_stereo] call
+    as numpy arrays (dict: spectra [T][C][1024], info, stereo_ops | None, tns_blob / tns_offsets | None)
+    and returns the PCM [T][1024][C] that is written into the typed array readChunk returns."""
+
+    def __init__(self, data: bytes, compute, channels=2, sample_index=4, profile=2, frames_per_chunk=4,
+                 src_dir=REF_SRC, stereo_on_device=True):
+        js_dir = os.path.join(ROOT, "aac.js_b200", "js")
+        ref = J.Runtime(src_dir)
+        av = ref.run(STREAM_AV_STUB)["AV"]
+        av.put("Bitstream", J.JSFunction(native=lambda this, args, new=False: args[0]))
+        ref.stubs["av"] = av
+        self.calls, self.channels = [], channels
+
+        def run(name, a, stereo):
+            spectra, info = a[1], a[2]
+            k = 1 if stereo else 0
+            n = int(J.to_number(a[6 + k]))
+            C = channels
+            call = {"spectra": spectra.a[: n * C * 1024].reshape(n, C, 1024).copy(),
+                    "info": info.a[: n * C * 8].copy().view(W.INFO_DTYPE).reshape(n, C),
+                    "stereo_ops": a[3].a[: n * 768].copy() if stereo else None,
+                    "tns_blob": a[3 + k].a.copy() if a[3 + k] not in (None, J.UNDEF) else None,
+                    "tns_offsets": a[4 + k].a[: n * C + 1].copy() if a[4 + k] not in (None, J.UNDEF) else None,
+                    "entry": name}
+            if call["tns_blob"] is not None:
+                call["tns_blob"] = call["tns_blob"][: int(call["tns_offsets"][-1])]
+            self.calls.append(call)
+            a[5 + k].a[:] = np.ascontiguousarray(compute(call), np.float32).reshape(-1)
+            return J.UNDEF
+
+        addon = J.obj(create=J.native(lambda this, a: J.obj()),
+                      process=J.native(lambda this, a: run("aacfb_process", a, False)),
+                      processStereo=J.native(lambda this, a: run("aacfb_process_stereo", a, True)))
+        stubs = {"av": av, "aac/src/decoder": ref.require("./decoder"), "aac/src/ics": ref.require("./ics"),
+                 "aac/src/cpe": ref.require("./cpe"), "./build/Release/aacfb.node": addon}
+        js = J.Runtime(js_dir, stubs=stubs)
+        self.Decoder = js.require("./decoder_b200")
+        self.stream = PyBitstream(data, av.get("UnderflowError"))
+        self.dec = self.Decoder.construct([])
+        self.dec.put("format", J.obj())
+        self.dec.put("framesPerChunk", float(frames_per_chunk))
+        self.dec.put("stereoOnDevice", bool(stereo_on_device))
+        cookie = bytes([(profile << 3) | ((sample_index >> 1) & 7), ((sample_index & 1) << 7) | (channels << 3), 0])
+        self.Decoder.get("prototype").get("setCookie").call(self.dec, [PyBitstream(cookie, av.get("UnderflowError")).js()])
+        self.dec.put("bitstream", self.stream.js())
+
+    def decode_all(self):
+        out = []
+        while self.stream.pos + 56 <= 8 * len(self.stream.data):
+            out.append(self.Decoder.get("prototype").get("readChunk").call(self.dec, []).a.copy())
+        return np.concatenate(out) if out else np.zeros(0, np.float32)
+
+
+class OracleLibrary:
+    """CPU stand-in for libaacfb behind B200DecoderHarness (tests only): the op semantics of
+    include/aacfb.h for the stereo records, then the oracle's TNS / filterbank / interleave, with the
+    overlap state carried from call to call like an aacfb_ctx does."""
+
+    def __init__(self, channels, sample_index=4, flags=0):
+        from oracle import oracle as O
+
+        self.O, self.C, self.si, self.flags = O, channels, sample_index, flags
+        self.overlap = np.zeros((1, channels, 1024), np.float32)
+
+    def __call__(self, call):
+        sp = call["spectra"].copy()
+        if call["stereo_ops"] is not None:
+            recs = call["stereo_ops"].view(np.dtype([("op", "u1", (256,)), ("scale", "f4", (128,))]))
+            for t in range(sp.shape[0]):
+                if not call["info"][t, 0]["stereo_present"]:
+                    continue
+                op = np.repeat(recs[t]["op"], 4)
+                l, r = sp[t, 0].copy(), sp[t, 1].copy()
+                ms, it = op == 1, op >= 2
+                sp[t, 0][ms] = l[ms] + r[ms]
+                sp[t, 1][ms] = l[ms] - r[ms]
+                sp[t, 1][it] = l[it] * recs[t]["scale"][op[it] - 2]
+        pcm, self.overlap = self.O.process(sp[None], call["info"][None], call["tns_blob"], call["tns_offsets"],
+                                           self.overlap, sample_index=self.si, flags=self.flags)
+        return pcm[0]
+
+
 class AdtsReference:
     """ADTSDemuxer.readHeader (adts_demuxer.js:28-52) cut out of the file -- the module itself needs
     the `av` peer dependency -- and run by the interpreter on a Python-side bit reader that offers
@@ -390,6 +555,36 @@ def main_decoder():
     print("decoder.process", pcm.shape, float(np.abs(pcm).max()), mpcm.shape)
 
 
+def stream_cases():
+    """(name, channels, n_frames, seed, frames_per_chunk) of tests/golden/stream/jsref_stream_*.npz"""
+    return [("stereo", 2, 14, 301, 4), ("mono", 1, 9, 302, 3)]
+
+
+def main_stream():
+    """A synthetic ADTS stream through (a) the reference's unmodified readChunk and (b) decoder_b200.js on
+    top of it with the oracle as the library; stores the stream, the reference PCM and, per addon call,
+    the arrays the JS staged -- the GPU box replays those through the real library."""
+    from tools import aac_bitstream as B
+
+    out_dir = os.path.join(ROOT, "tests", "golden", "stream")
+    os.makedirs(out_dir, exist_ok=True)
+    for name, C, n, seed, K in stream_cases():
+        data = B.write_adts_stream(B.random_frames(np.random.default_rng(seed), n, channels=C), B.codebooks(), channels=C)
+        ref = StreamReference(data, channels=C).decode_all()
+        h = B200DecoderHarness(data, OracleLibrary(C), channels=C, frames_per_chunk=K)
+        got = h.decode_all()
+        assert np.array_equal(ref.view(np.uint32), got.view(np.uint32))
+        arrays = {"adts": np.frombuffer(data, np.uint8), "pcm": ref, "meta": np.array([C, n, seed, K, len(h.calls)])}
+        for i, c in enumerate(h.calls):
+            arrays[f"c{i}_spectra"] = c["spectra"]
+            arrays[f"c{i}_info"] = c["info"].view(np.uint8).reshape(-1)
+            arrays[f"c{i}_stereo"] = c["stereo_ops"] if c["stereo_ops"] is not None else np.zeros(0, np.uint8)
+            arrays[f"c{i}_tns_blob"] = c["tns_blob"] if c["tns_blob"] is not None else np.zeros(0, np.uint8)
+            arrays[f"c{i}_tns_offsets"] = c["tns_offsets"] if c["tns_offsets"] is not None else np.zeros(0, np.uint32)
+        np.savez_compressed(os.path.join(out_dir, f"jsref_stream_{name}.npz"), **arrays)
+        print(name, len(data), "bytes,", n, "frames,", len(h.calls), "calls, peak", float(np.abs(ref).max()))
+
+
 def main_adts():
     """ADTSDemuxer.readHeader run by the interpreter on every frame of a seeded synthetic ADTS stream."""
     out_dir = os.path.join(ROOT, "tests", "golden", "adts")
@@ -408,4 +603,4 @@ def main_adts():
 
 
 if __name__ == "__main__":
-    {"stereo": main_stereo, "adts": main_adts, "decoder": main_decoder}.get((sys.argv[1:] or [""])[0], main)()
+    {"stereo": main_stereo, "adts": main_adts, "decoder": main_decoder, "stream": main_stream}.get((sys.argv[1:] or [""])[0], main)()
