@@ -12,6 +12,9 @@ written with the reference's own code tables):
   * per addon call, the typed arrays that aac.js_b200/js/decoder_b200.js -- running on top of that same
     unmodified decoder, its parse intercepted -- staged for aacfb_process / aacfb_process_stereo.
 
+(A third stream is 5.1: centre SCE, two channel pair elements, LFE per access unit; the stereo tools of
+its pairs stay on the host, the device path takes them for 2-channel streams only.)
+
 Replaying the staged calls through the library must give the reference's PCM: bit for bit with the
 oracle standing in for the library (CPU), within 1e-5 with the CUDA library (GPU).  Where the
 reference tree is present the whole thing is also run live on a fresh stream."""
@@ -44,7 +47,8 @@ def load(path):
 
 
 def test_fixtures_cover_both_layouts():
-    assert [os.path.basename(p) for p in GOLD] == ["jsref_stream_mono.npz", "jsref_stream_stereo.npz"]
+    assert [os.path.basename(p) for p in GOLD] == ["jsref_stream_mono.npz", "jsref_stream_stereo.npz",
+                                                   "jsref_stream_surround.npz"]   # 1, 2 and 5.1 channels
 
 
 @pytest.mark.parametrize("path", GOLD, ids=os.path.basename)
@@ -71,7 +75,7 @@ def test_oracle_replay_of_the_staged_calls_equals_the_reference_decoder(path):
 
 
 @pytest.mark.skipif(not HAVE_REF, reason="/root/reference is not on this machine")
-@pytest.mark.parametrize("channels,stereo_on_device", [(2, True), (2, False), (1, True)])
+@pytest.mark.parametrize("channels,stereo_on_device", [(2, True), (2, False), (1, True), (6, True)])
 def test_batching_decoder_equals_stock_decoder_live(channels, stereo_on_device):
     """decoder_b200.js on top of the unmodified reference == the unmodified reference, sample for sample,
     for any chunking (frames per chunk 1, 3, 64) and with the stereo tools on either side."""
@@ -88,7 +92,7 @@ def test_batching_decoder_equals_stock_decoder_live(channels, stereo_on_device):
         got = h.decode_all()
         assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))
         assert len(h.calls) == -(-7 // K)
-        assert all((c["entry"] == "aacfb_process_stereo") <= stereo_on_device for c in h.calls)
+        assert all((c["entry"] == "aacfb_process_stereo") <= (stereo_on_device and channels == 2) for c in h.calls)
 
 
 @pytest.mark.gpu

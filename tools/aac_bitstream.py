@@ -193,8 +193,8 @@ def write_raw_data_block(frame, books):
     """frame: list of elements, ("sce", ics) or ("cpe", common_window, ms_mask, ms_used, left, right)."""
     w = BitWriter()
     for tag, el in enumerate(frame):
-        if el[0] == "sce":
-            w.put(0, 3); w.put(tag, 4)
+        if el[0] in ("sce", "lfe"):               # single_channel_element / lfe_channel_element: same syntax
+            w.put(0 if el[0] == "sce" else 3, 3); w.put(tag, 4)
             _write_ics(w, el[1], books, False)
         else:
             _, common, mask, ms_used, left, right = el
@@ -316,9 +316,25 @@ def random_frames(rng, n_frames, channels=2, sample_index=4):
 
     seqs = [W.legal_random_sequence(n_frames, rng) for _ in range(channels)]
     frames = []
+
+    def pair(t, ca, cb):
+        common = bool(rng.random() < 0.6)
+        sl = int(seqs[ca][t])
+        sr = sl if common else int(seqs[cb][t])
+        shape = int(rng.integers(0, 2))
+        left = _random_ics(rng, sl, shape, sample_index)
+        right = _random_ics(rng, sr, shape if common else int(rng.integers(0, 2)), sample_index, stereo_right=True,
+                            like=left if common else None)
+        return ("cpe", common, int(rng.integers(0, 3)) if common else 0, rng.integers(0, 2, 128), left, right)
+
     for t in range(n_frames):
         if channels == 1:
             frames.append([("sce", _random_ics(rng, int(seqs[0][t]), int(rng.integers(0, 2)), sample_index))])
+            continue
+        if channels == 6:   # 5.1: centre, front pair, rear pair, LFE (channel configuration 6)
+            frames.append([("sce", _random_ics(rng, int(seqs[0][t]), int(rng.integers(0, 2)), sample_index)),
+                           pair(t, 1, 2), pair(t, 3, 4),
+                           ("lfe", _random_ics(rng, int(seqs[5][t]), int(rng.integers(0, 2)), sample_index, allow_tns=False))])
             continue
         common = bool(rng.random() < 0.6)
         sl = int(seqs[0][t])

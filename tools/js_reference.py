@@ -557,7 +557,7 @@ def main_decoder():
 
 def stream_cases():
     """(name, channels, n_frames, seed, frames_per_chunk) of tests/golden/stream/jsref_stream_*.npz"""
-    return [("stereo", 2, 14, 301, 4), ("mono", 1, 9, 302, 3)]
+    return [("stereo", 2, 14, 301, 4), ("mono", 1, 9, 302, 3), ("surround", 6, 5, 303, 2)]
 
 
 def main_stream():
