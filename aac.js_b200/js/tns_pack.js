@@ -39,6 +39,7 @@ exports.process = function(handle, tns, ics, data, decode, mode) {
     exports.writeBlock(tns, bytes, new DataView(buf), 0);
     var info = new Uint8Array(8);
     info[0] = ics.info.windowSequence; info[1] = ics.info.windowShape[0]; info[2] = ics.info.windowShape[1];
-    info[3] = ics.maxSFB; info[4] = 1;
+    // tns.js:106 reads ics.maxSFB, which ICStream never sets (it lives on ics.info): take the evident intent
+    info[3] = ics.maxSFB !== undefined ? ics.maxSFB : ics.info.maxSFB; info[4] = 1;
     addon.tnsProcess(handle, info, bytes, data, mode);
 };
