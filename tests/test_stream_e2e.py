@@ -32,6 +32,13 @@ HAVE_REF = os.path.isdir("/root/reference/src")
 TOL = 1e-5
 
 
+def tns_flags(path):
+    """`*_tnsfixed`: the reference ran with its two TNS tokens fixed (tools/js_reference.TNS_FIXES: `tmp` -> `top`
+    at tns.js:122 and `ics.maxSFB` -> `ics.info.maxSFB` at :106), so its decoder -- which passes decode = false
+    -- really runs the MA filter: the library mode is TNS_FIXED_MA.  Otherwise TNS is the identity."""
+    return A.TNS_FIXED_MA if path.endswith("_tnsfixed.npz") else A.TNS_AS_SHIPPED
+
+
 def load(path):
     z = np.load(path)
     C, n, seed, K, n_calls = (int(v) for v in z["meta"])
@@ -48,6 +55,7 @@ def load(path):
 
 def test_fixtures_cover_both_layouts():
     assert [os.path.basename(p) for p in GOLD] == ["jsref_stream_mono.npz", "jsref_stream_stereo.npz",
+                                                   "jsref_stream_stereo_tnsfixed.npz",
                                                    "jsref_stream_surround.npz"]   # 1, 2 and 5.1 channels
 
 
@@ -65,7 +73,7 @@ def test_oracle_replay_of_the_staged_calls_equals_the_reference_decoder(path):
     from tools.js_reference import OracleLibrary
 
     z, C, n, calls = load(path)
-    lib = OracleLibrary(C)
+    lib = OracleLibrary(C, flags=tns_flags(path))
     pcm = np.concatenate([lib(c).reshape(-1) for c in calls])
     assert pcm.size == n * 1024 * C
     assert np.array_equal(pcm.view(np.uint32), z["pcm"].view(np.uint32))
@@ -99,7 +107,7 @@ def test_batching_decoder_equals_stock_decoder_live(channels, stereo_on_device):
 @pytest.mark.parametrize("path", GOLD, ids=os.path.basename)
 def test_gpu_replay_of_the_staged_calls_equals_the_reference_decoder(path):
     z, C, n, calls = load(path)
-    ctx = A.Context(1, C, 4, A.TNS_AS_SHIPPED)
+    ctx = A.Context(1, C, 4, tns_flags(path))
     out = []
     for c in calls:
         T = c["spectra"].shape[0]
@@ -110,3 +118,19 @@ def test_gpu_replay_of_the_staged_calls_equals_the_reference_decoder(path):
     pcm = np.concatenate(out)
     ref = z["pcm"]
     assert np.abs(pcm.astype(np.float64) - ref).max() <= TOL * max(1.0, float(np.abs(ref).max()))
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="/root/reference is not on this machine")
+def test_tns_end_to_end_with_the_reference_tokens_fixed_live():
+    """With both defects fixed the reference's real decoder filters (MA branch); the batching decoder with
+    the library in TNS_FIXED_MA mode gives the same bits -- TNS data parsed from the bitstream (coefficient
+    tables, compression, short-window filters) -> tns_pack.js blocks -> filter, end to end."""
+    from tools import aac_bitstream as B
+    from tools.js_reference import TNS_FIXES, B200DecoderHarness, OracleLibrary, StreamReference
+
+    data = B.write_adts_stream(B.random_frames(np.random.default_rng(77), 6, channels=2), B.codebooks(), channels=2)
+    shipped = StreamReference(data).decode_all()
+    fixed = StreamReference(data, patches=TNS_FIXES).decode_all()
+    assert not np.array_equal(shipped, fixed) and np.isfinite(fixed).all()
+    got = B200DecoderHarness(data, OracleLibrary(2, flags=A.TNS_FIXED_MA), channels=2, frames_per_chunk=4).decode_all()
+    assert np.array_equal(got.view(np.uint32), fixed.view(np.uint32))

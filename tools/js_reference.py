@@ -181,13 +181,41 @@ AV.Stream = {fromBuffer: function(b) { return b; }};
 """
 
 
+# The two tokens that keep TNS from doing anything in the reference as shipped (defects):
+TNS_FIXES = {"tns.js": [(r"bottom = Math\.max\(0, tmp - length_w\[filt\]\)", "bottom = Math.max(0, top - length_w[filt])"),
+                        (r"Math\.min\(this\.maxBands, ics\.maxSFB\)", "Math.min(this.maxBands, ics.info.maxSFB)")]}
+
+
+def preload_patched(rt, patches):
+    """Load modules of rt.src_dir with regex substitutions applied in memory (each must match once)."""
+    for fname, subs in patches.items():
+        path = os.path.normpath(os.path.join(rt.src_dir, fname))
+        text = open(path).read()
+        for pat, repl in subs:
+            text, n = re.subn(pat, repl, text)
+            assert n == 1, (fname, pat)
+        module, exports = J.JSObject(J.OBJECT_PROTO), J.JSObject(J.OBJECT_PROTO)
+        module.put("exports", exports)
+        rt.modules[path] = module
+        ast = J.Parser(J.tokenize(text)).program()
+        names = set()
+        J.hoisted_names(ast, names)
+        scope = {n_: J.UNDEF for n_ in names}
+        scope.update(module=module, exports=exports, this=exports,
+                     require=J.native(lambda this, args: rt.require(J.to_string(args[0]))))
+        J.compile_node(ast)((scope, (rt.globals, None)))
+
+
 class StreamReference:
     """The reference's unmodified decoder.js end to end: setCookie on the 2-byte AudioSpecificConfig the
     ADTS demuxer makes (adts_demuxer.js:66-69), then readChunk -- ADTS header, the whole bit parse
     (ics.js, cpe.js, tns.js, huffman.js), process, interleave -- per access unit of a byte stream."""
 
-    def __init__(self, data: bytes, profile=2, sample_index=4, channels=2, src_dir=REF_SRC, decoder_module="./decoder"):
+    def __init__(self, data: bytes, profile=2, sample_index=4, channels=2, src_dir=REF_SRC, decoder_module="./decoder",
+                 patches=None):
         self.rt = J.Runtime(src_dir)
+        if patches:
+            preload_patched(self.rt, patches)
         self.av = self.rt.run(STREAM_AV_STUB)["AV"]
         self.stream = PyBitstream(data, self.av.get("UnderflowError"))
         js_stream = self.stream.js()
@@ -557,7 +585,8 @@ def main_decoder():
 
 def stream_cases():
     """(name, channels, n_frames, seed, frames_per_chunk) of tests/golden/stream/jsref_stream_*.npz"""
-    return [("stereo", 2, 14, 301, 4), ("mono", 1, 9, 302, 3), ("surround", 6, 5, 303, 2)]
+    return [("stereo", 2, 14, 301, 4), ("mono", 1, 9, 302, 3), ("surround", 6, 5, 303, 2),
+            ("stereo_tnsfixed", 2, 10, 304, 5)]
 
 
 def main_stream():
@@ -570,8 +599,9 @@ def main_stream():
     os.makedirs(out_dir, exist_ok=True)
     for name, C, n, seed, K in stream_cases():
         data = B.write_adts_stream(B.random_frames(np.random.default_rng(seed), n, channels=C), B.codebooks(), channels=C)
-        ref = StreamReference(data, channels=C).decode_all()
-        h = B200DecoderHarness(data, OracleLibrary(C), channels=C, frames_per_chunk=K)
+        fixed = name.endswith("_tnsfixed")   # the reference with its two TNS tokens fixed: decode=false -> MA branch
+        ref = StreamReference(data, channels=C, patches=TNS_FIXES if fixed else None).decode_all()
+        h = B200DecoderHarness(data, OracleLibrary(C, flags=2 if fixed else 0), channels=C, frames_per_chunk=K)
         got = h.decode_all()
         assert np.array_equal(ref.view(np.uint32), got.view(np.uint32))
         arrays = {"adts": np.frombuffer(data, np.uint8), "pcm": ref, "meta": np.array([C, n, seed, K, len(h.calls)])}
