@@ -134,3 +134,30 @@ def test_tns_end_to_end_with_the_reference_tokens_fixed_live():
     assert not np.array_equal(shipped, fixed) and np.isfinite(fixed).all()
     got = B200DecoderHarness(data, OracleLibrary(2, flags=A.TNS_FIXED_MA), channels=2, frames_per_chunk=4).decode_all()
     assert np.array_equal(got.view(np.uint32), fixed.view(np.uint32))
+
+
+@pytest.mark.parametrize("path", GOLD, ids=os.path.basename)
+def test_emulated_kernel_replay_of_the_staged_calls(path):
+    """The kernels' own arithmetic (the same source compiled for the host, tests/emul.py) on the staged
+    calls, against the reference decoder's PCM: what the GPU replay below sees, minus the GPU."""
+    from tests import emul
+
+    z, C, n, calls = load(path)
+    ov = np.zeros((1, C, 1024), np.float32)
+    out = []
+    for c in calls:
+        sp = c["spectra"].copy()
+        if c["stereo_ops"] is not None:      # the op semantics of include/aacfb.h (stereo_apply on the device)
+            recs = c["stereo_ops"].view(A.STEREO_DTYPE)
+            for t in range(sp.shape[0]):
+                if c["info"][t, 0]["stereo_present"]:
+                    op = np.repeat(recs[t]["op"], 4)
+                    l, r = sp[t, 0].copy(), sp[t, 1].copy()
+                    ms, it = op == A.STEREO_MS, op >= A.STEREO_IS
+                    sp[t, 0][ms], sp[t, 1][ms] = l[ms] + r[ms], l[ms] - r[ms]
+                    sp[t, 1][it] = l[it] * recs[t]["scale"][op[it] - A.STEREO_IS]
+        out.append(np.asarray(emul.process(sp[None], c["info"][None], c["tns_blob"], c["tns_offsets"], ov, 4,
+                                           tns_flags(path), 3)).reshape(-1))
+    ref = z["pcm"]
+    err = np.abs(np.concatenate(out).astype(np.float64) - ref).max()
+    assert err <= TOL * max(1.0, float(np.abs(ref).max())) / 5, err      # 5x inside the bar
