@@ -16,6 +16,12 @@ is the whole-job frames/s over the max-over-ranks device time.
 `roofline`: algorithmic bytes (8192 B per channel-frame + overlap state + side info)
             / mean launch duration of the synthesis kernel vs MEASURED_PEAKS.json hbm_gbs.
 `cpu_baseline`: the oracle (C restatement of the reference's JS) on the host cores, bounded sample.
+`configs` : (N = 1) the other north_star configurations -- EIGHT_SHORT, LONG + TNS, mixed, config 2 with
+            the stereo tools -- timed the same way in the same run: ms_per_step, frames/s, roofline.
+`config5_scatter`: (N > 1) BASELINE.json configs[4] at full size: 1 048 576 stereo mixed frames that start
+            on rank 0, through the NCCL scatter -> kernel -> gather path and through the fused
+            peer-memory path (synth_kernel on rank 0's buffers over NVLink), each timed and bit-checked.
+`pcie_concurrent`: (N > 1) host<->device copy rates per GPU with all ranks copying at once.
 """
 from __future__ import annotations
 
@@ -201,6 +207,244 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+class Batch:
+    """One synthetic batch of a workload, resident in HBM on this rank, with its context."""
+
+    def __init__(self, A, W, torch, workload, S, T, rank, dev, local):
+        cfg, _, _, C, desc = WORKLOADS[workload]
+        self.workload, self.cfg, self.S, self.T, self.C, self.desc = workload, cfg, S, T, C, desc
+        stereo = workload.endswith("_stereo")
+        sigma = {2: 3.0e5, 3: 1.0e5, 4: 0.75e5, 5: 1.0e5}[cfg] * (0.5 if stereo else 1.0)
+        g = torch.Generator(device=dev).manual_seed(1234 + rank)
+        self.spectra = torch.randn((S, T, C, 1024), device=dev, generator=g) * sigma
+        self.side = side = W.make(cfg, S, T, C, seed=rank, side_only=True)  # info/TNS side data only
+        self.info_np = side["info"]
+        self.blob = self.offs = self.ops = self.ops_np = None
+        self.tns_bytes = 0
+        if side["tns_blob"] is not None:
+            self.blob = torch.from_numpy(side["tns_blob"]).to(dev)
+            self.offs = torch.from_numpy(side["tns_offsets"].view(np.int32).copy()).to(dev)
+            self.tns_bytes = int(side["tns_blob"].size)
+        if stereo:
+            self.ops_np = W.joint_stereo_ops(S, T, seed=rank)
+            self.info_np["stereo_present"][:, :, 0] = 1
+            self.ops = torch.from_numpy(self.ops_np.view(np.uint8).reshape(S, T, 768).copy()).to(dev)
+        self.info = torch.from_numpy(self.info_np.view(np.uint8).reshape(S, T, C, 8).copy()).to(dev)
+        self.stereo_bytes = 0 if self.ops_np is None else int(self.ops_np.nbytes)
+        self.pcm = torch.empty((S, T, 1024, C), device=dev)
+        self.ctx = A.Context(S, C, side["sample_index"], side["flags"], device=local)
+        self.alg_bytes = algorithmic_bytes(S, T, C, self.tns_bytes, self.stereo_bytes)
+
+    def step(self, stream):
+        self.ctx.process_device(self.spectra.data_ptr(), self.info.data_ptr(), self.pcm.data_ptr(), self.T,
+                                stream.cuda_stream, self.blob.data_ptr() if self.blob is not None else 0,
+                                self.offs.data_ptr() if self.offs is not None else 0, self.tns_bytes,
+                                self.ops.data_ptr() if self.ops is not None else 0)
+
+    def close(self):
+        self.ctx.close()
+        self.spectra = self.pcm = self.info = self.blob = self.offs = self.ops = None
+
+
+def time_steps(torch, step, steps, warmup, stream, barrier):
+    """W untimed steps, then exactly `steps` steps between CUDA events on `stream`, barrier +
+    synchronize on both sides.  Returns (total ms, [per-step ms])."""
+    for _ in range(warmup):
+        step()
+    barrier()
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+    evs[0].record(stream)
+    for i in range(steps):
+        step()
+        evs[i + 1].record(stream)
+    barrier()
+    return evs[0].elapsed_time(evs[-1]), [evs[i].elapsed_time(evs[i + 1]) for i in range(steps)]
+
+
+def load_traffic():
+    """Measured DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum of one
+    `ncu --set full` capture per workload; profiles/traffic.json is written by tools/ncu_traffic.py
+    from the committed captures -- a profiler cannot run inside a timed bench)."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        return json.load(open(p))
+    except Exception:
+        return {}
+
+
+def roofline_record(workload, alg, launch_ms, tns, traffic_tab):
+    peak_gbs, peak_src = measured_peak()
+    achieved = alg / (launch_ms * 1e-3) / 1e9
+    t = traffic_tab.get(workload)
+    return {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
+            "traffic": t, "traffic_source": traffic_tab.get("_source") if t else None, "peak_source": peak_src,
+            "kernel": "aacfb::synth_kernel" + (" (TNS fused)" if tns else ""),
+            "algorithmic_bytes_per_launch": alg, "launch_ms": launch_ms}
+
+
+def pcie_probe(torch, dev, world, n_bytes=256 << 20, reps=6):
+    """Host<->device copy rates of this rank while ALL ranks copy at once (pinned memory, one
+    stream per direction): what the box gives N GPUs concurrently -- the ceiling of `e2e`."""
+    h_in = torch.empty(n_bytes, dtype=torch.uint8, pin_memory=True)
+    h_out = torch.empty(n_bytes, dtype=torch.uint8, pin_memory=True)
+    d_in = torch.empty(n_bytes, dtype=torch.uint8, device=dev)
+    d_out = torch.empty(n_bytes, dtype=torch.uint8, device=dev)
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+
+    def run(h2d, d2h):
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            if h2d:
+                with torch.cuda.stream(s1):
+                    d_in.copy_(h_in, non_blocking=True)
+            if d2h:
+                with torch.cuda.stream(s2):
+                    h_out.copy_(d_out, non_blocking=True)
+        torch.cuda.synchronize()
+        return n_bytes * reps / (time.perf_counter() - t0) / 1e9
+
+    run(True, True)
+    mine = torch.tensor([run(True, False), run(False, True), run(True, True)], device=dev, dtype=torch.float64)
+    allr = [torch.zeros_like(mine) for _ in range(world)]
+    if world > 1:
+        torch.distributed.all_gather(allr, mine)
+    else:
+        allr = [mine]
+    m = torch.stack(allr).cpu().numpy()
+    return {"concurrent_ranks": world, "bytes_per_copy": n_bytes,
+            "h2d_alone_gbs_per_gpu": [round(float(v), 1) for v in m[:, 0]],
+            "d2h_alone_gbs_per_gpu": [round(float(v), 1) for v in m[:, 1]],
+            "duplex_each_way_gbs_per_gpu": [round(float(v), 1) for v in m[:, 2]],
+            "duplex_each_way_gbs_sum": round(float(m[:, 2].sum()), 1)}
+
+
+def bit_checksum(torch, t):
+    """Order-independent 2 x 64-bit checksum of the raw bits of a float tensor (wrapping sums)."""
+    v = t.reshape(-1).view(torch.int32).to(torch.int64)
+    return torch.stack([v.sum(), (v * v + (v >> 3)).sum()])
+
+
+def run_config5_scatter(A, W, torch, args, rank, world, local, dev):
+    """BASELINE.json configs[4]: 1 048 576 stereo mixed long/short frames that START ON RANK 0, sharded
+    by stream over the N GPUs.  Two exchange paths, both timed (CUDA events, max over ranks) and both
+    checked bit for bit against each rank's own run on its shard:
+      nccl : NCCL scatter of spectra + side info -> synth_kernel -> NCCL gather of PCM
+      fused: every rank maps rank 0's buffers (CUDA IPC) and runs synth_kernel directly on the peer
+             addresses: TMA row loads and PCM stores cross NVLink inside the kernel."""
+    import torch.distributed as dist
+    from aacjs_b200 import sharding
+
+    S, T, C = args.scatter_streams, 256, 2
+    lo, hi = sharding.stream_range(S, world, rank)
+    n = hi - lo
+    st = torch.cuda.current_stream()
+    full_spec = full_info = full_pcm = None
+    if rank == 0:
+        side = W.make(5, S, T, C, seed=0, side_only=True)
+        g = torch.Generator(device=dev).manual_seed(99)
+        full_spec = torch.randn((S, T, C, 1024), device=dev, generator=g) * 1.0e5
+        full_info = torch.from_numpy(side["info"].view(np.uint8).reshape(S, T, C, 8).copy()).to(dev)
+        full_pcm = torch.zeros((S, T, 1024, C), device=dev)
+    spec = torch.empty((n, T, C, 1024), device=dev)
+    info = torch.empty((n, T, C, 8), dtype=torch.uint8, device=dev)
+    pcm = torch.empty((n, T, 1024, C), device=dev)
+
+    def barrier():
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    def region_sums():   # rank 0: checksum of every rank's region of the root PCM buffer
+        out = torch.zeros((world, 2), dtype=torch.int64, device=dev)
+        if rank == 0:
+            for r in range(world):
+                a, b = sharding.stream_range(S, world, r)
+                out[r] = bit_checksum(torch, full_pcm[a:b])
+        dist.broadcast(out, src=0)
+        return out
+
+    def local_sums(t):
+        mine = bit_checksum(torch, t)
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        return torch.stack(allr)
+
+    def timed(fn, steps):
+        total, _ = time_steps(torch, fn, steps, 2, st, barrier)
+        t = torch.tensor([total / steps], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    res = {"workload": f"config5: {S * T} stereo frames mixed long/short ({S} streams x {T}), resident on rank 0",
+           "n_gpus": world}
+    # ---- reference result of every shard: its own rows, its own GPU, fresh (zero) overlap ----------
+    sharding.scatter_streams(full_spec, spec, S)
+    sharding.scatter_streams(full_info, info, S)
+    c0 = A.Context(n, C, 4, 0, device=local)
+    c0.process_device(spec.data_ptr(), info.data_ptr(), pcm.data_ptr(), T, st.cuda_stream)
+    torch.cuda.synchronize()
+    c0.close()
+    want = local_sums(pcm)
+
+    # ---- NCCL scatter -> kernel -> NCCL gather -----------------------------------------------------
+    ctx = A.Context(n, C, 4, 0, device=local)
+
+    def kernel():
+        ctx.process_device(spec.data_ptr(), info.data_ptr(), pcm.data_ptr(), T, st.cuda_stream)
+
+    def nccl_path():
+        sharding.scatter_streams(full_spec, spec, S)
+        sharding.scatter_streams(full_info, info, S)
+        kernel()
+        sharding.gather_streams(pcm, full_pcm, S)
+
+    nccl_path()          # first step of ctx: zero overlap, like the reference result
+    barrier()
+    res["nccl_bit_identical"] = bool(torch.equal(region_sums(), want))
+    steps = max(2, min(args.steps, 5))
+    res["nccl_ms"] = timed(nccl_path, steps)
+    res["kernel_ms"] = timed(kernel, steps)
+    ctx.close()
+    moved = (S - n) * T * C * 4096 if rank == 0 else 0
+    mv = torch.tensor([moved], device=dev, dtype=torch.float64)
+    dist.broadcast(mv, src=0)
+    moved = float(mv.item())
+    res["nvlink_bytes_each_way_at_root"] = int(moved)
+    res["nccl_frames_per_s"] = S * T / res["nccl_ms"] * 1e3
+    res["kernel_frames_per_s"] = S * T / res["kernel_ms"] * 1e3
+    if res["nccl_ms"] > res["kernel_ms"]:
+        res["nccl_nvlink_gbs_each_way"] = moved / ((res["nccl_ms"] - res["kernel_ms"]) / 2 * 1e-3) / 1e9
+
+    # ---- fused over peer memory --------------------------------------------------------------------
+    try:
+        a_spec = sharding.share_from_root(full_spec)
+        a_info = sharding.share_from_root(full_info)
+        a_pcm = sharding.share_from_root(full_pcm)
+        row = T * C * 4096
+        ctx2 = A.Context(n, C, 4, 0, device=local)
+
+        def fused():
+            ctx2.process_device(a_spec + lo * row, a_info + lo * T * C * 8, a_pcm + lo * row, T, st.cuda_stream)
+
+        if rank == 0:
+            full_pcm.zero_()
+        barrier()
+        fused()          # first step of ctx2 (zero overlap) straight into rank 0's buffer
+        barrier()
+        res["fused_bit_identical"] = bool(torch.equal(region_sums(), want))
+        barrier()        # nobody overwrites rank 0's buffer while rank 0 still sums it
+        res["fused_ms"] = timed(fused, steps)
+        res["fused_frames_per_s"] = S * T / res["fused_ms"] * 1e3
+        res["fused_nvlink_gbs_each_way"] = moved / (res["fused_ms"] * 1e-3) / 1e9
+        ctx2.close()
+    except Exception as e:  # the NCCL path above stays valid
+        res["fused_error"] = f"{type(e).__name__}: {e}"[:300]
+    barrier()
+    return res
+
+
 def run_ours(args):
     import torch
 
@@ -221,57 +465,25 @@ def run_ours(args):
         S = args.streams
     if args.frames:
         T = args.frames
-
-    # --- synthetic batch of this rank (seeded per rank), resident in HBM --------------------
-    sigma = {2: 3.0e5, 3: 1.0e5, 4: 0.75e5, 5: 1.0e5}[cfg] * (0.5 if args.workload.endswith("_stereo") else 1.0)
-    g = torch.Generator(device=dev).manual_seed(1234 + rank)
-    spectra = torch.randn((S, T, C, 1024), device=dev, generator=g) * sigma
-    side = W.make(cfg, S, T, C, seed=rank, side_only=True)  # info/TNS side data only
-    info_np = side["info"]
-    info = torch.from_numpy(info_np.view(np.uint8).reshape(S, T, C, 8).copy()).to(dev)
-    blob = offs = None
-    tns_bytes = 0
-    if side["tns_blob"] is not None:
-        blob = torch.from_numpy(side["tns_blob"]).to(dev)
-        offs = torch.from_numpy(side["tns_offsets"].view(np.int32).copy()).to(dev)
-        tns_bytes = int(side["tns_blob"].size)
-    ops_np = ops = None
-    if args.workload.endswith("_stereo"):
-        ops_np = W.joint_stereo_ops(S, T, seed=rank)
-        info_np["stereo_present"][:, :, 0] = 1
-        info = torch.from_numpy(info_np.view(np.uint8).reshape(S, T, C, 8).copy()).to(dev)
-        ops = torch.from_numpy(ops_np.view(np.uint8).reshape(S, T, 768).copy()).to(dev)
-    stereo_bytes = 0 if ops_np is None else int(ops_np.nbytes)
-    pcm = torch.empty((S, T, 1024, C), device=dev)
-    ctx = A.Context(S, C, side["sample_index"], side["flags"], device=local)
     stream = torch.cuda.current_stream()
-
-    def step():
-        ctx.process_device(spectra.data_ptr(), info.data_ptr(), pcm.data_ptr(), T, stream.cuda_stream,
-                           blob.data_ptr() if blob is not None else 0, offs.data_ptr() if offs is not None else 0,
-                           tns_bytes, ops.data_ptr() if ops is not None else 0)
+    traffic_tab = load_traffic()
 
     def barrier():
         if world > 1:
             torch.distributed.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
-        step()
+    # --- headline: synthetic batch of this rank (seeded per rank), resident in HBM ------------
+    b = Batch(A, W, torch, args.workload, S, T, rank, dev, local)
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
+        b.step(stream)
     barrier()
-    launches0 = ctx.launches
-    evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    launches0 = b.ctx.launches
     with ClockSampler(local) as clocks:
-        barrier()
-        evs[0].record(stream)
-        for i in range(args.steps):
-            step()
-            evs[i + 1].record(stream)
-        barrier()
+        total_ms, per_step = time_steps(torch, lambda: b.step(stream), args.steps, 0, stream, barrier)
     clock_kernel = clocks.summary()
-    total_ms = evs[0].elapsed_time(evs[-1])
-    per_step = [evs[i].elapsed_time(evs[i + 1]) for i in range(args.steps)]
-    gpu_launches = ctx.launches - launches0
+    gpu_launches = b.ctx.launches - launches0
     t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
     if world > 1:
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
@@ -279,14 +491,15 @@ def run_ours(args):
     value = world * S * T * args.steps / (total_ms_max * 1e-3)
 
     # sanity: the timed kernels produced real PCM
-    peak = float(pcm.abs().max())
-    assert 0.05 < peak < 50 and bool(torch.isfinite(pcm).all()), peak
+    peak = float(b.pcm.abs().max())
+    assert 0.05 < peak < 50 and bool(torch.isfinite(b.pcm).all()), peak
 
     # --- end to end through the host-buffer C-ABI call (H2D + D2H inside the timed region) ---
     e2e = None
+    side, info_np, ops_np, tns_bytes = b.side, b.info_np, b.ops_np, b.tns_bytes
     if not args.no_e2e:
         h_spec = torch.empty((S, T, C, 1024), dtype=torch.float32, pin_memory=True)
-        h_spec.copy_(spectra)
+        h_spec.copy_(b.spectra)
         h_pcm = torch.empty((S, T, 1024, C), dtype=torch.float32, pin_memory=True)
         spec_np, pcm_np = h_spec.numpy(), h_pcm.numpy()
         ctx2 = A.Context(S, C, side["sample_index"], side["flags"], device=local)
@@ -311,28 +524,55 @@ def run_ours(args):
             torch.distributed.all_reduce(te, op=torch.distributed.ReduceOp.MAX)
         e2e_val = world * S * T * e2e_steps / float(te.item())
         assert np.isfinite(pcm_np[0, 0]).all() and np.abs(pcm_np[-1, -1]).max() > 0
-        side_bytes = info_np.nbytes + (tns_bytes + side["tns_offsets"].nbytes if tns_bytes else 0) + stereo_bytes
+        side_bytes = info_np.nbytes + (tns_bytes + side["tns_offsets"].nbytes if tns_bytes else 0) + b.stereo_bytes
         e2e = {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(spec_np.nbytes + side_bytes),
                "d2h_bytes_per_step": int(pcm_np.nbytes), "steps": e2e_steps,
                "ms_per_step": float(te.item()) / e2e_steps * 1e3,
                "api": "aacfb_process (pinned host buffers, 2-lane copy/compute pipeline)",
                "numa": f"process bound to the {numa_cpus} CPUs local to the GPU" if numa_cpus else "no binding"}
         ctx2.close()
+        del h_spec, h_pcm, spec_np, pcm_np
+    alg_head = b.alg_bytes
+    b.close()
+    del b
+    torch.cuda.empty_cache()
+
+    # --- the other north_star configurations, same clock, same box (N = 1: BENCH and SCALE's first point) ---
+    configs = None
+    if world == 1 and not args.no_configs and args.workload == "config2" and not args.streams and not args.frames:
+        configs = {}
+        for name in ("config3", "config4", "config5", "config2_stereo"):
+            _, S2, T2, C2, desc2 = WORKLOADS[name]
+            bb = Batch(A, W, torch, name, S2, T2, rank, dev, local)
+            k = max(5, min(args.steps, 100))
+            for _ in range(3):
+                bb.step(stream)
+            l0 = bb.ctx.launches
+            tot, per = time_steps(torch, lambda: bb.step(stream), k, 0, stream, barrier)
+            ms = tot / k
+            pk = float(bb.pcm.abs().max())
+            assert 0.01 < pk < 100 and bool(torch.isfinite(bb.pcm).all()), (name, pk)
+            configs[name] = {"workload": desc2, "steps": k, "ms_per_step": ms, "value": S2 * T2 / ms * 1e3, "unit": UNIT,
+                             "gpu_launches": int(bb.ctx.launches - l0),
+                             "roofline": roofline_record(name, bb.alg_bytes, float(np.mean(per)), bb.tns_bytes > 0, traffic_tab)}
+            bb.close()
+            del bb
+            torch.cuda.empty_cache()
+
+    # --- N > 1: what the box's host<->device path gives all ranks at once, and config 5 from rank 0 ---
+    pcie = scatter = None
+    if world > 1 and not args.no_pcie_probe:
+        pcie = pcie_probe(torch, dev, world)
+    if world > 1 and not args.no_scatter:
+        try:
+            scatter = run_config5_scatter(A, W, torch, args, rank, world, local, dev)
+        except Exception as e:
+            scatter = {"error": f"{type(e).__name__}: {e}"[:300]}
 
     if rank == 0:
-        peak_gbs, peak_src = measured_peak()
-        # synthesis-kernel launch time: each step is one memset + (tns_kernel) + synth_kernel on one
+        # synthesis-kernel launch time: each step is one memset + synth_kernel (x2 instantiations) on one
         # stream; event-to-event time of a step is the launch duration the roofline uses
         launch_ms = float(np.mean(per_step))
-        alg = algorithmic_bytes(S, T, C, tns_bytes, stereo_bytes)
-        achieved = alg / (launch_ms * 1e-3) / 1e9
-        traffic = None
-        prof = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(prof):
-            try:
-                traffic = json.load(open(prof)).get(args.workload)
-            except Exception:
-                traffic = None
         cpu = None
         os.sched_setaffinity(0, all_cpus)  # the CPU baseline uses every host core again
         if world == 1 and not args.no_cpu:
@@ -351,7 +591,7 @@ def run_ours(args):
                    "note": "C restatement of aac.js under the JS rounding model (no JS engine on this image)"}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": total_ms_max / args.steps, "higher_is_better": True,
+            "warmup": warm, "ms_per_step": total_ms_max / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"{args.workload}: {desc}", "streams_per_gpu": S, "frames_per_stream": T,
                        "channels": C, "parallelism": f"streams sharded over {world} GPU(s), no data-path collective",
@@ -359,15 +599,16 @@ def run_ours(args):
             "clocks": clock_kernel,
             "e2e": e2e,
             "gpu_launches": int(gpu_launches),
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
-                         "frac": achieved / peak_gbs, "traffic": traffic, "peak_source": peak_src,
-                         "kernel": "aacfb::synth_kernel" + (" (+ aacfb::tns_kernel)" if tns_bytes else ""),
-                         "algorithmic_bytes_per_launch": alg,
-                         "launch_ms": launch_ms},
+            "roofline": roofline_record(args.workload, alg_head, launch_ms, tns_bytes > 0, traffic_tab),
             "cpu_baseline": cpu,
         }
+        if configs is not None:
+            line["configs"] = configs
+        if pcie is not None:
+            line["pcie_concurrent"] = pcie
+        if scatter is not None:
+            line["config5_scatter"] = scatter
         print(json.dumps(line), flush=True)
-    ctx.close()
     if world > 1:
         torch.distributed.destroy_process_group()
 
@@ -385,6 +626,10 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=0, help="timed steps of the e2e leg (default min(steps, 20))")
     ap.add_argument("--no-numa", action="store_true", help="do not bind the process to the GPU's NUMA node")
+    ap.add_argument("--no-configs", action="store_true", help="N = 1: skip the configs record (configs 3, 4, 5, config2_stereo)")
+    ap.add_argument("--no-scatter", action="store_true", help="N > 1: skip BASELINE configs[4] (1 048 576 frames from rank 0)")
+    ap.add_argument("--no-pcie-probe", action="store_true", help="N > 1: skip the concurrent host<->device copy probe")
+    ap.add_argument("--scatter-streams", type=int, default=4096, help="streams of the config-5 batch on rank 0 (x 256 frames)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
