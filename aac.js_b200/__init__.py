@@ -43,7 +43,17 @@ ERRORS = {-1: "AACFB_ERR_ARG", -2: "AACFB_ERR_SMALL", -3: "AACFB_ERR_SEQUENCE", 
 ABI_SYMBOLS = ["aacfb_create", "aacfb_destroy", "aacfb_reset", "aacfb_process", "aacfb_process_device",
                "aacfb_filterbank_process", "aacfb_tns_process", "aacfb_get_overlap", "aacfb_set_overlap",
                "aacfb_last_error", "aacfb_version", "aacfb_launch_count", "aacfb_get_table",
-               "aacfb_process_stereo", "aacfb_process_device_stereo", "aacfb_get_swb_offsets", "aacfb_adts_index"]
+               "aacfb_process_stereo", "aacfb_process_device_stereo", "aacfb_get_swb_offsets", "aacfb_adts_index",
+               "aacfb_process_io", "aacfb_process_device_io", "aacfb_host_alloc", "aacfb_host_free",
+               "aacfb_host_register", "aacfb_host_unregister"]
+
+# aacfb_qframe: one channel-frame BEFORE inverse quantisation (include/aacfb.h)
+QFRAME_DTYPE = np.dtype([("group_len", "u1", (8,)), ("band", "u2", (120,)), ("reserved", "u1", (8,)), ("q", "i2", (1024,))])
+assert QFRAME_DTYPE.itemsize == 2304
+BAND_ZERO, BAND_SPECTRAL, BAND_NOISE, BAND_UNDEFINED = 0x0000, 0x4000, 0x8000, 0x01ff
+IN_F32, IN_Q16 = 0, 1
+PCM_F32, PCM_S16 = 0, 1
+ZERO_BT = 0  # ics.js:35
 
 ADTS_FRAME_DTYPE = np.dtype([("offset", "u8"), ("frame_length", "u4"), ("header_bytes", "u1"), ("profile", "u1"),
                              ("sampling_index", "u1"), ("chan_config", "u1"), ("num_frames", "u1"), ("reserved", "u1", (7,))])
@@ -95,6 +105,14 @@ def lib():
             L.aacfb_get_swb_offsets.argtypes = [ci, ci, vp, ci]
         if hasattr(L, "aacfb_adts_index"):
             L.aacfb_adts_index.argtypes = [vp, C.c_size_t, vp, ci, C.POINTER(C.c_size_t)]
+        if hasattr(L, "aacfb_process_io"):
+            L.aacfb_process_io.argtypes = [vp, vp, u32, vp, vp, vp, vp, vp, u32, ci]
+            L.aacfb_process_device_io.argtypes = [vp, vp, u32, vp, vp, vp, vp, C.c_size_t, vp, u32, ci, vp]
+            L.aacfb_host_alloc.argtypes = [C.c_size_t]
+            L.aacfb_host_alloc.restype = vp
+            L.aacfb_host_free.argtypes = [vp]
+            L.aacfb_host_register.argtypes = [vp, C.c_size_t]
+            L.aacfb_host_unregister.argtypes = [vp]
         _lib = L
     return _lib
 
@@ -136,6 +154,40 @@ def adts_index(data, capacity: int | None = None):
     if n < 0:
         raise AacfbError(n, lib().aacfb_last_error(None).decode())
     return frames[:n], int(consumed.value)
+
+
+def host_alloc(shape, dtype) -> np.ndarray:
+    """A numpy array on page-locked memory owned by the library (aacfb_host_alloc) -- what the N-API
+    addon wraps in an external ArrayBuffer for the decoder's staging typed arrays.  Free with host_free."""
+    dt = np.dtype(dtype)
+    n = int(np.prod(shape)) * dt.itemsize
+    p = lib().aacfb_host_alloc(n)
+    if not p:
+        raise AacfbError(-5, lib().aacfb_last_error(None).decode())
+    buf = (C.c_uint8 * n).from_address(p)
+    a = np.frombuffer(buf, dtype=dt).reshape(shape)
+    _host_allocs[a.ctypes.data] = p
+    return a
+
+
+_host_allocs: dict = {}
+
+
+def host_free(a: np.ndarray):
+    p = _host_allocs.pop(a.ctypes.data, None)
+    if p:
+        lib().aacfb_host_free(C.c_void_p(p))
+
+
+def host_register(a: np.ndarray):
+    """Page-lock an existing contiguous array for the life of the decoder (aacfb_host_register)."""
+    rc = lib().aacfb_host_register(C.c_void_p(a.ctypes.data), a.nbytes)
+    if rc != 0:
+        raise AacfbError(rc, lib().aacfb_last_error(None).decode())
+
+
+def host_unregister(a: np.ndarray):
+    lib().aacfb_host_unregister(C.c_void_p(a.ctypes.data))
 
 
 class Context:
@@ -202,6 +254,43 @@ class Context:
         self._check(lib().aacfb_process(self._h, _ptr(spectra), _ptr(info), _ptr(tns_blob), _ptr(tns_offsets),
                                         _ptr(pcm), T))
         return pcm
+
+    def process_io(self, inp, info, tns_blob=None, tns_offsets=None, out=None, stereo_ops=None, *, in_format=IN_F32,
+                   pcm_format=PCM_F32) -> np.ndarray:
+        """aacfb_process_io: `inp` is spectra [S][T][C][1024] f32 (IN_F32) or aacfb_qframe records [S][T][C]
+        (IN_Q16: the device dequantises, ics.js:203-266); returns pcm [S][T][1024][C] as f32 (/32768) or int16."""
+        if in_format == IN_Q16:
+            inp = np.ascontiguousarray(inp, QFRAME_DTYPE)
+            S, T, Cn = inp.shape
+        else:
+            inp = np.ascontiguousarray(inp, np.float32)
+            S, T, Cn, n = inp.shape
+            assert n == 1024
+        assert (S, Cn) == (self.n_streams, self.channels), inp.shape
+        info = np.ascontiguousarray(info, INFO_DTYPE)
+        assert info.size == S * T * Cn
+        if tns_blob is not None:
+            tns_blob = np.ascontiguousarray(tns_blob, np.uint8)
+            tns_offsets = np.ascontiguousarray(tns_offsets, np.uint32)
+            assert tns_offsets.size == S * T * Cn + 1
+        dt = np.int16 if pcm_format == PCM_S16 else np.float32
+        pcm = out if out is not None else np.empty((S, T, 1024, Cn), dt)
+        assert pcm.dtype == dt and pcm.flags.c_contiguous and pcm.size == S * T * Cn * 1024
+        if stereo_ops is not None:
+            stereo_ops = np.ascontiguousarray(stereo_ops, STEREO_DTYPE)
+            assert stereo_ops.size * 2 == S * T * Cn, stereo_ops.shape
+        self._check(lib().aacfb_process_io(self._h, _ptr(inp), in_format, _ptr(info), _ptr(stereo_ops), _ptr(tns_blob),
+                                           _ptr(tns_offsets), _ptr(pcm), pcm_format, T))
+        return pcm
+
+    def process_device_io(self, d_input: int, in_format: int, d_info: int, d_pcm: int, pcm_format: int, n_frames: int,
+                          stream: int = 0, d_tns_blob: int = 0, d_tns_offsets: int = 0, tns_blob_bytes: int = 0,
+                          d_stereo_ops: int = 0):
+        """aacfb_process_device_io with raw device addresses."""
+        self._check(lib().aacfb_process_device_io(
+            self._h, C.c_void_p(d_input), in_format, C.c_void_p(d_info), C.c_void_p(d_stereo_ops or None),
+            C.c_void_p(d_tns_blob or None), C.c_void_p(d_tns_offsets or None), tns_blob_bytes, C.c_void_p(d_pcm),
+            pcm_format, n_frames, C.c_void_p(stream or None)))
 
     def process_device(self, d_spectra: int, d_info: int, d_pcm: int, n_frames: int, stream: int = 0,
                        d_tns_blob: int = 0, d_tns_offsets: int = 0, tns_blob_bytes: int = 0, d_stereo_ops: int = 0):
@@ -360,6 +449,47 @@ def pack_stereo(element, sample_index: int, out=None):
                 i = end
         group_off += int(glen[g]) * 128
     return rec, present
+
+
+_SF_INDEX = None
+
+
+def scalefactor_index(value) -> int:
+    """Index i with SCALEFACTOR_TABLE[i] == |value| (tables.js:168-176: distinct powers 2^((i-200)/4)), or
+    BAND_UNDEFINED when the value is not in the table (NaN: the reference read outside it)."""
+    global _SF_INDEX
+    if _SF_INDEX is None:
+        tab = np.empty(8192, np.float32)
+        n = lib().aacfb_get_table(9, _ptr(tab), tab.size)
+        _SF_INDEX = {float(v): i for i, v in enumerate(tab[:n])}
+    return _SF_INDEX.get(abs(float(np.float32(value))), BAND_UNDEFINED)
+
+
+def pack_qframe(ics, quant, out=None):
+    """The host's share of ICStream.decodeSpectralData (ics.js:203-266) when the device dequantises:
+    `ics` = what decodeBandTypes / decodeScaleFactors left behind (info.windowSequence, groupCount,
+    groupLength, maxSFB; bandTypes[idx], scaleFactors[idx]) and `quant` = the 1024 Huffman-decoded
+    integers in data[] order.  Python twin of js/quant_pack.js.  Returns one QFRAME_DTYPE record."""
+    rec = out if out is not None else np.zeros((), QFRAME_DTYPE)
+    get = (lambda o, k: o[k]) if isinstance(ics, dict) else getattr
+    info = get(ics, "info")
+    geti = (lambda k: info[k]) if isinstance(info, dict) else (lambda k: getattr(info, k))
+    groups, max_sfb = int(geti("groupCount")), int(geti("maxSFB"))
+    rec["group_len"][...] = 0
+    rec["group_len"][:groups] = np.asarray(geti("groupLength"))[:groups]
+    rec["band"][...] = BAND_ZERO
+    bt, sf = get(ics, "bandTypes"), get(ics, "scaleFactors")
+    for idx in range(groups * max_sfb):
+        t = int(bt[idx])
+        if t == ZERO_BT or t == INTENSITY_BT or t == INTENSITY_BT2:      # ics.js:222
+            rec["band"][idx] = BAND_ZERO
+        elif t == NOISE_BT:                                                # scaleFactors = -TABLE[i], ics.js:158
+            rec["band"][idx] = BAND_NOISE | scalefactor_index(sf[idx])
+        else:
+            rec["band"][idx] = BAND_SPECTRAL | scalefactor_index(sf[idx])
+    rec["reserved"][...] = 0
+    rec["q"][...] = np.asarray(quant, np.int16)
+    return rec
 
 
 class AACDecoder:

@@ -33,9 +33,10 @@ struct Lane {                    // device staging of one in-flight sub-batch of
     uint32_t *d_offsets = nullptr;
     aacfb_stereo_ops *d_stereo = nullptr;  // [cap_stereo] records of the sub-batch's pair-frames
     float *d_stereo_out = nullptr;         // output of the stereo pre-pass (TNS modes only)
+    float *d_deq = nullptr;                // output of the inverse-quantisation pre-pass (Q16 input + TNS modes only)
     size_t cap_cf = 0;           // capacity in channel-frames
     size_t cap_scratch = 0;
-    size_t cap_stereo = 0, cap_stereo_out = 0;
+    size_t cap_stereo = 0, cap_stereo_out = 0, cap_deq = 0;
     // scratch holds cap_scratch rows followed by cap_scratch range words (see tns_kernel)
     uint32_t *ranges() const { return reinterpret_cast<uint32_t *>(d_scratch + cap_scratch * 1024); }
 };
@@ -50,6 +51,7 @@ struct aacfb_ctx {
     SynthTables *d_tab = nullptr;       // windows carry the 2^-15 output scale (decoder.js:210)
     SynthTables *d_tab_unit = nullptr;  // unscaled windows, for the inner seam (FilterBank.process output)
     TnsBandTables *d_bands = nullptr;
+    DequantTables *d_dq = nullptr;      // inverse-quantisation tables of this sample rate (ics.js:203-266)
     unsigned *d_counters = nullptr;
     unsigned counter_next = 0;
     Lane lane[kLanes];
@@ -59,6 +61,8 @@ struct aacfb_ctx {
     size_t cap_dev_scratch = 0;
     float *d_dev_stereo_out = nullptr;  // stereo pre-pass output of the device-pointer path
     size_t cap_dev_stereo_out = 0;
+    float *d_dev_deq = nullptr;         // inverse-quantisation pre-pass output of the device-pointer path
+    size_t cap_dev_deq = 0;
     uint64_t launches = 0;
     char err[256] = "";
 };
@@ -111,58 +115,95 @@ int pick_slice(int n_pairs, int T, int workers) {
 
 bool stereo_needs_prepass(int nc, bool tns_on) { return tns_on || nc != 2; }
 
-// Enqueue TNS pre-pass (if the context's mode asks for it) and the synthesis
-// kernel for S_sub streams starting at stream s_base, all on `stream`.
+// What one enqueue works on (device pointers).
+struct Job {
+    const float *d_spectra = nullptr;         // float rows (AACFB_IN_F32) ...
+    const aacfb_qframe *d_q = nullptr;        // ... or aacfb_qframe records (AACFB_IN_Q16)
+    float *d_deq = nullptr;                   // Q16 + TNS modes: where the inverse-quantisation pre-pass writes
+    const aacfb_frame_info *d_info = nullptr;
+    const aacfb_stereo_ops *d_stereo = nullptr;
+    float *d_stereo_out = nullptr;
+    const uint8_t *d_blob = nullptr;
+    const uint32_t *d_offsets = nullptr;
+    size_t blob_bytes = 0;
+    float *d_scratch = nullptr;
+    uint32_t *d_ranges = nullptr;
+    void *d_pcm = nullptr;
+    bool s16 = false;                         // AACFB_PCM_S16
+    int S_sub = 0, s_base = 0, T = 0, nc = 0, c0 = 0;
+    float scale = 1.0f;                       // 2^-15 for float PCM (decoder.js:210), 1 for the inner seam and int16
+    bool in_place_state = false;
+    bool no_short = false;                    // the caller has seen every window_sequence: no EIGHT_SHORT in the batch
+};
+
+bool tns_active(const aacfb_ctx *ctx, const Job &j) {
+    const uint32_t mode = ctx->flags & AACFB_TNS_MODE_MASK;
+    return mode != AACFB_TNS_AS_SHIPPED && j.d_blob && j.d_offsets && j.blob_bytes > 0 && j.d_scratch;
+}
+
+// Enqueue the pre-passes the context's mode asks for and the synthesis kernel for S_sub streams
+// starting at stream s_base, all on `stream`.
 //
+// Quantised input (d_q): synth_kernel dequantises the staged records itself (ics.js:203-266) unless a
+// TNS pass has to see float rows first; then dequant_kernel writes them to d_deq.
 // Stereo tools (d_stereo != nullptr): with two channels and no TNS pass, synth_kernel applies the
 // ops to the staged rows (no extra traffic but the records).  When TNS has to run between the
 // stereo tools and the IMDCT (decoder.js:300-319), or with more than one pair per stream, a
 // pre-pass writes the processed spectra to d_stereo_out and everything downstream reads that.
-int enqueue(aacfb_ctx *ctx, const float *d_spectra, const aacfb_frame_info *d_info, const aacfb_stereo_ops *d_stereo,
-            float *d_stereo_out, const uint8_t *d_blob,
-            const uint32_t *d_offsets, size_t blob_bytes, float *d_scratch, uint32_t *d_ranges, float *d_pcm, int S_sub,
-            int s_base,
-            int T, int nc, int c0, float scale, bool in_place_state, cudaStream_t stream) {
+int enqueue(aacfb_ctx *ctx, Job j, cudaStream_t stream) {
     const uint32_t mode = ctx->flags & AACFB_TNS_MODE_MASK;
-    const size_t n_cf = (size_t)S_sub * T * nc;
-    const bool tns_on = mode != AACFB_TNS_AS_SHIPPED && d_blob && d_offsets && blob_bytes > 0 && d_scratch;
-    if (d_stereo && stereo_needs_prepass(nc, tns_on)) {
-        if (!d_stereo_out) return fail(ctx, AACFB_ERR_ARG, "internal: no buffer for the stereo pre-pass");
+    const size_t n_cf = (size_t)j.S_sub * j.T * j.nc;
+    if ((long long)j.S_sub * j.T * j.nc >= (1ll << 30)) return fail(ctx, AACFB_ERR_ARG, "batch too large: split it (channel-frames < 2^30)");
+    const bool tns_on = tns_active(ctx, j);
+    const bool stereo_pre = j.d_stereo && stereo_needs_prepass(j.nc, tns_on);
+    if (j.d_q && (tns_on || stereo_pre)) {
+        if (!j.d_deq) return fail(ctx, AACFB_ERR_ARG, "internal: no buffer for the inverse-quantisation pre-pass");
+        DequantParams dp{};
+        dp.qframes = reinterpret_cast<const uint8_t *>(j.d_q); dp.info = j.d_info; dp.dq = ctx->d_dq; dp.out = j.d_deq; dp.n_cf = n_cf;
+        CU(ctx, launch_dequant(dp, stream));
+        ctx->launches++;
+        j.d_spectra = j.d_deq;
+        j.d_q = nullptr;
+    }
+    if (stereo_pre) {
+        if (!j.d_stereo_out) return fail(ctx, AACFB_ERR_ARG, "internal: no buffer for the stereo pre-pass");
         StereoParams st{};
-        st.spectra = d_spectra; st.out = d_stereo_out; st.info = d_info; st.stereo = d_stereo; st.n_pairs_frames = n_cf / 2;
+        st.spectra = j.d_spectra; st.out = j.d_stereo_out; st.info = j.d_info; st.stereo = j.d_stereo; st.n_pairs_frames = n_cf / 2;
         CU(ctx, launch_stereo(st, stream));
         ctx->launches++;
-        d_spectra = d_stereo_out;
-        d_stereo = nullptr;
+        j.d_spectra = j.d_stereo_out;
+        j.d_stereo = nullptr;
     }
     if (tns_on) {
         TnsParams tp{};
-        tp.spectra = d_spectra; tp.scratch = d_scratch; tp.ranges = d_ranges; tp.info = d_info; tp.blob = d_blob;
-        tp.offsets = d_offsets;
-        tp.blob_bytes = blob_bytes; tp.n_cf = n_cf; tp.sample_index = ctx->sample_index;
+        tp.spectra = j.d_spectra; tp.scratch = j.d_scratch; tp.ranges = j.d_ranges; tp.info = j.d_info; tp.blob = j.d_blob;
+        tp.offsets = j.d_offsets;
+        tp.blob_bytes = j.blob_bytes; tp.n_cf = n_cf; tp.sample_index = ctx->sample_index;
         tp.ar = mode == AACFB_TNS_FIXED_AR; tp.bands = ctx->d_bands;
         CU(ctx, launch_tns(tp, stream));
         ctx->launches++;
     }
     SynthParams sp{};
-    sp.spectra = d_spectra; sp.scratch = tns_on ? d_scratch : nullptr; sp.ranges = d_ranges; sp.info = d_info; sp.pcm = d_pcm;
-    sp.stereo = d_stereo;
+    sp.spectra = j.d_spectra; sp.scratch = tns_on ? j.d_scratch : nullptr; sp.ranges = j.d_ranges; sp.info = j.d_info;
+    sp.pcm = static_cast<float *>(j.d_pcm);
+    sp.qframes = reinterpret_cast<const uint8_t *>(j.d_q); sp.dq = ctx->d_dq; sp.pcm_s16 = j.s16 ? 1 : 0;
+    sp.stereo = j.d_stereo;
     sp.ovl_in = ctx->d_ovl[ctx->cur];
-    sp.ovl_out = in_place_state ? ctx->d_ovl[ctx->cur] : ctx->d_ovl[ctx->cur ^ 1];
-    sp.tab = scale == 1.0f ? ctx->d_tab_unit : ctx->d_tab;
-    const int n_pairs = (S_sub * nc + 1) / 2;
-    if ((long long)S_sub * T * nc >= (1ll << 30)) return fail(ctx, AACFB_ERR_ARG, "batch too large: split it (channel-frames < 2^30)");
+    sp.ovl_out = j.in_place_state ? ctx->d_ovl[ctx->cur] : ctx->d_ovl[ctx->cur ^ 1];
+    sp.tab = j.scale == 1.0f ? ctx->d_tab_unit : ctx->d_tab;
+    const int n_pairs = (j.S_sub * j.nc + 1) / 2;
     // in-place state (inner seam): one item, so the state is read before it is written
-    const int Q = in_place_state ? n_pairs * T : pick_slice(n_pairs, T, ctx->num_sms * kWorkers);
-    sp.g = make_geometry(S_sub, T, nc, ctx->C, c0, s_base, Q);
-    sp.scale = scale;
+    const int Q = j.in_place_state ? n_pairs * j.T : pick_slice(n_pairs, j.T, ctx->num_sms * kWorkers);
+    sp.g = make_geometry(j.S_sub, j.T, j.nc, ctx->C, j.c0, j.s_base, Q);
+    sp.scale = j.scale;
     // Two instantiations walk the same item list: the long-only one takes the items without
     // EIGHT_SHORT frames, the generic one the rest (each item is classified on the device).
-    // If the long-only pass finds no such item the generic pass exits at once.
+    // If the long-only pass finds no such item the generic pass exits at once; a caller that has
+    // looked at every window_sequence itself (the host path's validation) spares that launch.
     unsigned *slots = ctx->d_counters + 4 * (ctx->counter_next++ % (kCounters / 4));
     CU(ctx, cudaMemsetAsync(slots, 0, 4 * sizeof(unsigned), stream));
     sp.short_items = slots + 2;
-    for (int generic = 0; generic < 2; ++generic) {
+    for (int generic = 0; generic < (j.no_short ? 1 : 2); ++generic) {
         sp.counter = slots + generic;
         CU(ctx, launch_synth(sp, ctx->num_sms, generic != 0, stream));
         ctx->launches++;
@@ -184,7 +225,8 @@ int grow_lane_stereo(aacfb_ctx *ctx, Lane &ln, size_t n_cf, bool prepass) {
     return AACFB_OK;
 }
 
-int grow_lane(aacfb_ctx *ctx, Lane &ln, size_t n_cf, bool need_scratch) {
+// d_spectra holds float rows or aacfb_qframe records (2304 <= 4096 bytes), d_pcm float or int16 samples.
+int grow_lane(aacfb_ctx *ctx, Lane &ln, size_t n_cf, bool need_scratch, bool need_deq = false) {
     if (n_cf > ln.cap_cf) {
         cudaFree(ln.d_spectra); cudaFree(ln.d_pcm); cudaFree(ln.d_info); cudaFree(ln.d_offsets);
         ln.d_spectra = ln.d_pcm = nullptr; ln.d_info = nullptr; ln.d_offsets = nullptr; ln.cap_cf = 0;
@@ -199,19 +241,30 @@ int grow_lane(aacfb_ctx *ctx, Lane &ln, size_t n_cf, bool need_scratch) {
         CU(ctx, cudaMalloc(&ln.d_scratch, n_cf * 4100));
         ln.cap_scratch = n_cf;
     }
+    if (need_deq && n_cf > ln.cap_deq) {
+        cudaFree(ln.d_deq); ln.d_deq = nullptr; ln.cap_deq = 0;
+        CU(ctx, cudaMalloc(&ln.d_deq, n_cf * 4096));
+        ln.cap_deq = n_cf;
+    }
     return AACFB_OK;
 }
 
-// Host-side validation of the side info (the reference throws on these:
-// tns.js:84-85; unknown window sequences cannot occur there, ics.js:282).
-int validate(aacfb_ctx *ctx, const aacfb_frame_info *info, const uint8_t *blob, const uint32_t *offsets, size_t n_cf) {
-    for (size_t i = 0; i < n_cf; ++i) {
+// Host-side validation of the side info of channel-frames [i0, i1) (the reference throws on these:
+// tns.js:84-85; unknown window sequences cannot occur there, ics.js:282).  `blob_bytes` = offsets[n_cf]:
+// every block has to lie inside it and the offsets must not decrease.  *any_short is raised when an
+// EIGHT_SHORT frame is seen (spares the generic kernel launch when none is).
+int validate(aacfb_ctx *ctx, const aacfb_frame_info *info, const uint8_t *blob, const uint32_t *offsets, size_t blob_bytes,
+             size_t i0, size_t i1, bool *any_short) {
+    for (size_t i = i0; i < i1; ++i) {
         if (info[i].window_sequence > 3)
             return fail(ctx, AACFB_ERR_SEQUENCE, "channel-frame %zu: window_sequence %u out of range", i,
                         (unsigned)info[i].window_sequence);
-        if (!info[i].tns_present || !blob || !offsets) continue;
+        if (info[i].window_sequence == AACFB_EIGHT_SHORT_SEQUENCE && any_short) *any_short = true;
+        if (!blob || !offsets) continue;
         const uint32_t o0 = offsets[i], o1 = offsets[i + 1];
-        if (o1 < o0 || (o0 & 3)) return fail(ctx, AACFB_ERR_TNS, "channel-frame %zu: bad TNS offsets", i);
+        if (o1 < o0 || o1 > blob_bytes) return fail(ctx, AACFB_ERR_TNS, "channel-frame %zu: TNS offsets decrease or leave the blob", i);
+        if (!info[i].tns_present) continue;
+        if (o0 & 3) return fail(ctx, AACFB_ERR_TNS, "channel-frame %zu: bad TNS offsets", i);
         if (o1 == o0) continue;
         if (o1 - o0 < 8) return fail(ctx, AACFB_ERR_TNS, "channel-frame %zu: TNS block too short", i);
         const uint8_t *b = blob + o0;
@@ -230,15 +283,34 @@ int validate(aacfb_ctx *ctx, const aacfb_frame_info *info, const uint8_t *blob, 
 }
 
 // Stereo side info: the flag belongs to the left channel of a pair, op codes index scale[128].
-int validate_stereo(aacfb_ctx *ctx, const aacfb_frame_info *info, const aacfb_stereo_ops *ops, size_t n_cf, int C) {
-    if (C & 1) return fail(ctx, AACFB_ERR_ARG, "stereo tools need an even channel count (pairs are channels 2j, 2j+1)");
-    for (size_t i = 0; i < n_cf; ++i) {
+int validate_stereo(aacfb_ctx *ctx, const aacfb_frame_info *info, const aacfb_stereo_ops *ops, size_t i0, size_t i1) {
+    for (size_t i = i0; i < i1; ++i) {
         if (!info[i].stereo_present) continue;
         if (i & 1) return fail(ctx, AACFB_ERR_ARG, "channel-frame %zu: stereo_present set on a right channel", i);
         const aacfb_stereo_ops &r = ops[i >> 1];
         for (int g = 0; g < 256; ++g)
             if (r.op[g] > AACFB_STEREO_IS + 127)
                 return fail(ctx, AACFB_ERR_ARG, "channel-frame %zu: stereo op %u out of range", i, (unsigned)r.op[g]);
+    }
+    return AACFB_OK;
+}
+
+// Quantised input: maxSFB must fit the band table of the window length (the reference would read
+// swbOffsets past its end, ics.js:217-219) and the groups of an EIGHT_SHORT frame must cover its 8 windows.
+int validate_q(aacfb_ctx *ctx, const aacfb_frame_info *info, const aacfb_qframe *q, size_t i0, size_t i1) {
+    const TnsBandTables &B = tns_band_tables();
+    for (size_t i = i0; i < i1; ++i) {
+        const bool is_short = info[i].window_sequence == AACFB_EIGHT_SHORT_SEQUENCE;
+        const int nb = is_short ? B.swb_short_count[ctx->sample_index] : B.swb_long_count[ctx->sample_index];
+        if (info[i].max_sfb > nb)
+            return fail(ctx, AACFB_ERR_ARG, "channel-frame %zu: max_sfb %u exceeds the %d bands of this window length", i,
+                        (unsigned)info[i].max_sfb, nb);
+        int windows = 0, groups = 0;
+        for (int g = 0; g < 8 && q[i].group_len[g]; ++g) { windows += q[i].group_len[g]; ++groups; }
+        if (windows != (is_short ? 8 : 1))
+            return fail(ctx, AACFB_ERR_ARG, "channel-frame %zu: group_len covers %d windows", i, windows);
+        if (groups * (int)info[i].max_sfb > 120)
+            return fail(ctx, AACFB_ERR_ARG, "channel-frame %zu: more than 120 sections", i);
     }
     return AACFB_OK;
 }
@@ -269,6 +341,14 @@ API int aacfb_get_table(int which, float *dst, int capacity) {
     case 5: src = H.kbd1024; n = 1024; break;
     case 6: src = H.sine128; n = 128; break;
     case 7: src = H.kbd128; n = 128; break;
+    case 8: case 9: case 10: {   // inverse-quantisation tables (the same for every sample rate)
+        static DequantTables *D = nullptr;
+        static std::once_flag once;
+        std::call_once(once, [] { D = new DequantTables; build_dequant_tables(4, *D); });
+        src = which == 8 ? D->iq : which == 9 ? D->sf : D->noise;
+        n = which == 8 ? 8192 : which == 9 ? 428 : 32;
+        break;
+    }
     default: return AACFB_ERR_ARG;
     }
     if (capacity < n) return AACFB_ERR_ARG;
@@ -374,6 +454,15 @@ API int aacfb_create(aacfb_ctx **out, int device, int n_streams, int channels, i
     if ((e = cudaMalloc(&ctx->d_bands, sizeof(TnsBandTables))) != cudaSuccess) return bail(e, "cudaMalloc bands");
     if ((e = cudaMemcpy(ctx->d_bands, &tns_band_tables(), sizeof(TnsBandTables), cudaMemcpyHostToDevice)) != cudaSuccess)
         return bail(e, "cudaMemcpy bands");
+    {
+        DequantTables *dq = new (std::nothrow) DequantTables;
+        if (!dq) { aacfb_destroy(ctx); return fail(nullptr, AACFB_ERR_NOMEM, "out of memory"); }
+        build_dequant_tables(sample_index, *dq);
+        e = cudaMalloc(&ctx->d_dq, sizeof(DequantTables));
+        if (e == cudaSuccess) e = cudaMemcpy(ctx->d_dq, dq, sizeof(DequantTables), cudaMemcpyHostToDevice);
+        delete dq;
+        if (e != cudaSuccess) return bail(e, "dequant tables");
+    }
     if ((e = cudaMalloc(&ctx->d_counters, kCounters * sizeof(unsigned))) != cudaSuccess) return bail(e, "cudaMalloc");
     for (int i = 0; i < kLanes; ++i)
         if ((e = cudaStreamCreateWithFlags(&ctx->lane[i].stream, cudaStreamNonBlocking)) != cudaSuccess)
@@ -390,9 +479,9 @@ API int aacfb_destroy(aacfb_ctx *ctx) {
         Lane &ln = ctx->lane[i];
         if (ln.stream) cudaStreamDestroy(ln.stream);
         cudaFree(ln.d_spectra); cudaFree(ln.d_pcm); cudaFree(ln.d_scratch); cudaFree(ln.d_info); cudaFree(ln.d_offsets);
-        cudaFree(ln.d_stereo); cudaFree(ln.d_stereo_out);
+        cudaFree(ln.d_stereo); cudaFree(ln.d_stereo_out); cudaFree(ln.d_deq);
     }
-    cudaFree(ctx->d_dev_stereo_out);
+    cudaFree(ctx->d_dev_stereo_out); cudaFree(ctx->d_dev_deq); cudaFree(ctx->d_dq);
     cudaFree(ctx->d_ovl[0]); cudaFree(ctx->d_ovl[1]); cudaFree(ctx->d_tab); cudaFree(ctx->d_tab_unit); cudaFree(ctx->d_bands);
     cudaFree(ctx->d_counters); cudaFree(ctx->d_blob); cudaFree(ctx->d_dev_scratch);
     delete ctx;
@@ -426,89 +515,114 @@ API int aacfb_set_overlap(aacfb_ctx *ctx, const float *overlap) {
 API int aacfb_process_device(aacfb_ctx *ctx, const float *d_spectra, const aacfb_frame_info *d_info,
                              const uint8_t *d_tns_blob, const uint32_t *d_tns_offsets, size_t tns_blob_bytes,
                              float *d_pcm, int n_frames, void *stream) {
-    return aacfb_process_device_stereo(ctx, d_spectra, d_info, nullptr, d_tns_blob, d_tns_offsets, tns_blob_bytes, d_pcm,
-                                       n_frames, stream);
+    return aacfb_process_device_io(ctx, d_spectra, AACFB_IN_F32, d_info, nullptr, d_tns_blob, d_tns_offsets, tns_blob_bytes,
+                                   d_pcm, AACFB_PCM_F32, n_frames, stream);
 }
 
 API int aacfb_process_device_stereo(aacfb_ctx *ctx, const float *d_spectra, const aacfb_frame_info *d_info,
                                     const aacfb_stereo_ops *d_stereo_ops, const uint8_t *d_tns_blob,
                                     const uint32_t *d_tns_offsets, size_t tns_blob_bytes, float *d_pcm, int n_frames,
                                     void *stream) {
+    return aacfb_process_device_io(ctx, d_spectra, AACFB_IN_F32, d_info, d_stereo_ops, d_tns_blob, d_tns_offsets,
+                                   tns_blob_bytes, d_pcm, AACFB_PCM_F32, n_frames, stream);
+}
+
+// The device-pointer entry points TRUST their side info (it lives in device memory: no host-side
+// validation; the kernels mask window_sequence to 2 bits and bound every TNS block by the blob size).
+// Use them from ONE stream per context: the pre-pass scratch buffers belong to the context, and they
+// are (re)allocated -- with a device synchronisation -- whenever a call needs more than any before it.
+API int aacfb_process_device_io(aacfb_ctx *ctx, const void *d_input, uint32_t in_format, const aacfb_frame_info *d_info,
+                                const aacfb_stereo_ops *d_stereo_ops, const uint8_t *d_tns_blob,
+                                const uint32_t *d_tns_offsets, size_t tns_blob_bytes, void *d_pcm, uint32_t pcm_format,
+                                int n_frames, void *stream) {
     if (!ctx) return fail(nullptr, AACFB_ERR_ARG, "null context");
     if (n_frames < 0) return fail(ctx, AACFB_ERR_ARG, "negative frame count");
+    if (in_format > AACFB_IN_Q16 || pcm_format > AACFB_PCM_S16) return fail(ctx, AACFB_ERR_ARG, "unknown input / PCM format");
     if (n_frames == 0) return AACFB_OK;
-    if (!d_spectra || !d_info || !d_pcm) return fail(ctx, AACFB_ERR_ARG, "null buffer");
-    if ((reinterpret_cast<uintptr_t>(d_spectra) | reinterpret_cast<uintptr_t>(d_pcm)) & 15)
-        return fail(ctx, AACFB_ERR_ARG, "spectra/pcm must be 16-byte aligned");
+    if (!d_input || !d_info || !d_pcm) return fail(ctx, AACFB_ERR_ARG, "null buffer");
+    if ((reinterpret_cast<uintptr_t>(d_input) | reinterpret_cast<uintptr_t>(d_pcm)) & 15)
+        return fail(ctx, AACFB_ERR_ARG, "input/pcm must be 16-byte aligned");
     DeviceGuard guard(ctx->device);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const uint32_t mode = ctx->flags & AACFB_TNS_MODE_MASK;
+    const size_t n_cf = (size_t)ctx->S * n_frames * ctx->C;
+    auto grow = [&](float *&buf, size_t &cap, size_t bytes_per_cf) -> int {
+        if (n_cf > cap) {
+            CU(ctx, cudaDeviceSynchronize());
+            cudaFree(buf); buf = nullptr; cap = 0;
+            CU(ctx, cudaMalloc(&buf, n_cf * bytes_per_cf));
+            cap = n_cf;
+        }
+        return AACFB_OK;
+    };
+    int rc;
     float *scratch = nullptr;
     if (mode != AACFB_TNS_AS_SHIPPED && d_tns_blob && d_tns_offsets && tns_blob_bytes) {
-        const size_t n_cf = (size_t)ctx->S * n_frames * ctx->C;
-        if (n_cf > ctx->cap_dev_scratch) {
-            CU(ctx, cudaDeviceSynchronize());
-            cudaFree(ctx->d_dev_scratch); ctx->d_dev_scratch = nullptr; ctx->cap_dev_scratch = 0;
-            CU(ctx, cudaMalloc(&ctx->d_dev_scratch, n_cf * 4100));
-            ctx->cap_dev_scratch = n_cf;
-        }
+        if ((rc = grow(ctx->d_dev_scratch, ctx->cap_dev_scratch, 4100)) != AACFB_OK) return rc;
         scratch = ctx->d_dev_scratch;
     }
     uint32_t *ranges = scratch ? reinterpret_cast<uint32_t *>(scratch + ctx->cap_dev_scratch * 1024) : nullptr;
     float *stereo_out = nullptr;
+    bool stereo_pre = false;
     if (d_stereo_ops) {
         if (ctx->C & 1) return fail(ctx, AACFB_ERR_ARG, "stereo tools need an even channel count (pairs are channels 2j, 2j+1)");
         if (reinterpret_cast<uintptr_t>(d_stereo_ops) & 15) return fail(ctx, AACFB_ERR_ARG, "stereo_ops must be 16-byte aligned");
-        if (stereo_needs_prepass(ctx->C, scratch != nullptr)) {
-            const size_t n_cf = (size_t)ctx->S * n_frames * ctx->C;
-            if (n_cf > ctx->cap_dev_stereo_out) {
-                CU(ctx, cudaDeviceSynchronize());
-                cudaFree(ctx->d_dev_stereo_out); ctx->d_dev_stereo_out = nullptr; ctx->cap_dev_stereo_out = 0;
-                CU(ctx, cudaMalloc(&ctx->d_dev_stereo_out, n_cf * 4096));
-                ctx->cap_dev_stereo_out = n_cf;
-            }
+        if ((stereo_pre = stereo_needs_prepass(ctx->C, scratch != nullptr))) {
+            if ((rc = grow(ctx->d_dev_stereo_out, ctx->cap_dev_stereo_out, 4096)) != AACFB_OK) return rc;
             stereo_out = ctx->d_dev_stereo_out;
         }
     }
-    const int rc = enqueue(ctx, d_spectra, d_info, d_stereo_ops, stereo_out, d_tns_blob, d_tns_offsets, tns_blob_bytes, scratch,
-                           ranges, d_pcm, ctx->S, 0, n_frames, ctx->C, 0, 1.0f / 32768.0f, false, st);
-    if (rc != AACFB_OK) return rc;
+    Job j;
+    if (in_format == AACFB_IN_Q16) {
+        j.d_q = static_cast<const aacfb_qframe *>(d_input);
+        if (scratch || stereo_pre) {
+            if ((rc = grow(ctx->d_dev_deq, ctx->cap_dev_deq, 4096)) != AACFB_OK) return rc;
+            j.d_deq = ctx->d_dev_deq;
+        }
+    } else {
+        j.d_spectra = static_cast<const float *>(d_input);
+    }
+    j.d_info = d_info; j.d_stereo = d_stereo_ops; j.d_stereo_out = stereo_out;
+    j.d_blob = d_tns_blob; j.d_offsets = d_tns_offsets; j.blob_bytes = tns_blob_bytes;
+    j.d_scratch = scratch; j.d_ranges = ranges; j.d_pcm = d_pcm; j.s16 = pcm_format == AACFB_PCM_S16;
+    j.S_sub = ctx->S; j.s_base = 0; j.T = n_frames; j.nc = ctx->C; j.c0 = 0;
+    j.scale = j.s16 ? 1.0f : 1.0f / 32768.0f;
+    if ((rc = enqueue(ctx, j, st)) != AACFB_OK) return rc;
     ctx->cur ^= 1;
     return AACFB_OK;
 }
 
 API int aacfb_process(aacfb_ctx *ctx, const float *spectra, const aacfb_frame_info *info, const uint8_t *tns_blob,
                       const uint32_t *tns_offsets, float *pcm, int n_frames) {
-    return aacfb_process_stereo(ctx, spectra, info, nullptr, tns_blob, tns_offsets, pcm, n_frames);
+    return aacfb_process_io(ctx, spectra, AACFB_IN_F32, info, nullptr, tns_blob, tns_offsets, pcm, AACFB_PCM_F32, n_frames);
 }
 
 API int aacfb_process_stereo(aacfb_ctx *ctx, const float *spectra, const aacfb_frame_info *info,
                              const aacfb_stereo_ops *stereo_ops, const uint8_t *tns_blob, const uint32_t *tns_offsets,
                              float *pcm, int n_frames) {
+    return aacfb_process_io(ctx, spectra, AACFB_IN_F32, info, stereo_ops, tns_blob, tns_offsets, pcm, AACFB_PCM_F32, n_frames);
+}
+
+API int aacfb_process_io(aacfb_ctx *ctx, const void *input, uint32_t in_format, const aacfb_frame_info *info,
+                         const aacfb_stereo_ops *stereo_ops, const uint8_t *tns_blob, const uint32_t *tns_offsets,
+                         void *pcm, uint32_t pcm_format, int n_frames) {
     if (!ctx) return fail(nullptr, AACFB_ERR_ARG, "null context");
     if (n_frames < 0) return fail(ctx, AACFB_ERR_ARG, "negative frame count");
+    if (in_format > AACFB_IN_Q16 || pcm_format > AACFB_PCM_S16) return fail(ctx, AACFB_ERR_ARG, "unknown input / PCM format");
     if (n_frames == 0) return AACFB_OK;
-    if (!spectra || !info || !pcm) return fail(ctx, AACFB_ERR_ARG, "null buffer");
+    if (!input || !info || !pcm) return fail(ctx, AACFB_ERR_ARG, "null buffer");
     const int S = ctx->S, C = ctx->C, T = n_frames;
-    const size_t per_stream = (size_t)T * C;
-    int rc = validate(ctx, info, tns_blob, tns_offsets, (size_t)S * per_stream);
-    if (rc != AACFB_OK) return rc;
-    if (stereo_ops && (rc = validate_stereo(ctx, info, stereo_ops, (size_t)S * per_stream, C)) != AACFB_OK) return rc;
+    if (stereo_ops && (C & 1)) return fail(ctx, AACFB_ERR_ARG, "stereo tools need an even channel count (pairs are channels 2j, 2j+1)");
+    const size_t per_stream = (size_t)T * C, n_all = (size_t)S * per_stream;
+    const bool q16 = in_format == AACFB_IN_Q16, s16 = pcm_format == AACFB_PCM_S16;
+    const size_t in_bytes = q16 ? sizeof(aacfb_qframe) : 4096, out_bytes = s16 ? 2048 : 4096;   // per channel-frame
+    const uint8_t *in8 = static_cast<const uint8_t *>(input);
+    uint8_t *out8 = static_cast<uint8_t *>(pcm);
     DeviceGuard guard(ctx->device);
     const uint32_t mode = ctx->flags & AACFB_TNS_MODE_MASK;
-    const bool tns_on = mode != AACFB_TNS_AS_SHIPPED && tns_blob && tns_offsets;
-    size_t blob_bytes = 0;
-    if (tns_on) {
-        blob_bytes = tns_offsets[(size_t)S * per_stream];
-        if (blob_bytes > ctx->cap_blob) {
-            CU(ctx, cudaDeviceSynchronize());
-            cudaFree(ctx->d_blob); ctx->d_blob = nullptr; ctx->cap_blob = 0;
-            CU(ctx, cudaMalloc(&ctx->d_blob, blob_bytes + 16));
-            ctx->cap_blob = blob_bytes;
-        }
-        if (blob_bytes) CU(ctx, cudaMemcpyAsync(ctx->d_blob, tns_blob, blob_bytes, cudaMemcpyHostToDevice, ctx->lane[0].stream));
-        CU(ctx, cudaStreamSynchronize(ctx->lane[0].stream));
-    }
+    const bool tns_on = mode != AACFB_TNS_AS_SHIPPED && tns_blob && tns_offsets && tns_offsets[n_all] > 0;
+    const size_t blob_bytes = (tns_blob && tns_offsets) ? tns_offsets[n_all] : 0;
+    int rc;
     // Sub-batches of whole streams, two in flight: the copy-in of one overlaps
     // the kernel and copy-out of the other (PCIe is the bottleneck end to end).
     // 16 equal sub-batches: measured best on B200 / PCIe 5 (8: +0.5 %, 32: +5 %, 64: +18 % time; a
@@ -519,42 +633,109 @@ API int aacfb_process_stereo(aacfb_ctx *ctx, const float *spectra, const aacfb_f
     int n_sub = std::min(S, 16);
     if (const char *env = std::getenv("AACFB_SUB_BATCHES")) n_sub = std::max(1, std::min(S, std::atoi(env)));   // tuning aids
     if (const char *env = std::getenv("AACFB_LANES")) lanes = std::atoi(env) >= 4 ? 4 : std::atoi(env) >= 2 ? 2 : 1;  // divisors of the counter ring
-    if ((size_t)S * per_stream * 4096 < (size_t)(8u << 20)) n_sub = 1;
+    if (n_all * (in_bytes + out_bytes) < (size_t)(16u << 20)) n_sub = 1;
     for (int i = 0, done = 0; i < n_sub; ++i) {
         const int upto = (int)((long long)S * (i + 1) / n_sub);
         if (upto > done) parts.push_back(upto - done);
         done = upto;
     }
-    const int s_max = *std::max_element(parts.begin(), parts.end());
-    for (int i = 0; i < lanes; ++i) {
-        if ((rc = grow_lane(ctx, ctx->lane[i], (size_t)s_max * per_stream, tns_on && blob_bytes)) != AACFB_OK) return rc;
-        if (stereo_ops && (rc = grow_lane_stereo(ctx, ctx->lane[i], (size_t)s_max * per_stream,
-                                                 stereo_needs_prepass(C, tns_on && blob_bytes))) != AACFB_OK)
-            return rc;
+    // The side info is validated sub-batch by sub-batch, each right before its copies are queued, so
+    // only the first one's check delays the first H2D; the rest overlaps the transfers in flight.
+    // A small call (one sub-batch) is checked as a whole, which also tells whether the generic
+    // kernel instantiation is needed at all.
+    bool any_short = false;
+    auto check = [&](size_t i0, size_t i1) -> int {
+        int r = validate(ctx, info, tns_blob, tns_offsets, blob_bytes, i0, i1, &any_short);
+        if (r == AACFB_OK && stereo_ops) r = validate_stereo(ctx, info, stereo_ops, i0, i1);
+        if (r == AACFB_OK && q16) r = validate_q(ctx, info, static_cast<const aacfb_qframe *>(input), i0, i1);
+        return r;
+    };
+    const bool whole_check = parts.size() == 1;
+    if (whole_check && (rc = check(0, n_all)) != AACFB_OK) return rc;
+    // From here on work is queued on the lanes: an error must drain them before returning (the
+    // caller's buffers are referenced by copies in flight) and leaves ctx->cur -- the overlap state
+    // the next call starts from -- untouched.
+    auto drain = [&](int code) {
+        for (int i = 0; i < kLanes; ++i) cudaStreamSynchronize(ctx->lane[i].stream);
+        return code;
+    };
+    if (tns_on) {
+        if (blob_bytes > ctx->cap_blob) {
+            CU(ctx, cudaDeviceSynchronize());
+            cudaFree(ctx->d_blob); ctx->d_blob = nullptr; ctx->cap_blob = 0;
+            CU(ctx, cudaMalloc(&ctx->d_blob, blob_bytes + 16));
+            ctx->cap_blob = blob_bytes;
+        }
+        CU(ctx, cudaMemcpyAsync(ctx->d_blob, tns_blob, blob_bytes, cudaMemcpyHostToDevice, ctx->lane[0].stream));
+        CU(ctx, cudaStreamSynchronize(ctx->lane[0].stream));
     }
+    const int s_max = *std::max_element(parts.begin(), parts.end());
+    const bool stereo_pre = stereo_ops && stereo_needs_prepass(C, tns_on);
+    for (int i = 0; i < lanes; ++i) {
+        if ((rc = grow_lane(ctx, ctx->lane[i], (size_t)s_max * per_stream, tns_on, q16 && (tns_on || stereo_pre))) != AACFB_OK) return rc;
+        if (stereo_ops && (rc = grow_lane_stereo(ctx, ctx->lane[i], (size_t)s_max * per_stream, stereo_pre)) != AACFB_OK) return rc;
+    }
+#define CUD(call)                                                                                                    \
+    do {                                                                                                             \
+        cudaError_t e__ = (call);                                                                                    \
+        if (e__ != cudaSuccess)                                                                                      \
+            return drain(fail(ctx, AACFB_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__)); \
+    } while (0)
     int li = 0, s0 = 0;
     for (size_t pi = 0; pi < parts.size(); s0 += parts[pi], ++pi, li = (li + 1) % lanes) {
         Lane &ln = ctx->lane[li];
         const int sn = parts[pi];
         const size_t n_cf = (size_t)sn * per_stream, off = (size_t)s0 * per_stream;
+        if (!whole_check && (rc = check(off, off + n_cf)) != AACFB_OK) return drain(rc);
         // stream order makes reuse of this lane's buffers safe
-        CU(ctx, cudaMemcpyAsync(ln.d_spectra, spectra + off * 1024, n_cf * 4096, cudaMemcpyHostToDevice, ln.stream));
-        CU(ctx, cudaMemcpyAsync(ln.d_info, info + off, n_cf * sizeof(aacfb_frame_info), cudaMemcpyHostToDevice, ln.stream));
-        if (tns_on && blob_bytes)
-            CU(ctx, cudaMemcpyAsync(ln.d_offsets, tns_offsets + off, (n_cf + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, ln.stream));
+        CUD(cudaMemcpyAsync(ln.d_spectra, in8 + off * in_bytes, n_cf * in_bytes, cudaMemcpyHostToDevice, ln.stream));
+        CUD(cudaMemcpyAsync(ln.d_info, info + off, n_cf * sizeof(aacfb_frame_info), cudaMemcpyHostToDevice, ln.stream));
+        if (tns_on)
+            CUD(cudaMemcpyAsync(ln.d_offsets, tns_offsets + off, (n_cf + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, ln.stream));
         if (stereo_ops)
-            CU(ctx, cudaMemcpyAsync(ln.d_stereo, stereo_ops + off / 2, (n_cf / 2) * sizeof(aacfb_stereo_ops),
-                                    cudaMemcpyHostToDevice, ln.stream));
-        rc = enqueue(ctx, ln.d_spectra, ln.d_info, stereo_ops ? ln.d_stereo : nullptr, ln.d_stereo_out,
-                     (tns_on && blob_bytes) ? ctx->d_blob : nullptr, ln.d_offsets, blob_bytes,
-                     ln.d_scratch, ln.d_scratch ? ln.ranges() : nullptr, ln.d_pcm, sn, s0, T, C, 0, 1.0f / 32768.0f, false,
-                     ln.stream);
-        if (rc != AACFB_OK) return rc;
-        CU(ctx, cudaMemcpyAsync(pcm + off * 1024, ln.d_pcm, n_cf * 4096, cudaMemcpyDeviceToHost, ln.stream));
+            CUD(cudaMemcpyAsync(ln.d_stereo, stereo_ops + off / 2, (n_cf / 2) * sizeof(aacfb_stereo_ops),
+                                cudaMemcpyHostToDevice, ln.stream));
+        Job j;
+        if (q16) { j.d_q = reinterpret_cast<const aacfb_qframe *>(ln.d_spectra); j.d_deq = ln.d_deq; }
+        else j.d_spectra = ln.d_spectra;
+        j.d_info = ln.d_info; j.d_stereo = stereo_ops ? ln.d_stereo : nullptr; j.d_stereo_out = ln.d_stereo_out;
+        j.d_blob = tns_on ? ctx->d_blob : nullptr; j.d_offsets = ln.d_offsets; j.blob_bytes = tns_on ? blob_bytes : 0;
+        j.d_scratch = ln.d_scratch; j.d_ranges = ln.d_scratch ? ln.ranges() : nullptr;
+        j.d_pcm = ln.d_pcm; j.s16 = s16;
+        j.S_sub = sn; j.s_base = s0; j.T = T; j.nc = C; j.c0 = 0;
+        j.scale = s16 ? 1.0f : 1.0f / 32768.0f;
+        j.no_short = whole_check && !any_short;
+        if ((rc = enqueue(ctx, j, ln.stream)) != AACFB_OK) return drain(rc);
+        CUD(cudaMemcpyAsync(out8 + off * out_bytes, ln.d_pcm, n_cf * out_bytes, cudaMemcpyDeviceToHost, ln.stream));
     }
+#undef CUD
     for (int i = 0; i < kLanes; ++i) CU(ctx, cudaStreamSynchronize(ctx->lane[i].stream));
     ctx->cur ^= 1;
     return AACFB_OK;
+}
+
+// ---- page-locked host memory for the caller's staging buffers (include/aacfb.h) -------------------
+API void *aacfb_host_alloc(size_t bytes) {
+    void *p = nullptr;
+    if (bytes == 0) return nullptr;
+    const cudaError_t e = cudaHostAlloc(&p, bytes, cudaHostAllocPortable);
+    if (e != cudaSuccess) { fail(nullptr, AACFB_ERR_CUDA, "cudaHostAlloc(%zu): %s", bytes, cudaGetErrorString(e)); return nullptr; }
+    return p;
+}
+API int aacfb_host_free(void *p) {
+    if (!p) return AACFB_OK;
+    const cudaError_t e = cudaFreeHost(p);
+    return e == cudaSuccess ? AACFB_OK : fail(nullptr, AACFB_ERR_CUDA, "cudaFreeHost: %s", cudaGetErrorString(e));
+}
+API int aacfb_host_register(void *p, size_t bytes) {
+    if (!p || !bytes) return fail(nullptr, AACFB_ERR_ARG, "null buffer");
+    const cudaError_t e = cudaHostRegister(p, bytes, cudaHostRegisterPortable);
+    return e == cudaSuccess ? AACFB_OK : fail(nullptr, AACFB_ERR_CUDA, "cudaHostRegister: %s", cudaGetErrorString(e));
+}
+API int aacfb_host_unregister(void *p) {
+    if (!p) return AACFB_OK;
+    const cudaError_t e = cudaHostUnregister(p);
+    return e == cudaSuccess ? AACFB_OK : fail(nullptr, AACFB_ERR_CUDA, "cudaHostUnregister: %s", cudaGetErrorString(e));
 }
 
 API int aacfb_filterbank_process(aacfb_ctx *ctx, int stream, int channel, const aacfb_frame_info *info,
@@ -574,8 +755,13 @@ API int aacfb_filterbank_process(aacfb_ctx *ctx, int stream, int channel, const 
     fi.tns_present = 0;  // the inner seam is the filterbank alone
     CU(ctx, cudaMemcpyAsync(ln.d_spectra, input, 4096, cudaMemcpyHostToDevice, ln.stream));
     CU(ctx, cudaMemcpyAsync(ln.d_info, &fi, sizeof fi, cudaMemcpyHostToDevice, ln.stream));
-    rc = enqueue(ctx, ln.d_spectra, ln.d_info, nullptr, nullptr, nullptr, nullptr, 0, nullptr, nullptr, ln.d_pcm, 1, stream, 1,
-                 1, channel, 1.0f, true, ln.stream);
+    {
+        Job j;
+        j.d_spectra = ln.d_spectra; j.d_info = ln.d_info; j.d_pcm = ln.d_pcm;
+        j.S_sub = 1; j.s_base = stream; j.T = 1; j.nc = 1; j.c0 = channel; j.scale = 1.0f; j.in_place_state = true;
+        j.no_short = fi.window_sequence != AACFB_EIGHT_SHORT_SEQUENCE;
+        rc = enqueue(ctx, j, ln.stream);
+    }
     if (rc != AACFB_OK) return rc;
     CU(ctx, cudaMemcpyAsync(output, ln.d_pcm, 4096, cudaMemcpyDeviceToHost, ln.stream));
     CU(ctx, cudaStreamSynchronize(ln.stream));
@@ -591,7 +777,7 @@ API int aacfb_tns_process(aacfb_ctx *ctx, const aacfb_frame_info *info, const ui
     aacfb_frame_info fi = *info;
     fi.tns_present = 1;
     const uint32_t offs[2] = {0, (uint32_t)block_bytes};
-    int rc = validate(ctx, &fi, tns_block, offs, 1);
+    int rc = validate(ctx, &fi, tns_block, offs, block_bytes, 0, 1, nullptr);
     if (rc != AACFB_OK) return rc;
     DeviceGuard guard(ctx->device);
     Lane &ln = ctx->lane[0];

@@ -365,9 +365,24 @@ struct OutDst {
     bool interleaved;   // chains are channels 0, 1 of one stereo stream: pcm[n][2]
     float scale;        // 2^-15 (decoder.js:210) or 1 for the inner seam; a power of two
     float inv_scale;    // 1 / scale
-    float *out0, *out1; // sample 0 of this frame for each chain
+    float *out0, *out1; // sample 0 of this frame for each chain (int16_t * behind the cast when s16)
     int ostride;        // distance between successive samples of one chain
+    bool s16;           // AACFB_PCM_S16: samples leave as int16 (scale is 1 then); constant false in the
+                        // float-only instantiations, where everything behind it folds away
 };
+
+// Float sample (un-normalised, decoder.js:210 before the division) -> int16 the way a JS sink does it:
+// Int16Array[i] = max(-32768, min(32767, Math.round(x))): round half UP, saturate, NaN -> 0
+// (include/aacfb.h, AACFB_PCM_S16).  rintf rounds half to even; the only inputs where that differs
+// from Math.round are the ties it rounded down, x - rint(x) == +0.5 exactly (the difference is exact).
+AACFB_HD int pcm_s16(float x) {
+    if (!(x == x)) return 0;
+    float r = rintf(x);
+    if (f_sub(x, r) == 0.5f) r = f_add(r, 1.0f);
+    r = r < -32768.0f ? -32768.0f : r;
+    r = r > 32767.0f ? 32767.0f : r;
+    return (int)r;
+}
 
 // Effective windows of a long-transform frame as (value at m, value at 1023-m):
 //   first half : ONLY_LONG/LONG_START -> long window of shape_prev (filter_bank.js:109-111,124-126)
@@ -409,6 +424,33 @@ AACFB_HD void emit_pair(int u, Sync &sync, int qq, const float (*a)[2], const fl
         r_hi[c] = sync.partner(u, b[0][c]);  // partner's 1023-m' of q' = qq    == my m(7-qq) + 1
     }
     const int m_lo = long_pos_of_bin(64 * qq + u), m_hi = long_pos_of_bin(64 * (7 - qq) + u);
+    if (d.s16) {   // same runs as below, 2 bytes per sample
+        if (NCH == 2 && d.interleaved) {
+            int16_t *o = reinterpret_cast<int16_t *>(d.out0);
+            uint2 v;
+            v.x = (uint32_t)(pcm_s16(a[0][0]) & 0xffff) | ((uint32_t)pcm_s16(a[0][1]) << 16);
+            v.y = (uint32_t)(pcm_s16(r_lo[0]) & 0xffff) | ((uint32_t)pcm_s16(r_lo[1]) << 16);
+            *reinterpret_cast<uint2 *>(o + 2 * m_lo) = v;
+            v.x = (uint32_t)(pcm_s16(a[1][0]) & 0xffff) | ((uint32_t)pcm_s16(a[1][1]) << 16);
+            v.y = (uint32_t)(pcm_s16(r_hi[0]) & 0xffff) | ((uint32_t)pcm_s16(r_hi[1]) << 16);
+            *reinterpret_cast<uint2 *>(o + 2 * m_hi) = v;
+        } else {
+#pragma unroll
+            for (int c = C0; c < C0 + NCH; ++c) {
+                int16_t *o = reinterpret_cast<int16_t *>(c == 0 ? d.out0 : d.out1);
+                if (d.ostride == 1) {
+                    *reinterpret_cast<uint32_t *>(o + m_lo) = (uint32_t)(pcm_s16(a[0][c]) & 0xffff) | ((uint32_t)pcm_s16(r_lo[c]) << 16);
+                    *reinterpret_cast<uint32_t *>(o + m_hi) = (uint32_t)(pcm_s16(a[1][c]) & 0xffff) | ((uint32_t)pcm_s16(r_hi[c]) << 16);
+                } else {
+                    o[(size_t)m_lo * d.ostride] = (int16_t)pcm_s16(a[0][c]);
+                    o[(size_t)(m_lo + 1) * d.ostride] = (int16_t)pcm_s16(r_lo[c]);
+                    o[(size_t)m_hi * d.ostride] = (int16_t)pcm_s16(a[1][c]);
+                    o[(size_t)(m_hi + 1) * d.ostride] = (int16_t)pcm_s16(r_hi[c]);
+                }
+            }
+        }
+        return;
+    }
     if (NCH == 2 && d.interleaved) {
         float4 v;
         v.x = a[0][0]; v.y = a[0][1]; v.z = r_lo[0]; v.w = r_lo[1];
@@ -741,6 +783,220 @@ AACFB_HD void ovl_store(int u, const Ovl &ov, float *state, float inv_scale) {
         state[m] = f_mul(ov.a[C][q], inv_scale);
         state[1023 - m] = f_mul(ov.b[C][q], inv_scale);
     }
+}
+
+// ------------------------------------------------------ inverse quantisation
+// ICStream.decodeSpectralData's arithmetic (ics.js:203-266) on a staged aacfb_qframe record
+// (include/aacfb.h): rec = group_len[8] | band[120] u16 | reserved[8] | q[1024] i16.
+#if defined(__CUDA_ARCH__)
+template <class T> AACFB_HD T dq_ld(const T *p) { return __ldg(p); }
+#else
+template <class T> AACFB_HD T dq_ld(const T *p) { return *p; }
+#endif
+
+// Perceptual noise substitution AS SHIPPED (ics.js:228-242) for the 4 coefficients 4 c4 .. 4 c4 + 3 of
+// band (g, sfb), window wg of the group.  The generator restarts at 0x1F2E3D4C in every new ICStream
+// (one per element per frame) and its output is a fixed sequence (DequantTables::noise) that is 0
+// from index noise_len = 11 on; what a coefficient gets depends only on how many noise
+// coefficients the reference generated before it, in its (group, band, window, k) order.
+AACFB_HD_NOINLINE void dequant_noise4(const DequantTables *D, const uint8_t *rec, bool is_short, int max_sfb, int g, int wg,
+                             int sfb, int c4, uint32_t code, float *out) {
+    const uint16_t *band = reinterpret_cast<const uint16_t *>(rec + 8);
+    const uint16_t *swb = is_short ? D->swb_short : D->swb_long;
+    const int noise_len = dq_ld(&D->noise_len);
+    int count = 0;
+    bool done = false;
+    for (int gg = 0; gg <= g && !done; ++gg) {
+        const int len = rec[gg];
+        for (int b = 0; b < max_sfb; ++b) {
+            if (gg == g && b == sfb) { done = true; break; }
+            if ((band[gg * max_sfb + b] & AACFB_BAND_KIND_MASK) == AACFB_BAND_NOISE) {
+                count += ((int)dq_ld(swb + b + 1) - (int)dq_ld(swb + b)) * len;
+                if (count >= noise_len) { done = true; break; }   // everything from here on is 0 * (sf / sqrt(0))
+            }
+        }
+    }
+    const int lo = dq_ld(swb + sfb), width = (int)dq_ld(swb + sfb + 1) - lo;
+    const int n0 = count + wg * width;                       // generator outputs consumed before this band-window
+    double energy = 0.0;                                      // ics.js:231-237 (zeros add nothing)
+    for (int k = 0; k < width && n0 + k < noise_len; ++k) {
+        const double v = (double)dq_ld(&D->noise[n0 + k]);
+        energy += v * v;
+    }
+    const double sfv = -(double)dq_ld(&D->sf[code & AACFB_BAND_INDEX_MASK]);   // scaleFactors[idx] = -SCALEFACTOR_TABLE[..], ics.js:158
+    const double scale = sfv / sqrt(energy);                  // ics.js:239: -Infinity once the generator is stuck at 0
+    const int k0 = ((4 * c4) & (is_short ? 127 : 1023)) - lo;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int i = n0 + k0 + j;
+        const double v = i < noise_len ? (double)dq_ld(&D->noise[i]) : 0.0;
+        out[j] = (float)(v * scale);                          // ics.js:240-241 (0 * -Infinity = NaN)
+    }
+}
+
+// The 4 coefficients of group c4 (scalefactor-band edges are multiples of 4, tables.js:34-124).
+AACFB_HD_NOINLINE void dequant4(const DequantTables *D, const uint8_t *rec, FrameBits fi, int c4, const int16_t *q4, float *out) {
+    const bool is_short = fb_seq(fi) == AACFB_EIGHT_SHORT_SEQUENCE;
+    const int max_sfb = (int)(fi >> 24);
+    int sfb, g = 0, wg = 0;
+    bool valid = true;
+    if (is_short) {   // window w of the frame belongs to group g: groupOff += groupLen << 7, ics.js:259
+        const int w = c4 >> 5;
+        sfb = dq_ld(&D->sfb_short[c4 & 31]);
+        int acc = 0;
+        valid = false;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int len = rec[k];
+            if (!valid && len != 0 && w >= acc && w < acc + len) { g = k; wg = w - acc; valid = true; }
+            acc += len;
+        }
+    } else {
+        sfb = dq_ld(&D->sfb_long[c4]);
+    }
+    const int idx = g * max_sfb + sfb;
+    uint32_t code = AACFB_BAND_ZERO;
+    if (valid && sfb < max_sfb && idx < 120) code = reinterpret_cast<const uint16_t *>(rec + 8)[idx];
+    const uint32_t kind = code & AACFB_BAND_KIND_MASK;
+    if (kind == AACFB_BAND_SPECTRAL) {          // ics.js:243-256
+        const float s = dq_ld(&D->sf[code & AACFB_BAND_INDEX_MASK]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int v = q4[j];
+            int a = v < 0 ? -v : v;
+            a = a > 8191 ? 8191 : a;              // outside IQ_TABLE: `undefined` -> NaN
+            const float t = dq_ld(&D->iq[a]);
+            out[j] = f_mul(v > 0 ? t : -t, s);    // (buf[j] > 0) ? IQ[buf[j]] : -IQ[-buf[j]]  (q = 0 gives -0)
+        }
+    } else if (kind == AACFB_BAND_NOISE) {
+        dequant_noise4(D, rec, is_short, max_sfb, g, wg, sfb, c4, code, out);
+    } else {                                    // ZERO_BT / intensity (ics.js:222-227) and everything above maxSFB
+        out[0] = out[1] = out[2] = out[3] = 0.f;
+    }
+}
+
+// One whole record -> 1024 floats (the pre-pass kernel and the tests).
+AACFB_HD void dequant_row(const DequantTables *D, const uint8_t *rec, FrameBits fi, float *out) {
+    const int16_t *q = reinterpret_cast<const int16_t *>(rec + 256);
+    for (int c4 = 0; c4 < 256; ++c4) dequant4(D, rec, fi, c4, q + 4 * c4, out + 4 * c4);
+}
+
+// Worker phase: the aacfb_qframe records of the frame's rows have landed at byte kQLandOffset of each
+// 4 KiB row slot; turn them into float rows in place.  Thread u owns groups u + 64 j: the 8-byte reads
+// of q and the 16-byte writes of the result are conflict-free.  All reads happen before the first
+// barrier (the floats overwrite the record), the second one publishes the rows.
+//
+// The lookups are arranged for throughput: which scalefactor band a thread's four groups fall into
+// depends on the sample rate alone, so it is read once per kernel (DqCtx::sfb_long4 / sfb_short1); the
+// scalefactor table and IQ_TABLE[0..1023] sit in shared memory (gathers through the L1 thrashed: it is
+// all but carved out by the staging buffers); band kinds are resolved by selects, not branches, so the
+// 4 + 16 independent table reads of a row are in flight together.  |q| >= 1024 and noise bands (rare)
+// take the general path through global memory.
+constexpr int kQFrameBytes = 2304;
+constexpr int kQLandOffset = 4096 - kQFrameBytes;
+constexpr int kDqIqLo = 1024;                 // entries of IQ_TABLE kept next to the rows
+struct DqCtx {
+    const DequantTables *D;                   // global memory: |q| >= kDqIqLo, PNS, band edges
+    const float *iq_lo;                       // IQ_TABLE[0 .. kDqIqLo - 1]
+    const float *sf;                          // SCALEFACTOR_TABLE padded to 512 entries (NaN from 428 on)
+    uint32_t sfb_long4;                       // sfb_long[u + 64 j] in byte j
+    uint32_t sfb_short1;                      // sfb_short[u & 31]
+};
+AACFB_HD void dq_thread_consts(const DequantTables *D, int u, DqCtx &dq) {
+    dq.sfb_long4 = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) dq.sfb_long4 |= (uint32_t)dq_ld(&D->sfb_long[u + 64 * j]) << (8 * j);
+    dq.sfb_short1 = dq_ld(&D->sfb_short[u & 31]);
+}
+
+template <class Sync>
+AACFB_HD void dequant_stage(int u, Sync &sync, float *stage, int nch, const FrameBits *fi, const DqCtx &dq) {
+    float v[2][16];
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+        if (c < nch) {
+            const uint8_t *rec = reinterpret_cast<const uint8_t *>(stage + c * kRowFloats) + kQLandOffset;
+            const uint16_t *band = reinterpret_cast<const uint16_t *>(rec + 8);
+            const bool is_short = fb_seq(fi[c]) == AACFB_EIGHT_SHORT_SEQUENCE;
+            const int max_sfb = (int)(fi[c] >> 24);
+            uint32_t code[4];
+            if (!is_short) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int sfb = (int)((dq.sfb_long4 >> (8 * j)) & 0xffu);
+                    code[j] = sfb < max_sfb ? (uint32_t)band[sfb < 119 ? sfb : 119] : (uint32_t)AACFB_BAND_ZERO;
+                }
+            } else {   // group j's window is 2 j + (u >> 5); its window group from the cumulative group lengths
+                const uint2 gl = *reinterpret_cast<const uint2 *>(rec);
+                const int sfb = (int)dq.sfb_short1;
+                int gidx[4] = {-1, -1, -1, -1};
+                int acc = 0;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const int len = (int)(((k < 4 ? gl.x : gl.y) >> (8 * (k & 3))) & 0xffu);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int w = 2 * j + (u >> 5);
+                        if (gidx[j] < 0 && w < acc + len) gidx[j] = k;   // len == 0 never matches: w >= acc
+                    }
+                    acc += len;
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int idx = gidx[j] * max_sfb + sfb;
+                    const bool ok = gidx[j] >= 0 && sfb < max_sfb && idx < 120;
+                    code[j] = ok ? (uint32_t)band[ok ? idx : 0] : (uint32_t)AACFB_BAND_ZERO;
+                }
+            }
+            float s[4];
+            uint2 raw[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                s[j] = dq.sf[code[j] & AACFB_BAND_INDEX_MASK];
+                raw[j] = *reinterpret_cast<const uint2 *>(rec + 256 + 8 * (u + 64 * j));
+            }
+            bool any_noise = false;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const bool spectral = (code[j] & AACFB_BAND_KIND_MASK) == AACFB_BAND_SPECTRAL;
+                any_noise |= (code[j] & AACFB_BAND_KIND_MASK) == AACFB_BAND_NOISE;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const uint32_t word = k < 2 ? raw[j].x : raw[j].y;
+                    const int q = (int)(int16_t)((k & 1) ? (word >> 16) : (word & 0xffffu));
+                    int a = q < 0 ? -q : q;
+                    float t = dq.iq_lo[a & (kDqIqLo - 1)];
+                    if (a >= kDqIqLo) t = dq_ld(&dq.D->iq[a > 8191 ? 8191 : a]);   // outside IQ_TABLE: `undefined` -> NaN
+                    const float val = f_mul(q > 0 ? t : -t, s[j]);                  // ics.js:250-253 (q = 0 gives -0)
+                    v[c][4 * j + k] = spectral ? val : 0.f;                         // ics.js:222-227: zero bands are +0
+                }
+            }
+            if (any_noise) {   // perceptual noise substitution: the general (slow) path for those groups
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if ((code[j] & AACFB_BAND_KIND_MASK) != AACFB_BAND_NOISE) continue;
+                    int16_t q4[4] = {0, 0, 0, 0};
+                    float tmp[4];               // (not &v[..]: that would push the whole array into local memory)
+                    dequant4(dq.D, rec, fi[c], u + 64 * j, q4, tmp);
+                    v[c][4 * j] = tmp[0]; v[c][4 * j + 1] = tmp[1]; v[c][4 * j + 2] = tmp[2]; v[c][4 * j + 3] = tmp[3];
+                }
+            }
+        }
+    }
+    sync.barrier();
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+        if (c < nch) {
+            float4 *row = reinterpret_cast<float4 *>(stage + c * kRowFloats);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float4 t;
+                t.x = v[c][4 * j]; t.y = v[c][4 * j + 1]; t.z = v[c][4 * j + 2]; t.w = v[c][4 * j + 3];
+                row[u + 64 * j] = t;
+            }
+        }
+    }
+    sync.barrier();
 }
 
 // ------------------------------------------------------------ stereo tools

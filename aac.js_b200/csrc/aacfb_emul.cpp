@@ -43,12 +43,20 @@ struct HostSync {
 };
 }  // namespace
 
-extern "C" __attribute__((visibility("default"))) int aacfb_emul_process(
-    const float *spectra, const aacfb_frame_info *info, const uint8_t *tns_blob, const uint32_t *tns_offsets,
-    float *overlap /*[S][C][1024] in/out*/, float *pcm, int S, int T, int C, int sample_index, uint32_t flags,
-    int chunk_len) {
+// input: float spectra (AACFB_IN_F32) or aacfb_qframe records (AACFB_IN_Q16); pcm: float or int16.
+extern "C" __attribute__((visibility("default"))) int aacfb_emul_process_io(
+    const void *input, uint32_t in_format, const aacfb_frame_info *info, const uint8_t *tns_blob, const uint32_t *tns_offsets,
+    float *overlap /*[S][C][1024] in/out*/, void *pcm_out, uint32_t pcm_format, int S, int T, int C, int sample_index,
+    uint32_t flags, int chunk_len) {
     const HostTables &H = host_tables();
-    const float kScale = 1.0f / 32768.0f;
+    const bool s16 = pcm_format == AACFB_PCM_S16;
+    const float kScale = s16 ? 1.0f : 1.0f / 32768.0f;   // int16 PCM: unit-scale windows, like the library
+    float *pcm = static_cast<float *>(pcm_out);
+    static DequantTables dq_tab;
+    build_dequant_tables(sample_index, dq_tab);
+    const uint8_t *qframes = in_format == AACFB_IN_Q16 ? static_cast<const uint8_t *>(input) : nullptr;
+    const float *spectra = qframes ? nullptr : static_cast<const float *>(input);
+    std::vector<float> deq;
     // the kernel's tables: every window carries the output scale (scale_windows)
     static SynthTables scaled;
     scaled = H.synth;
@@ -60,6 +68,13 @@ extern "C" __attribute__((visibility("default"))) int aacfb_emul_process(
     // TNS pre-pass (the kernel's tns_kernel): filtered copies of the rows that carry TNS
     std::vector<float> scratch;
     const bool tns_on = mode != AACFB_TNS_AS_SHIPPED && tns_blob && tns_offsets;
+    if (tns_on && qframes) {   // the library's dequant_kernel pre-pass: TNS needs float rows
+        deq.resize((size_t)S * T * C * 1024);
+        for (size_t cf = 0; cf < (size_t)S * T * C; ++cf)
+            dequant_row(&dq_tab, qframes + cf * kQFrameBytes, fb_pack(info[cf]), deq.data() + cf * 1024);
+        spectra = deq.data();
+        qframes = nullptr;
+    }
     if (tns_on) {
         scratch.assign(spectra, spectra + (size_t)S * T * C * 1024);
         for (size_t cf = 0; cf < (size_t)S * T * C; ++cf) {
@@ -107,24 +122,33 @@ extern "C" __attribute__((visibility("default"))) int aacfb_emul_process(
                 }
                 // "TMA": thread 0 fills the stage, everyone waits
                 if (u == 0)
-                    for (int c = 0; c < pr.nch; ++c)
-                        std::memcpy(stage + 1024 * c, rows + cf_index(g, pr.s[c], t, pr.j[c]) * 1024, 4096);
+                    for (int c = 0; c < pr.nch; ++c) {
+                        const size_t cf = cf_index(g, pr.s[c], t, pr.j[c]);
+                        if (qframes) std::memcpy(reinterpret_cast<uint8_t *>(stage + 1024 * c) + kQLandOffset, qframes + cf * kQFrameBytes, kQFrameBytes);
+                        else std::memcpy(stage + 1024 * c, rows + cf * 1024, 4096);
+                    }
                 bar.arrive_and_wait();
                 FrameIO io;
                 io.stage = stage;
                 io.scratch = scratch2[f & 1];
                 io.nch = pr.nch;
                 io.ops = nullptr;  // the stereo tools are exercised on the device only
+                DqCtx dqc;
+                dqc.D = &dq_tab; dqc.iq_lo = dq_tab.iq; dqc.sf = dq_tab.sf;
+                dq_thread_consts(&dq_tab, u, dqc);
+                io.dq = qframes ? &dqc : nullptr;
+                io.dst.s16 = s16;
                 io.dst.emit = fb + f >= f0;
                 io.dst.interleaved = pr.interleaved;
                 io.dst.scale = kScale;
                 io.dst.inv_scale = 1.0f / kScale;
                 io.dst.ostride = g.nc;
                 for (int c = 0; c < 2; ++c) io.fi[c] = fb_pack(info[cf_index(g, pr.s[c], t, pr.j[c])]);
-                io.dst.out0 = pcm + ((size_t)pr.s[0] * g.T + t) * 1024 * g.nc + pr.j[0];
-                io.dst.out1 = pcm + ((size_t)pr.s[1] * g.T + t) * 1024 * g.nc + pr.j[1];
-                if (item_has_short) worker_frame<true, false>(u, sync, io, tab, tab, z, ov);
-                else worker_frame<false, false>(u, sync, io, tab, tab, z, ov);
+                const size_t oa = ((size_t)pr.s[0] * g.T + t) * 1024 * g.nc + pr.j[0], ob = ((size_t)pr.s[1] * g.T + t) * 1024 * g.nc + pr.j[1];
+                io.dst.out0 = s16 ? reinterpret_cast<float *>(static_cast<int16_t *>(pcm_out) + oa) : pcm + oa;
+                io.dst.out1 = s16 ? reinterpret_cast<float *>(static_cast<int16_t *>(pcm_out) + ob) : pcm + ob;
+                if (item_has_short) worker_frame<true, false, true>(u, sync, io, tab, tab, z, ov);
+                else worker_frame<false, false, true>(u, sync, io, tab, tab, z, ov);
                 if (t == g.T - 1) {
                     // NOTE: in place -- safe here because items run one after the other, in order
                     ovl_store<0>(u, ov, overlap + state_index(g, pr.s[0], pr.j[0]), 1.0f / kScale);
@@ -137,6 +161,25 @@ extern "C" __attribute__((visibility("default"))) int aacfb_emul_process(
         for (auto &t : th) t.join();
     }
     return 0;
+}
+
+extern "C" __attribute__((visibility("default"))) int aacfb_emul_process(
+    const float *spectra, const aacfb_frame_info *info, const uint8_t *tns_blob, const uint32_t *tns_offsets,
+    float *overlap, float *pcm, int S, int T, int C, int sample_index, uint32_t flags, int chunk_len) {
+    return aacfb_emul_process_io(spectra, AACFB_IN_F32, info, tns_blob, tns_offsets, overlap, pcm, AACFB_PCM_F32, S, T, C,
+                                 sample_index, flags, chunk_len);
+}
+
+// dequant_row / pcm_s16 alone (unit tests of the phase code against the oracle)
+extern "C" __attribute__((visibility("default"))) void aacfb_emul_dequant(const uint8_t *qframe, const aacfb_frame_info *info,
+                                                                         int sample_index, float *out) {
+    DequantTables *D = new DequantTables;
+    build_dequant_tables(sample_index, *D);
+    dequant_row(D, qframe, fb_pack(*info), out);
+    delete D;
+}
+extern "C" __attribute__((visibility("default"))) void aacfb_emul_pcm_s16(const float *x, int16_t *out, int n) {
+    for (int i = 0; i < n; ++i) out[i] = (int16_t)pcm_s16(x[i]);
 }
 
 extern "C" __attribute__((visibility("default"))) int aacfb_emul_table(int which, float *dst, int cap) {

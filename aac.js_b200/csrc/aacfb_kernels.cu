@@ -32,7 +32,7 @@ constexpr int kTabBytes = (kSmemTableBytes + 127) & ~127;
 // Shared-memory layout of a CTA with W workers and a TMA ring of ST stages per worker.
 // STEREO: the instantiation that also applies the stereo tools (wider side-info ring entries,
 // one aacfb_stereo_ops record per stage); the plain one is byte for byte what it was without them.
-template <int W, int ST, bool STEREO = false>
+template <int W, int ST, bool STEREO = false, bool IOV = false>
 struct Layout {
     static constexpr int kBufsPerWorker = ST + 2;  // TMA ring + two alternating scratch buffers
     static constexpr int kOffStages = kTabBytes;
@@ -42,7 +42,11 @@ struct Layout {
     static constexpr int kPendInts = 12;                // the refill the leader has prepared (see DevSync)
     static constexpr int kSlotInts = 8 + kPendInts + 2 * kRingWords * ST;   // per worker: item, flag, cursor[6], pending refill, side-info ring [2 ST]
     static constexpr int kOffOps = (kOffSlots + W * kSlotInts * 4 + 15) & ~15;   // aacfb_stereo_ops per worker and stage
-    static constexpr int kTotal = STEREO ? kOffOps + W * ST * (int)sizeof(aacfb_stereo_ops) : kOffSlots + W * kSlotInts * 4;
+    static constexpr int kEndOps = STEREO ? kOffOps + W * ST * (int)sizeof(aacfb_stereo_ops) : kOffSlots + W * kSlotInts * 4;
+    // IOV: SCALEFACTOR_TABLE (512 entries, NaN tail) and IQ_TABLE[0 .. kDqIqLo) for dequant_stage
+    static constexpr int kOffDq = (kEndOps + 15) & ~15;
+    static constexpr int kDqBytes = (512 + kDqIqLo) * 4;
+    static constexpr int kTotal = IOV ? kOffDq + kDqBytes : kEndOps;
     static_assert(kTotal <= 227 * 1024, "shared memory budget");
     static_assert(2 * W + 1 <= 16, "named barriers");
 };
@@ -77,7 +81,7 @@ __device__ __forceinline__ void bulk_load(uint32_t dst, const void *src, uint32_
 // PARK: keep the prepared refill in shared memory instead of registers.  Costs the leader's warp
 // a few dozen instructions per frame (measured -4 % on the long-only instantiations) but frees
 // ~8 registers per thread, which is what keeps the generic instantiations from spilling.
-template <bool STEREO, bool PARK>
+template <bool STEREO, bool PARK, bool IOV>
 struct DevSync {
     uint32_t bar_id;      // named barrier of this worker (all 64 threads block)
     uint32_t free_id;     // named barrier "stage is free": followers arrive, the leader's warp waits
@@ -95,11 +99,16 @@ struct DevSync {
     __device__ __forceinline__ void put(int i, uint32_t v) { if (PARK) pend[i] = v; else reg[i] = v; }
     __device__ __forceinline__ uint32_t get(int i) const { return PARK ? pend[i] : reg[i]; }
     const float *spectra, *scratch;
+    const uint8_t *qframes;           // IOV: aacfb_qframe records instead of float rows (nullptr: float rows)
     const aacfb_stereo_ops *stereo;   // global records (nullptr: none)
     __device__ __forceinline__ void barrier() { asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory"); }
     // One row = 4096 bytes on the mbarrier, fetched as up to three 1-D bulk copies: the interval
     // the TNS pass filtered comes from its scratch, the rest straight from the spectra.
     __device__ __forceinline__ void issue_row(uint32_t d, uint32_t mbar, int cfi, uint32_t r) {
+        if (IOV && qframes) {   // one 2304-byte record, landing in the upper part of the row slot (dequant_stage)
+            bulk_load(d + (uint32_t)kQLandOffset, qframes + (size_t)cfi * kQFrameBytes, (uint32_t)kQFrameBytes, mbar);
+            return;
+        }
         const float *a = spectra + (size_t)cfi * 1024;
         const uint32_t lo = r & 0xffffu, hi = r >> 16;
         if (hi <= lo) { bulk_load(d, a, 4096u, mbar); return; }
@@ -115,7 +124,8 @@ struct DevSync {
         const uint32_t dst = get(1), mbar = get(2), nrows = get(3);
         bool ops = false;
         if (STEREO) ops = get(10) != 0 && ((ring[4 * get(8) + 1] >> 8) & 0xffu) != 0;
-        mbar_expect_tx(mbar, nrows * 4096u + (ops ? (uint32_t)sizeof(aacfb_stereo_ops) : 0u));
+        const uint32_t row_bytes = (IOV && qframes) ? (uint32_t)kQFrameBytes : 4096u;
+        mbar_expect_tx(mbar, nrows * row_bytes + (ops ? (uint32_t)sizeof(aacfb_stereo_ops) : 0u));
         issue_row(dst, mbar, (int)get(4), get(6));
         if (nrows == 2) issue_row(dst + 4096u, mbar, (int)get(5), get(7));
         if (STEREO && ops) bulk_load(get(9), stereo + (get(4) >> 1), (uint32_t)sizeof(aacfb_stereo_ops), mbar);
@@ -155,9 +165,10 @@ __device__ __forceinline__ uint32_t row_range(const SynthParams &P, size_t cf) {
 // GENERIC = false: takes only work items without EIGHT_SHORT frames (the long-transform code
 // alone, best register allocation); GENERIC = true: takes only the items that have one.
 // Both instantiations are launched back to back and walk the same item list.
-template <bool GENERIC, bool STEREO, int W, int ST>
+// IOV: the instantiations that also take aacfb_qframe input and / or write int16 PCM.
+template <bool GENERIC, bool STEREO, bool IOV, int W, int ST>
 __global__ void __launch_bounds__(W * 64, 1) synth_kernel(const __grid_constant__ SynthParams P) {
-    using L = Layout<W, ST, STEREO>;
+    using L = Layout<W, ST, STEREO, IOV>;
     constexpr int kCtaThreads = W * 64, kWorkers = W, kStages = ST, kBufsPerWorker = L::kBufsPerWorker;
     constexpr int kOffStages = L::kOffStages, kOffBars = L::kOffBars, kOffSlots = L::kOffSlots;
     extern __shared__ __align__(128) uint8_t smem[];
@@ -172,6 +183,14 @@ __global__ void __launch_bounds__(W * 64, 1) synth_kernel(const __grid_constant_
         const float4 *src = reinterpret_cast<const float4 *>(P.tab);
         float4 *dst = reinterpret_cast<float4 *>(smem);
         for (int i = tid; i < kSmemTableBytes / 16; i += kCtaThreads) dst[i] = src[i];
+    }
+    DqCtx dqc;
+    if (IOV && P.qframes != nullptr) {   // lookup tables of the inverse quantisation -> shared memory
+        float *dst = reinterpret_cast<float *>(smem + L::kOffDq);
+        for (int i = tid; i < 512; i += kCtaThreads) dst[i] = P.dq->sf[i];
+        for (int i = tid; i < kDqIqLo; i += kCtaThreads) dst[512 + i] = P.dq->iq[i];
+        dqc.D = P.dq; dqc.sf = dst; dqc.iq_lo = dst + 512;
+        dq_thread_consts(P.dq, u, dqc);
     }
     const SynthTables *ts = reinterpret_cast<const SynthTables *>(smem);
     float *stages = reinterpret_cast<float *>(smem + kOffStages) + (size_t)w * kBufsPerWorker * kStageFloats;
@@ -193,13 +212,14 @@ __global__ void __launch_bounds__(W * 64, 1) synth_kernel(const __grid_constant_
     }
     __syncthreads();
 
-    DevSync<STEREO, GENERIC> sync;
+    DevSync<STEREO, GENERIC, IOV> sync;
     sync.bar_id = 1 + w;
     sync.free_id = 1 + kWorkers + w;
     sync.leader_warp = ((tid >> 5) & 1) == 0;
     sync.leader = leader;
     sync.spectra = P.spectra;
     sync.scratch = P.scratch;
+    sync.qframes = IOV ? P.qframes : nullptr;
     sync.stereo = P.stereo;
     sync.ring = fi_ring;
     sync.pend = reinterpret_cast<volatile uint32_t *>(slot + 8);
@@ -317,19 +337,26 @@ __global__ void __launch_bounds__(W * 64, 1) synth_kernel(const __grid_constant_
             io.dst.scale = P.scale;
             io.dst.inv_scale = 1.0f / P.scale;
             io.dst.ostride = g.nc;
+            io.dst.s16 = IOV && P.pcm_s16 != 0;
+            io.dq = (IOV && P.qframes != nullptr) ? &dqc : nullptr;
             io.fi[0] = fi_ring[kRW * (fc % kFiRing)];
             io.fi[1] = fi_ring[kRW * (fc % kFiRing) + kRW / 2];
             io.ops = nullptr;
             if (STEREO && pr.interleaved && ((fi_ring[4 * (fc % kFiRing) + 1] >> 8) & 0xffu) != 0) io.ops = ops_area + st;
-            io.dst.out0 = P.pcm + oa;
-            io.dst.out1 = P.pcm + ob;
+            if (IOV && P.pcm_s16 != 0) {   // same element offsets, 2-byte samples
+                io.dst.out0 = reinterpret_cast<float *>(reinterpret_cast<int16_t *>(P.pcm) + oa);
+                io.dst.out1 = reinterpret_cast<float *>(reinterpret_cast<int16_t *>(P.pcm) + ob);
+            } else {
+                io.dst.out0 = P.pcm + oa;
+                io.dst.out1 = P.pcm + ob;
+            }
             if (leader) {
                 const bool next_valid = f + kStages < nf;
                 sync.put(0, next_valid ? 1u : 0u);
                 if (next_valid) refill(st, fc + kStages);
             }
             mbar_wait(bars + 8 * st, (fc / kStages) & 1u);
-            worker_frame<GENERIC, STEREO>(u, sync, io, ts, P.tab, z, ov);
+            worker_frame<GENERIC, STEREO, IOV>(u, sync, io, ts, P.tab, z, ov);
             cfa += g.nc; cfb += g.nc;
             oa += (size_t)1024 * g.nc; ob += (size_t)1024 * g.nc;
             if (++t == g.T) {  // the pair is complete: its overlap goes back to the state
@@ -679,28 +706,64 @@ cudaError_t launch_stereo(const StereoParams &P, cudaStream_t stream) {
     return cudaGetLastError();
 }
 
-template <bool GENERIC, bool STEREO, int W, int ST>
+template <bool GENERIC, bool STEREO, bool IOV, int W, int ST>
 static cudaError_t launch_one(const SynthParams &P, int num_sms, cudaStream_t stream) {
     static bool attr_done[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 64 && !attr_done[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(synth_kernel<GENERIC, STEREO, W, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             Layout<W, ST, STEREO>::kTotal);
+        cudaError_t e = cudaFuncSetAttribute(synth_kernel<GENERIC, STEREO, IOV, W, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             Layout<W, ST, STEREO, IOV>::kTotal);
         if (e != cudaSuccess) return e;
         attr_done[dev] = true;
     }
     const int grid = num_sms < (P.g.n_items + W - 1) / W ? num_sms : (P.g.n_items + W - 1) / W;
-    synth_kernel<GENERIC, STEREO, W, ST><<<grid < 1 ? 1 : grid, W * 64, Layout<W, ST, STEREO>::kTotal, stream>>>(P);
+    synth_kernel<GENERIC, STEREO, IOV, W, ST><<<grid < 1 ? 1 : grid, W * 64, Layout<W, ST, STEREO, IOV>::kTotal, stream>>>(P);
     return cudaGetLastError();
 }
 
 cudaError_t launch_synth(const SynthParams &P, int num_sms, bool generic, cudaStream_t stream) {
-    if (P.stereo != nullptr)   // the instantiations that also apply the stereo tools of the pair-frames
-        return generic ? launch_one<true, true, kWorkersGeneric, kStagesGeneric>(P, num_sms, stream)
-                       : launch_one<false, true, kWorkers, kStages>(P, num_sms, stream);
-    return generic ? launch_one<true, false, kWorkersGeneric, kStagesGeneric>(P, num_sms, stream)
-                   : launch_one<false, false, kWorkers, kStages>(P, num_sms, stream);
+    const bool iov = P.qframes != nullptr || P.pcm_s16 != 0;   // quantised input and / or int16 PCM
+    if (P.stereo != nullptr) {   // the instantiations that also apply the stereo tools of the pair-frames
+        if (iov) return generic ? launch_one<true, true, true, kWorkersGeneric, kStagesGeneric>(P, num_sms, stream)
+                                : launch_one<false, true, true, kWorkers, kStages>(P, num_sms, stream);
+        return generic ? launch_one<true, true, false, kWorkersGeneric, kStagesGeneric>(P, num_sms, stream)
+                       : launch_one<false, true, false, kWorkers, kStages>(P, num_sms, stream);
+    }
+    if (iov) return generic ? launch_one<true, false, true, kWorkersGeneric, kStagesGeneric>(P, num_sms, stream)
+                            : launch_one<false, false, true, kWorkers, kStages>(P, num_sms, stream);
+    return generic ? launch_one<true, false, false, kWorkersGeneric, kStagesGeneric>(P, num_sms, stream)
+                   : launch_one<false, false, false, kWorkers, kStages>(P, num_sms, stream);
+}
+
+// Inverse quantisation as a pre-pass: qframes -> float rows.  Only used when a TNS pass has to run
+// between it and the IMDCT (TNS_FIXED_* modes); otherwise synth_kernel dequantises the staged records.
+// One warp per channel-frame: lane l owns groups l + 32 j.
+__global__ void __launch_bounds__(128) dequant_kernel(const __grid_constant__ DequantParams P) {
+    const size_t cf = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (cf >= P.n_cf) return;
+    const uint8_t *rec = P.qframes + cf * kQFrameBytes;
+    const FrameBits fi = __ldg(reinterpret_cast<const uint32_t *>(P.info) + 2 * cf);
+    float4 *out = reinterpret_cast<float4 *>(P.out) + cf * 256;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int c4 = lane + 32 * j;
+        const uint2 raw = __ldg(reinterpret_cast<const uint2 *>(rec + 256 + 8 * c4));
+        int16_t q4[4];
+        q4[0] = (int16_t)(raw.x & 0xffffu); q4[1] = (int16_t)(raw.x >> 16);
+        q4[2] = (int16_t)(raw.y & 0xffffu); q4[3] = (int16_t)(raw.y >> 16);
+        float v[4];
+        dequant4(P.dq, rec, fi, c4, q4, v);
+        out[c4] = make_float4(v[0], v[1], v[2], v[3]);
+    }
+}
+
+cudaError_t launch_dequant(const DequantParams &P, cudaStream_t stream) {
+    const size_t threads = P.n_cf * 32;
+    if (threads == 0) return cudaSuccess;
+    dequant_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, stream>>>(P);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_tns(const TnsParams &P, cudaStream_t stream) {

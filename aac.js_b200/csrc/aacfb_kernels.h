@@ -33,6 +33,9 @@ struct SynthParams {
     float *ovl_out;                 // overlap state written by chunks ending at t = T
     const SynthTables *tab;         // device copy of the tables
     Geometry g;
+    const uint8_t *qframes;         // [S][T][nc] aacfb_qframe records INSTEAD of `spectra` (AACFB_IN_Q16), or nullptr
+    const DequantTables *dq;        // device tables of the inverse quantisation (needed with qframes)
+    int pcm_s16;                    // 1: `pcm` is int16_t [S][T][1024][nc] (AACFB_PCM_S16; scale must be 1)
     unsigned *counter;              // zeroed before launch (one per kernel instantiation)
     unsigned *short_items;          // zeroed; number of items with EIGHT_SHORT frames (set by the long-only pass)
     float scale;
@@ -59,6 +62,14 @@ struct StereoParams {            // stereo tools as a pre-pass (only when TNS ha
     const aacfb_stereo_ops *stereo;
     size_t n_pairs_frames;          // S * T * nc / 2
 };
+struct DequantParams {           // inverse quantisation as a pre-pass (TNS modes only)
+    const uint8_t *qframes;         // [n_cf] aacfb_qframe
+    const aacfb_frame_info *info;
+    const DequantTables *dq;
+    float *out;                     // [n_cf][1024]
+    size_t n_cf;
+};
+cudaError_t launch_dequant(const DequantParams &P, cudaStream_t stream);
 cudaError_t launch_stereo(const StereoParams &P, cudaStream_t stream);
 cudaError_t launch_synth(const SynthParams &P, int num_sms, bool generic, cudaStream_t stream);
 cudaError_t launch_tns(const TnsParams &P, cudaStream_t stream);

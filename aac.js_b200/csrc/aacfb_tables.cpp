@@ -214,6 +214,45 @@ void scale_windows(SynthTables &S, float scale) {
     }
 }
 
+// ics.js:203-266 needs IQ_TABLE / SCALEFACTOR_TABLE (tables.js:168-191), the scalefactor bands
+// of the context's sample rate and -- for perceptual noise substitution as shipped -- what the
+// generator of ics.js:234 produces: randomState = (randomState * (1664525 + 1013904223))|0 from
+// 0x1F2E3D4C, the product formed in double precision and wrapped by ToInt32.
+void build_dequant_tables(int sample_index, DequantTables &D) {
+    std::memset(&D, 0, sizeof D);
+    const float nan = std::nanf("");
+    const double four_thirds = 4.0 / 3.0;
+    for (int i = 0; i < 8191; ++i) D.iq[i] = (float)std::pow((double)i, four_thirds);
+    D.iq[8191] = nan;
+    for (int i = 0; i < 512; ++i) D.sf[i] = i < 428 ? (float)std::pow(2.0, (i - 200) / 4.0) : nan;
+    double state = (double)0x1F2E3D4C;
+    D.noise_len = 0;
+    for (int k = 0; k < 32; ++k) {
+        const double prod = state * (double)(1664525 + 1013904223);
+        // ToInt32: truncate (already integral), modulo 2^32, reinterpret as signed
+        double m = std::fmod(prod, 4294967296.0);
+        if (m < 0) m += 4294967296.0;
+        if (m >= 2147483648.0) m -= 4294967296.0;
+        state = m + 0.0;                    // ToInt32 never yields -0
+        D.noise[k] = (float)state;          // data[off + k] = this.randomState (Float32Array store)
+        if (state != 0.0) D.noise_len = k + 1;
+    }
+    const TnsBandTables &B = tns_band_tables();
+    std::memcpy(D.swb_long, B.swb_long[sample_index], sizeof D.swb_long);
+    std::memcpy(D.swb_short, B.swb_short[sample_index], sizeof D.swb_short);
+    const int nl = B.swb_long_count[sample_index], ns = B.swb_short_count[sample_index];
+    for (int i = 0; i < 256; ++i) {
+        int b = 0;
+        while (b + 1 < nl && D.swb_long[b + 1] <= 4 * i) ++b;
+        D.sfb_long[i] = (uint8_t)b;
+    }
+    for (int i = 0; i < 32; ++i) {
+        int b = 0;
+        while (b + 1 < ns && D.swb_short[b + 1] <= 4 * i) ++b;
+        D.sfb_short[i] = (uint8_t)b;
+    }
+}
+
 const TnsBandTables &tns_band_tables() {
     static TnsBandTables *B = nullptr;
     static std::once_flag once;

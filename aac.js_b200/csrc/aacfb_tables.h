@@ -70,6 +70,19 @@ const HostTables &host_tables();   // built once, thread-safe
 // with the overlap kept in scaled units -- bit-identical, two multiplies per bin cheaper.
 void scale_windows(SynthTables &S, float scale);
 
+// Inverse quantisation (ICStream.decodeSpectralData, reference src/ics.js:203-266).  Lives in global
+// memory and is read through the L1 (quantised values are small: the hot part of `iq` is a few lines).
+struct alignas(16) DequantTables {
+    float iq[8192];          // IQ_TABLE tables.js:181-191 = f32(i^(4/3)); [8191] = NaN (the reference reads `undefined`)
+    float sf[512];           // SCALEFACTOR_TABLE tables.js:168-176 = f32(2^((i-200)/4)); [428..511] = NaN (`undefined`)
+    float noise[32];         // PNS as shipped (ics.js:234-235): the generator's outputs as Float32Array elements;
+                             // 0 from noise_len on (the state collapses)
+    int noise_len, pad[3];
+    uint16_t swb_long[52], swb_short[16];   // info.swbOffsets of the context's sample rate (tables.js:126-154)
+    uint8_t sfb_long[256], sfb_short[32];   // scalefactor band that holds coefficients 4i .. 4i+3
+};
+void build_dequant_tables(int sample_index, DequantTables &D);
+
 // TNS band tables (device + host share the same flat arrays)
 struct TnsBandTables {
     uint16_t swb_long[12][52];

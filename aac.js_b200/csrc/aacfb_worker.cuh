@@ -45,6 +45,7 @@ struct FrameIO {
     FrameBits fi[2];              // packed aacfb_frame_info of each chain
     int nch;                      // 1 or 2 live chains
     const aacfb_stereo_ops *ops;  // stereo tools of this pair-frame (staged next to the rows) or nullptr
+    const DqCtx *dq;              // != nullptr: the stage holds aacfb_qframe records (dequant_stage turns them into rows)
     OutDst dst;                   // where the frame's PCM goes
 };
 
@@ -187,9 +188,13 @@ AACFB_HD void frame_with_short(int u, Sync &sync, const FrameIO &io, const Synth
 // instantiation for work items without any EIGHT_SHORT frame: it contains no
 // short-window code at all, so its register allocation is that of the long
 // path alone (the kernel is compiled twice, see synth_kernel).
-template <bool GENERIC, bool STEREO, class Sync>
+// IOV: the instantiation that also takes quantised input (AACFB_IN_Q16) and / or emits int16 PCM; the
+// float-only instantiations (IOV = false) contain none of that code.
+template <bool GENERIC, bool STEREO, bool IOV, class Sync>
 AACFB_HD void worker_frame(int u, Sync &sync, const FrameIO &io, const SynthTables *ts, const SynthTables *tg, Pts &z,
                            Ovl &ov) {
+    // inverse quantisation first: ics.js:203-266 runs inside the bit parse, before the stereo tools
+    if (IOV && io.dq) dequant_stage(u, sync, io.stage, io.nch, io.fi, *io.dq);
     // Packed two-chain arithmetic (FFMA2) halves the FP instruction count; on its own it is neutral
     // for the long-only instantiation (bounded by the shared-memory pipe, not by issue slots), but
     // it is what pays for deriving the MDCT twiddles in registers instead of loading them (cs_at):

@@ -210,7 +210,10 @@ def run_reference(args):
 class Batch:
     """One synthetic batch of a workload, resident in HBM on this rank, with its context."""
 
-    def __init__(self, A, W, torch, workload, S, T, rank, dev, local):
+    def __init__(self, A, W, torch, workload, S, T, rank, dev, local, q16_s16=False):
+        self.A, self.q16_s16 = A, q16_s16
+        if q16_s16:
+            workload = workload[: -len("_q16_s16")]
         cfg, _, _, C, desc = WORKLOADS[workload]
         self.workload, self.cfg, self.S, self.T, self.C, self.desc = workload, cfg, S, T, C, desc
         stereo = workload.endswith("_stereo")
@@ -231,11 +234,20 @@ class Batch:
             self.ops = torch.from_numpy(self.ops_np.view(np.uint8).reshape(S, T, 768).copy()).to(dev)
         self.info = torch.from_numpy(self.info_np.view(np.uint8).reshape(S, T, C, 8).copy()).to(dev)
         self.stereo_bytes = 0 if self.ops_np is None else int(self.ops_np.nbytes)
-        self.pcm = torch.empty((S, T, 1024, C), device=dev)
+        self.pcm = torch.empty((S, T, 1024, C), device=dev, dtype=torch.int16 if q16_s16 else torch.float32)
         self.ctx = A.Context(S, C, side["sample_index"], side["flags"], device=local)
         self.alg_bytes = algorithmic_bytes(S, T, C, self.tns_bytes, self.stereo_bytes)
+        if q16_s16:   # aacfb_qframe records in (2304 B), int16 PCM out (2048 B) per channel-frame
+            wq = W.make_q(cfg, S, T, C, seed=rank)
+            self.spectra = torch.from_numpy(wq["qframes"].view(np.uint8).reshape(S, T, C, 2304)).to(dev)
+            self.alg_bytes -= S * T * C * (8192 - 2304 - 2048)
 
     def step(self, stream):
+        if self.q16_s16:
+            A = self.A
+            self.ctx.process_device_io(self.spectra.data_ptr(), A.IN_Q16, self.info.data_ptr(), self.pcm.data_ptr(), A.PCM_S16,
+                                       self.T, stream.cuda_stream)
+            return
         self.ctx.process_device(self.spectra.data_ptr(), self.info.data_ptr(), self.pcm.data_ptr(), self.T,
                                 stream.cuda_stream, self.blob.data_ptr() if self.blob is not None else 0,
                                 self.offs.data_ptr() if self.offs is not None else 0, self.tns_bytes,
@@ -495,43 +507,103 @@ def run_ours(args):
     assert 0.05 < peak < 50 and bool(torch.isfinite(b.pcm).all()), peak
 
     # --- end to end through the host-buffer C-ABI call (H2D + D2H inside the timed region) ---
+    # Headline leg: the host hands over what the bit parse holds BEFORE inverse quantisation (aacfb_qframe:
+    # int16 coefficients + scalefactor indices, 2304 B per channel-frame; the device runs ics.js:203-266) and
+    # takes int16 PCM back (2048 B) -- 4.3 instead of 8.0 KiB per channel-frame over PCIe.  The float-in /
+    # float-out call of round 1 (readChunk's own formats) is timed beside it, and so is the headline leg
+    # from pageable memory (a host that neither allocates through aacfb_host_alloc nor registers its arrays).
     e2e = None
     side, info_np, ops_np, tns_bytes = b.side, b.info_np, b.ops_np, b.tns_bytes
     if not args.no_e2e:
-        h_spec = torch.empty((S, T, C, 1024), dtype=torch.float32, pin_memory=True)
-        h_spec.copy_(b.spectra)
-        h_pcm = torch.empty((S, T, 1024, C), dtype=torch.float32, pin_memory=True)
-        spec_np, pcm_np = h_spec.numpy(), h_pcm.numpy()
-        ctx2 = A.Context(S, C, side["sample_index"], side["flags"], device=local)
         e2e_steps = args.e2e_steps or max(2, min(args.steps, 20))
-        for _ in range(2):
-            ctx2.process(spec_np, info_np, side["tns_blob"], side["tns_offsets"], out=pcm_np, stereo_ops=ops_np)
-        barrier()
-        with ClockSampler(local) as clocks_e2e:
-            t0 = time.perf_counter()
-            for _ in range(e2e_steps):
-                ctx2.process(spec_np, info_np, side["tns_blob"], side["tns_offsets"], out=pcm_np, stereo_ops=ops_np)
-            torch.cuda.synchronize()
-            dt = time.perf_counter() - t0
-        ce = clocks_e2e.summary()
+        side_bytes = info_np.nbytes + (tns_bytes + side["tns_offsets"].nbytes if tns_bytes else 0) + b.stereo_bytes
+
+        def leg(inp, in_format, out, pcm_format, steps):
+            ctx2 = A.Context(S, C, side["sample_index"], side["flags"], device=local)
+            call = lambda: ctx2.process_io(inp, info_np, side["tns_blob"], side["tns_offsets"], out=out, stereo_ops=ops_np,
+                                           in_format=in_format, pcm_format=pcm_format)
+            for _ in range(2):
+                call()
+            barrier()
+            with ClockSampler(local) as cs:
+                t0 = time.perf_counter()
+                for _ in range(steps):
+                    call()
+                torch.cuda.synchronize()
+                dt = time.perf_counter() - t0
+            ctx2.close()
+            te = torch.tensor([dt], device=dev, dtype=torch.float64)
+            if world > 1:
+                torch.distributed.all_reduce(te, op=torch.distributed.ReduceOp.MAX)
+            return float(te.item()) / steps * 1e3, cs.summary()
+
+        def record(ms, inp, out, api):
+            return {"value": world * S * T / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms,
+                    "h2d_bytes_per_step": int(inp.nbytes + side_bytes), "d2h_bytes_per_step": int(out.nbytes), "api": api}
+
+        numa = f"process bound to the {numa_cpus} CPUs local to the GPU" if numa_cpus else "no binding"
+        variants = {}
+        # (1) float spectra in, float PCM out (pinned)
+        h_spec = A.host_alloc((S, T, C, 1024), np.float32)
+        h_spec[...] = b.spectra.cpu().numpy()
+        h_pcm = A.host_alloc((S, T, 1024, C), np.float32)
+        ms, ce = leg(h_spec, A.IN_F32, h_pcm, A.PCM_F32, e2e_steps)
+        assert np.isfinite(h_pcm[0, 0]).all() and np.abs(h_pcm[-1, -1]).max() > 0
+        variants["f32_in_f32_out"] = record(ms, h_spec, h_pcm, "aacfb_process (float spectra -> float PCM, page-locked buffers)")
+        A.host_free(h_spec); A.host_free(h_pcm)
+        del h_spec, h_pcm
+        e2e = dict(variants["f32_in_f32_out"])
+        if args.workload in ("config2", "config3", "config5") and ops_np is None:
+            wq = W.make_q(cfg, S, T, C, seed=rank)
+            h_q = A.host_alloc((S, T, C), A.QFRAME_DTYPE)
+            h_q[...] = wq["qframes"]
+            h_p16 = A.host_alloc((S, T, 1024, C), np.int16)
+            ms, ce = leg(h_q, A.IN_Q16, h_p16, A.PCM_S16, e2e_steps)
+            pk = int(np.abs(h_p16[0].astype(np.int32)).max())
+            assert 500 < pk <= 32768, pk
+            variants["q16_in_s16_out"] = record(ms, h_q, h_p16, "aacfb_process_io (aacfb_qframe -> int16 PCM, page-locked buffers "
+                                                "from aacfb_host_alloc): inverse quantisation on the device")
+            h_pf = A.host_alloc((S, T, 1024, C), np.float32)
+            ms2, _ = leg(h_q, A.IN_Q16, h_pf, A.PCM_F32, max(2, e2e_steps // 2))
+            variants["q16_in_f32_out"] = record(ms2, h_q, h_pf, "aacfb_process_io (aacfb_qframe -> float PCM)")
+            A.host_free(h_pf)
+            del h_pf
+            # the same call from ordinary (pageable) numpy arrays
+            p_q, p_p16 = wq["qframes"], np.empty((S, T, 1024, C), np.int16)
+            ms3, _ = leg(p_q, A.IN_Q16, p_p16, A.PCM_S16, max(2, e2e_steps // 4))
+            variants["q16_in_s16_out_pageable"] = record(ms3, p_q, p_p16, "the headline call from pageable memory")
+            A.host_free(h_q); A.host_free(h_p16)
+            del h_q, h_p16, wq, p_q, p_p16
+            e2e = dict(variants["q16_in_s16_out"])
+        e2e["steps"] = e2e_steps
+        e2e["numa"] = numa
+        e2e["variants"] = variants
         if ce["samples"]:  # the e2e loop is long enough for nvidia-smi's 100 ms sampling: merge
             clock_kernel = {"sm_mhz": ce["sm_mhz"] if not clock_kernel["samples"] else clock_kernel["sm_mhz"],
                             "sm_max_mhz": ce["sm_max_mhz"],
                             "reasons": sorted(set(ce["reasons"]) | set(clock_kernel["reasons"])),
                             "samples": clock_kernel["samples"], "samples_e2e": ce["samples"], "sm_mhz_e2e": ce["sm_mhz"]}
-        te = torch.tensor([dt], device=dev, dtype=torch.float64)
-        if world > 1:
-            torch.distributed.all_reduce(te, op=torch.distributed.ReduceOp.MAX)
-        e2e_val = world * S * T * e2e_steps / float(te.item())
-        assert np.isfinite(pcm_np[0, 0]).all() and np.abs(pcm_np[-1, -1]).max() > 0
-        side_bytes = info_np.nbytes + (tns_bytes + side["tns_offsets"].nbytes if tns_bytes else 0) + b.stereo_bytes
-        e2e = {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(spec_np.nbytes + side_bytes),
-               "d2h_bytes_per_step": int(pcm_np.nbytes), "steps": e2e_steps,
-               "ms_per_step": float(te.item()) / e2e_steps * 1e3,
-               "api": "aacfb_process (pinned host buffers, 2-lane copy/compute pipeline)",
-               "numa": f"process bound to the {numa_cpus} CPUs local to the GPU" if numa_cpus else "no binding"}
-        ctx2.close()
-        del h_spec, h_pcm, spec_np, pcm_np
+        # one call at the shape the drop-in decoder (js/decoder_b200.js) actually makes: 1 stream x K frames
+        lat = {}
+        for K in (64, 1):
+            cl = A.Context(1, C, side["sample_index"], 0, device=local)
+            wl = W.make_q(2, 1, K, C, seed=5)
+            hq = A.host_alloc((1, K, C), A.QFRAME_DTYPE); hq[...] = wl["qframes"]
+            hp = A.host_alloc((1, K, 1024, C), np.int16)
+            hs = A.host_alloc((1, K, C, 1024), np.float32); hs[...] = 1000.0
+            hf = A.host_alloc((1, K, 1024, C), np.float32)
+            for name, fn in (("q16_s16", lambda: cl.process_io(hq, wl["info"], out=hp, in_format=A.IN_Q16, pcm_format=A.PCM_S16)),
+                             ("f32_f32", lambda: cl.process_io(hs, wl["info"], out=hf))):
+                for _ in range(10):
+                    fn()
+                t0 = time.perf_counter()
+                for _ in range(200):
+                    fn()
+                lat[f"S1_T{K}_{name}"] = (time.perf_counter() - t0) / 200 * 1e6
+            cl.close()
+            for h in (hq, hp, hs, hf):
+                A.host_free(h)
+        e2e["latency_us_per_call"] = lat
     alg_head = b.alg_bytes
     b.close()
     del b
@@ -541,17 +613,20 @@ def run_ours(args):
     configs = None
     if world == 1 and not args.no_configs and args.workload == "config2" and not args.streams and not args.frames:
         configs = {}
-        for name in ("config3", "config4", "config5", "config2_stereo"):
-            _, S2, T2, C2, desc2 = WORKLOADS[name]
-            bb = Batch(A, W, torch, name, S2, T2, rank, dev, local)
+        for name in ("config3", "config4", "config5", "config2_stereo", "config2_q16_s16"):
+            q16 = name.endswith("_q16_s16")
+            _, S2, T2, C2, desc2 = WORKLOADS[name[: -len("_q16_s16")] if q16 else name]
+            if q16:
+                desc2 += "; input = aacfb_qframe records (inverse quantisation on the device), output = int16 PCM"
+            bb = Batch(A, W, torch, name, S2, T2, rank, dev, local, q16_s16=q16)
             k = max(5, min(args.steps, 100))
             for _ in range(3):
                 bb.step(stream)
             l0 = bb.ctx.launches
             tot, per = time_steps(torch, lambda: bb.step(stream), k, 0, stream, barrier)
             ms = tot / k
-            pk = float(bb.pcm.abs().max())
-            assert 0.01 < pk < 100 and bool(torch.isfinite(bb.pcm).all()), (name, pk)
+            pk = float(bb.pcm.float().abs().max()) / (32768.0 if q16 else 1.0)
+            assert 0.01 < pk < 100 and bool(torch.isfinite(bb.pcm.float()).all()), (name, pk)
             configs[name] = {"workload": desc2, "steps": k, "ms_per_step": ms, "value": S2 * T2 / ms * 1e3, "unit": UNIT,
                              "gpu_launches": int(bb.ctx.launches - l0),
                              "roofline": roofline_record(name, bb.alg_bytes, float(np.mean(per)), bb.tns_bytes > 0, traffic_tab)}

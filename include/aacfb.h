@@ -127,6 +127,53 @@ typedef struct aacfb_tns_filter {
     uint8_t reserved;
 } aacfb_tns_filter;
 
+/* ---- inverse quantisation + scalefactors + PNS on the device ---------------
+ * ICStream.decodeSpectralData (reference src/ics.js:203-266) interleaves the Huffman decode with
+ *     data[i] = +-IQ_TABLE[|q|];  data[i] *= scaleFactors[idx]          (ics.js:247-254)
+ * A host that ships the Huffman-decoded INTEGERS and the per-band scalefactor indices instead of
+ * the Float32 spectrum moves 2304 instead of 4104 bytes per channel-frame over PCIe; the device
+ * dequantises the row while it sits in shared memory.  One record per channel-frame, [S][T][C]:
+ *   q[i]        buf[j] of ics.js:247 at data index i (window-grouped order, as the reference
+ *               stores it); |q| <= 8191 (IQ_TABLE has 8191 entries: |q| = 8191 reads `undefined`
+ *               there -> NaN, reproduced).  Coefficients of ZERO / intensity / noise bands and
+ *               everything at or above swbOffsets[maxSFB] are ignored.
+ *   band[idx]   idx = g * maxSFB + sfb as in ics.js:213-219: kind | index i into
+ *               SCALEFACTOR_TABLE (tables.js:168-176, 428 entries; i > 427 = `undefined` -> NaN)
+ *                 AACFB_BAND_ZERO      ZERO_BT, INTENSITY_BT, INTENSITY_BT2: data = 0   (ics.js:222-227)
+ *                 AACFB_BAND_SPECTRAL  scaleFactors[idx] =  SCALEFACTOR_TABLE[i]          (ics.js:166-172)
+ *                 AACFB_BAND_NOISE     scaleFactors[idx] = -SCALEFACTOR_TABLE[i]; perceptual noise
+ *                                      substitution AS SHIPPED (ics.js:228-242): the generator
+ *                                      randomState = (randomState * (1664525 + 1013904223))|0 starts
+ *                                      at 0x1F2E3D4C in every new ICStream (one per element per frame,
+ *                                      decoder.js:146,154), yields 11 non-zero values and then 0 for
+ *                                      ever, so all but the first noise coefficients of a
+ *                                      channel-frame become 0 * (sf / sqrt(0)) = NaN.  Reproduced.
+ *   group_len   info.groupLength[0 .. groupCount-1], zero-terminated (ONLY_LONG etc.: {1})
+ * window_sequence and maxSFB come from the channel-frame's aacfb_frame_info. */
+#define AACFB_BAND_ZERO       0x0000u
+#define AACFB_BAND_SPECTRAL   0x4000u
+#define AACFB_BAND_NOISE      0x8000u
+#define AACFB_BAND_KIND_MASK  0xc000u
+#define AACFB_BAND_INDEX_MASK 0x01ffu
+#define AACFB_BAND_UNDEFINED  0x01ffu   /* scalefactor index outside the table: NaN           */
+typedef struct aacfb_qframe {
+    uint8_t  group_len[8];
+    uint16_t band[120];          /* MAX_SECTIONS, ics.js:49                                */
+    uint8_t  reserved[8];        /* must be 0                                              */
+    int16_t  q[1024];
+} aacfb_qframe;                  /* 2304 bytes, 16-byte aligned rows                        */
+
+/* PCM sample formats of the *_io entry points.  S16 is what Aurora's sinks
+ * make of readChunk's Float32 output OUTSIDE the reference tree (parity unpinned there); here it
+ * is defined as  Int16Array[i] = max(-32768, min(32767, Math.round(data[ch][k])))  on the
+ * un-normalised sample (decoder.js:210 divides by 32768 only to normalise): round half up,
+ * saturate, NaN -> 0.  Pinned by known-answer tests. */
+#define AACFB_PCM_F32 0u
+#define AACFB_PCM_S16 1u
+/* input formats */
+#define AACFB_IN_F32  0u         /* float spectra [S][T][C][1024] (ics.data)               */
+#define AACFB_IN_Q16  1u         /* aacfb_qframe  [S][T][C]                                */
+
 typedef struct aacfb_ctx aacfb_ctx;
 
 /* Construct.  Replaces `new FilterBank(smallFrames, channels)`
@@ -178,6 +225,35 @@ int aacfb_process_device_stereo(aacfb_ctx *ctx, const float *d_spectra,
                                 size_t tns_blob_bytes,
                                 float *d_pcm, int n_frames, void *stream);
 
+/* The general form of the four calls above: `input` is float spectra (AACFB_IN_F32) or
+ * aacfb_qframe records (AACFB_IN_Q16: the device runs ICStream.decodeSpectralData's inverse
+ * quantisation, ics.js:203-266, first); `pcm` receives [S][T][1024][C] samples as Float32 / 32768
+ * (AACFB_PCM_F32, readChunk's output) or as int16 (AACFB_PCM_S16).  stereo_ops, tns_blob and
+ * tns_offsets may be NULL.  Host buffers, blocking. */
+int aacfb_process_io(aacfb_ctx *ctx, const void *input, uint32_t in_format,
+                     const aacfb_frame_info *info,
+                     const aacfb_stereo_ops *stereo_ops,
+                     const uint8_t *tns_blob, const uint32_t *tns_offsets,
+                     void *pcm, uint32_t pcm_format, int n_frames);
+/* Same with DEVICE pointers, asynchronous on `stream`. */
+int aacfb_process_device_io(aacfb_ctx *ctx, const void *d_input, uint32_t in_format,
+                            const aacfb_frame_info *d_info,
+                            const aacfb_stereo_ops *d_stereo_ops,
+                            const uint8_t *d_tns_blob, const uint32_t *d_tns_offsets,
+                            size_t tns_blob_bytes,
+                            void *d_pcm, uint32_t pcm_format, int n_frames, void *stream);
+
+/* Page-locked host memory for the buffers of the host-buffer calls.  The copies of
+ * aacfb_process* run at the PCIe rate only from page-locked memory; a host that keeps its
+ * staging arrays for the life of the decoder (the N-API addon's typed arrays) either allocates
+ * them here (aacfb_host_alloc: the addon wraps the pointer in an external ArrayBuffer) or
+ * registers existing memory once (aacfb_host_register; `bytes` > 0, any alignment).  Buffers
+ * that are neither still work (pageable copies, slower). */
+void *aacfb_host_alloc(size_t bytes);
+int aacfb_host_free(void *p);
+int aacfb_host_register(void *p, size_t bytes);
+int aacfb_host_unregister(void *p);
+
 /* The inner seam, one channel-frame at a time, HOST buffers:
  *     filterBank.process(info, input, output, channel)  filter_bank.js:88
  * `output` is the 1024 un-scaled, un-interleaved samples of this.data[channel]
@@ -208,6 +284,9 @@ uint64_t aacfb_launch_count(const aacfb_ctx *ctx);
  * 3 MDCT twiddles 256 [128], 4 sine1024, 5 kbd1024, 6 sine128, 7 kbd128.
  * Returns the number of floats written or a negative error. */
 int aacfb_get_table(int which, float *dst, int capacity);
+/* which: 8 IQ_TABLE [8192 f32, entry 8191 = NaN for the reference's out-of-table read]
+ * (tables.js:181-191), 9 SCALEFACTOR_TABLE [428] (tables.js:168-176), 10 the PNS generator's
+ * output as shipped, as floats [32] (ics.js:234-235).  Needs capacity >= 8192 for 8. */
 /* Scalefactor-band offsets info.swbOffsets (tables.js:126-154, ics.js:301,307) of one
  * sample rate: is_short = 0 -> SWB_OFFSET_1024[sample_index], 1 -> SWB_OFFSET_128.
  * Returns the number of bands (swbCount); dst receives swbCount + 1 offsets. */

@@ -586,6 +586,95 @@ API void aacfb_oracle_tns(const aacfb_frame_info *info, const uint8_t *block, si
     tns_process(info, block, block_bytes, sample_index, mode, data);
 }
 
+/* ------------------------------------------------------------ inverse quantisation
+ * ICStream.decodeSpectralData, ics.js:203-266, with the Huffman decoder's output (buf[j],
+ * ics.js:247) taken from aacfb_qframe.q and bandTypes / scaleFactors from aacfb_qframe.band
+ * (include/aacfb.h).  tables.js:168-191 build the two lookup tables with Math.pow. */
+static float g_iq_table[8191];        /* tables.js:181-191 */
+static float g_sf_table[428];         /* tables.js:168-176 */
+static pthread_once_t g_dq_once = PTHREAD_ONCE_INIT;
+static void init_dequant(void) {
+    double four_thirds = 4.0 / 3.0;
+    for (int i = 0; i < 8191; i++) g_iq_table[i] = (float)pow((double)i, four_thirds);
+    for (int i = 0; i < 428; i++) g_sf_table[i] = (float)pow(2.0, (i - 200) / 4.0);
+}
+/* JS ToInt32 of an integral double (the |0 of ics.js:234) */
+static double to_int32(double x) {
+    if (isnan(x) || isinf(x)) return 0;
+    double m = fmod(trunc(x), 4294967296.0);
+    if (m < 0) m += 4294967296.0;
+    if (m >= 2147483648.0) m -= 4294967296.0;
+    return m + 0.0;   /* ToInt32 never yields -0 (fmod keeps the sign of a negative multiple of 2^32) */
+}
+static void decode_spectral_data(const aacfb_qframe *qf, const aacfb_frame_info *info, int sample_index, float *data) {
+    pthread_once(&g_dq_once, init_dequant);
+    memset(data, 0, 4096);                       /* this.data = new Float32Array(frameLength), ics.js:28 */
+    int is_short = info->window_sequence == AACFB_EIGHT_SHORT_SEQUENCE;
+    const uint16_t *offsets = is_short ? SWB_OFFSET_128[sample_index].off : SWB_OFFSET_1024[sample_index].off; /* ics.js:301,307 */
+    int maxSFB = info->max_sfb, windowGroups = 0;
+    while (windowGroups < 8 && qf->group_len[windowGroups]) windowGroups++;
+    double randomState = (double)0x1F2E3D4C;      /* ics.js:31; a new ICStream per element per frame, decoder.js:146,154 */
+    int groupOff = 0, idx = 0;
+    for (int g = 0; g < windowGroups; g++) {
+        int groupLen = qf->group_len[g];
+        for (int sfb = 0; sfb < maxSFB; sfb++, idx++) {
+            unsigned code = qf->band[idx], kind = code & AACFB_BAND_KIND_MASK, ti = code & AACFB_BAND_INDEX_MASK;
+            int off = groupOff + offsets[sfb], width = offsets[sfb + 1] - offsets[sfb];
+            /* scaleFactors[idx] is a Float32Array element: +-SCALEFACTOR_TABLE[i], `undefined` -> NaN outside the table */
+            float tab = ti < 428 ? g_sf_table[ti] : NAN;
+            if (kind == AACFB_BAND_ZERO) {                         /* ics.js:222-227 */
+                for (int group = 0; group < groupLen; group++, off += 128)
+                    for (int i = off; i < off + width; i++) data[i] = 0;
+            } else if (kind == AACFB_BAND_NOISE) {                 /* ics.js:228-242 */
+                float sf = -tab;                                   /* ics.js:158 */
+                for (int group = 0; group < groupLen; group++, off += 128) {
+                    double energy = 0;
+                    for (int k = 0; k < width; k++) {
+                        randomState = to_int32(randomState * (double)(1664525 + 1013904223));
+                        data[off + k] = (float)randomState;
+                        energy += (double)data[off + k] * (double)data[off + k];
+                    }
+                    double scale = (double)sf / sqrt(energy);
+                    for (int k = 0; k < width; k++) data[off + k] = (float)((double)data[off + k] * scale);
+                }
+            } else {                                               /* ics.js:243-256 */
+                float sf = tab;                                    /* ics.js:171 */
+                for (int group = 0; group < groupLen; group++, off += 128)
+                    for (int k = 0; k < width; k++) {
+                        int b = qf->q[off + k];
+                        float iq;
+                        if (b > 0) iq = b < 8191 ? g_iq_table[b] : NAN;
+                        else iq = -b < 8191 ? -g_iq_table[-b] : NAN;
+                        data[off + k] = iq;
+                        data[off + k] = (float)((double)data[off + k] * (double)sf);
+                    }
+            }
+        }
+        groupOff += groupLen << 7;
+    }
+}
+API void aacfb_oracle_dequant(const aacfb_qframe *qf, const aacfb_frame_info *info, int sample_index, float *data) {
+    decode_spectral_data(qf, info, sample_index, data);
+}
+API int aacfb_oracle_dequant_table(int which, float *dst, int cap) {
+    pthread_once(&g_dq_once, init_dequant);
+    if (which == 0) { if (cap < 8191) return -1; memcpy(dst, g_iq_table, sizeof g_iq_table); return 8191; }
+    if (which == 1) { if (cap < 428) return -1; memcpy(dst, g_sf_table, sizeof g_sf_table); return 428; }
+    return -1;
+}
+
+/* AACFB_PCM_S16 (include/aacfb.h): Int16Array[i] = Math.max(-32768, Math.min(32767, Math.round(x))).
+ * Math.round = floor(x + 0.5) evaluated exactly (x is a float, the sum is exact in double);
+ * NaN survives min/max and is stored as 0. */
+static int16_t pcm_s16(float x) {
+    if (isnan(x)) return 0;
+    double r = floor((double)x + 0.5);
+    if (r > 32767) r = 32767;
+    if (r < -32768) r = -32768;
+    return (int16_t)r;
+}
+API void aacfb_oracle_pcm_s16(const float *x, int16_t *out, int n) { for (int i = 0; i < n; i++) out[i] = pcm_s16(x[i]); }
+
 /* The whole path for a batch, same contract as aacfb_process (aacfb.h):
  *   spectra [S][T][C][1024], info [S][T][C], pcm [S][T][1024][C],
  *   overlap [S][C][1024] in/out.   decoder.js:263-269 + :204-213. */
@@ -593,6 +682,8 @@ typedef struct {
     const float *spectra; const aacfb_frame_info *info; const uint8_t *tns_blob;
     const uint32_t *tns_offsets; float *overlap; float *pcm;
     int S, T, C, sample_index; uint32_t flags; int s0, s1;
+    const aacfb_qframe *q;   /* != NULL: input is quantised (decodeSpectralData runs first) */
+    int16_t *pcm16;          /* != NULL: AACFB_PCM_S16 output instead of pcm */
 } job_t;
 
 static void *job_run(void *arg) {
@@ -608,7 +699,8 @@ static void *job_run(void *arg) {
             for (int c = 0; c < C; c++) {
                 size_t cf = f * C + c;
                 const aacfb_frame_info *inf = &j->info[cf];
-                memcpy(data, j->spectra + cf * 1024, 4096);
+                if (j->q) decode_spectral_data(&j->q[cf], inf, j->sample_index, data);   /* ics.js:80 */
+                else memcpy(data, j->spectra + cf * 1024, 4096);
                 if (inf->tns_present && j->tns_offsets && j->tns_blob) { /* decoder.js:263-264 */
                     uint32_t o0 = j->tns_offsets[cf], o1 = j->tns_offsets[cf + 1];
                     if (o1 > o0) tns_process(inf, j->tns_blob + o0, o1 - o0, j->sample_index, j->flags, data);
@@ -618,19 +710,42 @@ static void *job_run(void *arg) {
                 filterbank_process(inf, data, out, j->overlap + ((size_t)s * C + c) * 1024, buf, sc); /* decoder.js:269 */
             }
             /* Interleave channels, decoder.js:204-213 */
-            float *o = j->pcm + f * 1024 * C;
             size_t jj = 0;
-            for (int k = 0; k < 1024; k++)
-                for (int i = 0; i < C; i++) o[jj++] = (float)((double)chan[(size_t)i * 1024 + k] / 32768);
+            if (j->pcm16) {
+                int16_t *o = j->pcm16 + f * 1024 * C;
+                for (int k = 0; k < 1024; k++)
+                    for (int i = 0; i < C; i++) o[jj++] = pcm_s16(chan[(size_t)i * 1024 + k]);
+            } else {
+                float *o = j->pcm + f * 1024 * C;
+                for (int k = 0; k < 1024; k++)
+                    for (int i = 0; i < C; i++) o[jj++] = (float)((double)chan[(size_t)i * 1024 + k] / 32768);
+            }
         }
     }
     free(sc); free(buf); free(data); free(chan);
     return NULL;
 }
 
+static int process_any(const float *spectra, const aacfb_qframe *q, const aacfb_frame_info *info, const uint8_t *tns_blob,
+                       const uint32_t *tns_offsets, float *overlap, float *pcm, int16_t *pcm16, int S, int T, int C,
+                       int sample_index, uint32_t flags, int n_threads);
 API int aacfb_oracle_process(const float *spectra, const aacfb_frame_info *info, const uint8_t *tns_blob,
                              const uint32_t *tns_offsets, float *overlap, float *pcm, int S, int T, int C,
                              int sample_index, uint32_t flags, int n_threads) {
+    return process_any(spectra, NULL, info, tns_blob, tns_offsets, overlap, pcm, NULL, S, T, C, sample_index, flags, n_threads);
+}
+/* same contract as aacfb_process_io (no stereo tools: callers apply aacfb_oracle_stereo first) */
+API int aacfb_oracle_process_io(const void *input, uint32_t in_format, const aacfb_frame_info *info, const uint8_t *tns_blob,
+                                const uint32_t *tns_offsets, float *overlap, void *pcm, uint32_t pcm_format, int S, int T,
+                                int C, int sample_index, uint32_t flags, int n_threads) {
+    return process_any(in_format == AACFB_IN_Q16 ? NULL : (const float *)input,
+                       in_format == AACFB_IN_Q16 ? (const aacfb_qframe *)input : NULL, info, tns_blob, tns_offsets, overlap,
+                       pcm_format == AACFB_PCM_S16 ? NULL : (float *)pcm, pcm_format == AACFB_PCM_S16 ? (int16_t *)pcm : NULL,
+                       S, T, C, sample_index, flags, n_threads);
+}
+static int process_any(const float *spectra, const aacfb_qframe *q, const aacfb_frame_info *info, const uint8_t *tns_blob,
+                       const uint32_t *tns_offsets, float *overlap, float *pcm, int16_t *pcm16, int S, int T, int C,
+                       int sample_index, uint32_t flags, int n_threads) {
     aacfb_oracle_init();
     if (S <= 0 || T < 0 || C <= 0) return -1;
     if (n_threads < 1) n_threads = 1;
@@ -639,7 +754,7 @@ API int aacfb_oracle_process(const float *spectra, const aacfb_frame_info *info,
     pthread_t *th = (pthread_t *)calloc(n_threads, sizeof *th);
     for (int i = 0; i < n_threads; i++) {
         jobs[i] = (job_t){spectra, info, tns_blob, tns_offsets, overlap, pcm, S, T, C, sample_index, flags,
-                          (int)((long)S * i / n_threads), (int)((long)S * (i + 1) / n_threads)};
+                          (int)((long)S * i / n_threads), (int)((long)S * (i + 1) / n_threads), q, pcm16};
         if (n_threads == 1) job_run(&jobs[i]);
         else pthread_create(&th[i], NULL, job_run, &jobs[i]);
     }

@@ -56,6 +56,13 @@ def lib():
         L.aacfb_oracle_stereo.restype = None
         L.aacfb_oracle_adts_header.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p]
         L.aacfb_oracle_adts_header.restype = C.c_int
+        L.aacfb_oracle_dequant.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        L.aacfb_oracle_dequant.restype = None
+        L.aacfb_oracle_dequant_table.argtypes = [C.c_int, C.c_void_p, C.c_int]
+        L.aacfb_oracle_pcm_s16.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        L.aacfb_oracle_pcm_s16.restype = None
+        L.aacfb_oracle_process_io.argtypes = [C.c_void_p, C.c_uint32] + [C.c_void_p] * 5 + [C.c_uint32] + [C.c_int] * 4 + [C.c_uint32, C.c_int]
+        L.aacfb_oracle_process_io.restype = C.c_int
         L.aacfb_oracle_init()
         _lib = L
     return _lib
@@ -171,3 +178,69 @@ def adts_header(data: bytes):
     if lib().aacfb_oracle_adts_header(_p(buf), buf.size, _p(out)) != 0:
         return None
     return dict(zip(("profile", "samplingIndex", "chanConfig", "frameLength", "numFrames", "bits"), (int(v) for v in out)))
+
+
+# ---- inverse quantisation (ics.js:203-266) and the int16 PCM sink -----------------------------
+QFRAME_DTYPE = np.dtype([("group_len", "u1", (8,)), ("band", "u2", (120,)), ("reserved", "u1", (8,)), ("q", "i2", (1024,))])
+assert QFRAME_DTYPE.itemsize == 2304
+IN_F32, IN_Q16, PCM_F32, PCM_S16 = 0, 1, 0, 1
+
+
+def dequant(qframe: np.ndarray, info: np.ndarray, sample_index: int = 4) -> np.ndarray:
+    """ICStream.decodeSpectralData's arithmetic on one aacfb_qframe record -> ics.data (1024 f32)."""
+    qf = np.ascontiguousarray(qframe, QFRAME_DTYPE)
+    info = np.ascontiguousarray(info, INFO_DTYPE)
+    out = np.empty(1024, np.float32)
+    lib().aacfb_oracle_dequant(_p(qf), _p(info), sample_index, _p(out))
+    return out
+
+
+def dequant_batch(qframes: np.ndarray, info: np.ndarray, sample_index: int = 4) -> np.ndarray:
+    """dequant over an [S][T][C] array of records -> spectra [S][T][C][1024]."""
+    qf = np.ascontiguousarray(qframes, QFRAME_DTYPE)
+    info = np.ascontiguousarray(info, INFO_DTYPE).reshape(qf.shape)
+    out = np.empty(qf.shape + (1024,), np.float32)
+    flat_q, flat_i, flat_o = qf.reshape(-1), info.reshape(-1), out.reshape(-1, 1024)
+    L = lib()
+    for i in range(flat_q.size):
+        L.aacfb_oracle_dequant(C.c_void_p(flat_q[i:i + 1].ctypes.data), C.c_void_p(flat_i[i:i + 1].ctypes.data),
+                               sample_index, C.c_void_p(flat_o[i].ctypes.data))
+    return out
+
+
+def dequant_table(which: int) -> np.ndarray:
+    """0: IQ_TABLE (8191), 1: SCALEFACTOR_TABLE (428) as the oracle builds them (tables.js:168-191)."""
+    out = np.empty(8192, np.float32)
+    n = lib().aacfb_oracle_dequant_table(which, _p(out), out.size)
+    assert n > 0
+    return out[:n].copy()
+
+
+def pcm_s16(x: np.ndarray) -> np.ndarray:
+    x = np.ascontiguousarray(x, np.float32)
+    out = np.empty(x.shape, np.int16)
+    lib().aacfb_oracle_pcm_s16(_p(x), _p(out), x.size)
+    return out
+
+
+def process_io(inp, in_format, info, tns_blob=None, tns_offsets=None, overlap=None, *, pcm_format=PCM_F32,
+               sample_index=4, flags=TNS_AS_SHIPPED, n_threads=1):
+    """aacfb_process_io's contract on the CPU: inp = spectra [S][T][C][1024] f32 (IN_F32) or records
+    [S][T][C] (IN_Q16); returns (pcm [S][T][1024][C] f32 or i16, overlap)."""
+    if in_format == IN_Q16:
+        inp = np.ascontiguousarray(inp, QFRAME_DTYPE)
+        S, T, Cn = inp.shape
+    else:
+        inp = np.ascontiguousarray(inp, np.float32)
+        S, T, Cn, _ = inp.shape
+    info = np.ascontiguousarray(info, INFO_DTYPE).reshape(S, T, Cn)
+    if overlap is None:
+        overlap = np.zeros((S, Cn, 1024), np.float32)
+    pcm = np.empty((S, T, 1024, Cn), np.int16 if pcm_format == PCM_S16 else np.float32)
+    if tns_blob is not None:
+        tns_blob = np.ascontiguousarray(tns_blob, np.uint8)
+        tns_offsets = np.ascontiguousarray(tns_offsets, np.uint32)
+    rc = lib().aacfb_oracle_process_io(_p(inp), in_format, _p(info), _p(tns_blob), _p(tns_offsets), _p(overlap), _p(pcm),
+                                       pcm_format, S, T, Cn, sample_index, flags, n_threads)
+    assert rc == 0
+    return pcm, overlap

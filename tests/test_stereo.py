@@ -173,11 +173,12 @@ def gpu_vs_oracle(case, S, T, flags):
 @pytest.mark.gpu
 @pytest.mark.parametrize("S,T", [(1, 1), (3, 9), (37, 33)])
 def test_gpu_stereo_tools_fused_into_synthesis(S, T):
-    """No TNS pass: synth_kernel applies the ops to the staged rows (2 launches, no pre-pass)."""
+    """No TNS pass: synth_kernel applies the ops to the staged rows (no pre-pass: the long-only
+    instantiation, plus the generic one unless the host-side check saw no EIGHT_SHORT frame)."""
     case = W.random_stereo_case(S, T, np.random.default_rng(100 + S), sigma=3e4)
     launches = gpu_vs_oracle(case, S, T, A.TNS_AS_SHIPPED)
     if S * T * 2 * 4096 < (8 << 20):   # one sub-batch (aacfb_process splits larger ones)
-        assert launches == 2
+        assert launches == (2 if (case["info"]["window_sequence"] == 2).any() else 1)
 
 
 @pytest.mark.gpu
@@ -185,7 +186,7 @@ def test_gpu_stereo_tools_fused_into_synthesis(S, T):
 def test_gpu_stereo_tools_before_tns(mode):
     """TNS runs between the stereo tools and the IMDCT (decoder.js:300-319): pre-pass kernel."""
     case = W.random_stereo_case(5, 11, np.random.default_rng(200 + mode), tns_mode=mode, sigma=2e4)
-    assert gpu_vs_oracle(case, 5, 11, mode) == 4
+    assert gpu_vs_oracle(case, 5, 11, mode) == (4 if (case["info"]["window_sequence"] == 2).any() else 3)
 
 
 @pytest.mark.gpu

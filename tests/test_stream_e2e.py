@@ -113,7 +113,7 @@ def test_gpu_replay_of_the_staged_calls_equals_the_reference_decoder(path):
         T = c["spectra"].shape[0]
         ops = c["stereo_ops"].view(A.STEREO_DTYPE).reshape(1, T, 1) if c["stereo_ops"] is not None else None
         out.append(ctx.process(c["spectra"][None], c["info"][None], c["tns_blob"], c["tns_offsets"], stereo_ops=ops).reshape(-1))
-    assert ctx.launches >= 2 * len(calls)
+    assert ctx.launches >= len(calls)
     ctx.close()
     pcm = np.concatenate(out)
     ref = z["pcm"]

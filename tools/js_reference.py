@@ -632,5 +632,99 @@ def main_adts():
     print("adts", len(rows), "frames;", msg)
 
 
+class DequantReference:
+    """ICStream.prototype.decodeSpectralData (src/ics.js:203-266), unmodified, run by the interpreter: the
+    ICStream is built with the reference's own constructor and filled with what decodeBandTypes /
+    decodeScaleFactors would have left behind; the one stand-in is the entropy decoder it calls --
+    `Huffman.decodeSpectralData(stream, hcb, buf, 0)` is replaced by a function that hands out the integers
+    of an aacfb_qframe record in the order the loop asks for them.  Inverse quantisation, scalefactor
+    multiplication, perceptual noise substitution (with its generator, ics.js:234) and the zero bands are
+    the reference's own statements, its lookup tables the ones src/tables.js builds."""
+
+    FIRST_PAIR_BT, NOISE_BT, ZERO_BT = 5, 13, 0
+
+    def __init__(self, sample_index=4, src_dir=REF_SRC):
+        self.rt = J.Runtime(src_dir)
+        self.ICStream = self.rt.require("./ics")
+        self.tables = self.rt.require("./tables")
+        self.huffman = self.rt.require("./huffman")
+        self.sample_index = sample_index
+        self.config = J.obj(profile=2, chanConfig=2, frameLength=1024, sampleIndex=sample_index)
+        self.sf_table = self.tables.get("SCALEFACTOR_TABLE").a
+        self.iq_table = self.tables.get("IQ_TABLE").a
+
+    def run(self, qframe, fi, rng=None):
+        """One aacfb_qframe record + its aacfb_frame_info -> ics.data (1024 f32) as the reference computes it."""
+        s = self.ICStream.construct([self.config])
+        info = s.get("info")
+        short = int(fi["window_sequence"]) == 2
+        which = "SWB_OFFSET_128" if short else "SWB_OFFSET_1024"
+        offsets_js = J.get_member(self.tables.get(which), float(self.sample_index))
+        offsets = np.asarray(offsets_js.a)
+        info.put("windowSequence", float(fi["window_sequence"]))
+        info.put("swbOffsets", offsets_js)
+        groups = int(np.count_nonzero(np.cumsum(qframe["group_len"] == 0) == 0))
+        max_sfb = int(fi["max_sfb"])
+        info.put("groupCount", float(groups))
+        info.get("groupLength").a[:8] = qframe["group_len"]
+        info.put("maxSFB", float(max_sfb))
+        feed = []
+        group_off = 0
+        for g in range(groups):
+            glen = int(qframe["group_len"][g])
+            for sfb in range(max_sfb):
+                idx = g * max_sfb + sfb
+                code = int(qframe["band"][idx])
+                kind, ti = code & 0xc000, code & 0x1ff
+                tab = float(self.sf_table[ti]) if ti < 428 else float("nan")
+                if kind == 0x0000:
+                    s.get("bandTypes").a[idx] = self.ZERO_BT
+                    s.get("scaleFactors").a[idx] = 0.0
+                elif kind == 0x8000:
+                    s.get("bandTypes").a[idx] = self.NOISE_BT
+                    s.get("scaleFactors").a[idx] = -tab                       # ics.js:158
+                else:
+                    # any spectral codebook: quads below FIRST_PAIR_BT, pairs from it on (ics.js:245)
+                    hcb = 1 + (idx % 11) if rng is None else int(rng.integers(1, 12))
+                    s.get("bandTypes").a[idx] = hcb
+                    s.get("scaleFactors").a[idx] = tab                        # ics.js:171
+                    lo, hi = int(offsets[sfb]), int(offsets[sfb + 1])
+                    for w in range(glen):
+                        base = group_off + 128 * w
+                        feed.extend(int(v) for v in qframe["q"][base + lo: base + hi])
+            group_off += glen << 7
+        pos = [0]
+
+        def decode_spectral_data(this, a):   # Huffman.decodeSpectralData(stream, hcb, buf, off): huffman.js:1426-1455
+            hcb, buf = int(J.to_number(a[1])), a[2]
+            num = 2 if hcb >= self.FIRST_PAIR_BT else 4
+            buf.a[:num] = feed[pos[0]: pos[0] + num]
+            pos[0] += num
+            return J.UNDEF
+
+        self.huffman.put("decodeSpectralData", J.native(decode_spectral_data))
+        s.get("decodeSpectralData").call(s, [J.obj()])
+        assert pos[0] == len(feed), (pos[0], len(feed))
+        return s.get("data").a.copy()
+
+
+def dequant_cases(seed=91, n=40):
+    rng = np.random.default_rng(seed)
+    case = W.random_q_case(n, 1, 1, rng, p_noise=0.12)
+    return case["qframes"].reshape(n), case["info"].reshape(n)
+
+
+def main_dequant():
+    """tests/golden/dequant/jsref_dequant.npz: 40 records through the reference's decodeSpectralData."""
+    ref = DequantReference()
+    q, info = dequant_cases()
+    data = np.stack([ref.run(q[i], info[i]) for i in range(len(q))])
+    out = os.path.join(ROOT, "tests", "golden", "dequant")
+    os.makedirs(out, exist_ok=True)
+    np.savez_compressed(os.path.join(out, "jsref_dequant.npz"), qframes=q, info=info, data=data,
+                        iq_table=ref.iq_table.copy(), sf_table=ref.sf_table.copy(), sample_index=4)
+    print("wrote jsref_dequant.npz", data.shape, "NaN rows:", int(np.isnan(data).any(axis=1).sum()))
+
+
 if __name__ == "__main__":
-    {"stereo": main_stereo, "adts": main_adts, "decoder": main_decoder, "stream": main_stream}.get((sys.argv[1:] or [""])[0], main)()
+    {"stereo": main_stereo, "adts": main_adts, "decoder": main_decoder, "stream": main_stream, "dequant": main_dequant}.get((sys.argv[1:] or [""])[0], main)()

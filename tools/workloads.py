@@ -265,3 +265,67 @@ def adts_stream(rng, n_frames, crc_every=3, sampling_index=4, chan_config=2):
         meta.append((len(out), length, hdr, profile_field + 1, nf_field + 1))
         out += h + bytes(rng.integers(0, 256, length - 7, dtype=np.uint8))
     return bytes(out), meta
+
+
+# ------------------------------------------------------------------ quantised input
+QFRAME_DTYPE = np.dtype([("group_len", "u1", (8,)), ("band", "u2", (120,)), ("reserved", "u1", (8,)), ("q", "i2", (1024,))])
+BAND_ZERO, BAND_SPECTRAL, BAND_NOISE = 0x0000, 0x4000, 0x8000
+
+
+def make_q(config: int, S: int, T: int, C: int = 2, seed: int = 0, sigma_q: float = 40.0):
+    """The quantised twin of make(): the same window sequences / shapes / TNS side info, but the input is
+    what the bit parse holds BEFORE inverse quantisation -- aacfb_qframe records: Huffman-decoded integers
+    q ~ round(N(0, sigma_q^2)) and one scalefactor per band, drawn within +-2 octaves of the value that gives
+    the float workload's spectral level (rms(|q|^(4/3)) * 2^((i - 200) / 4) ~ sigma).  Every band below
+    maxSFB is spectral; everything above it is zero (as in a real stream).  Returns make()'s dict with
+    `qframes` [S][T][C] instead of `spectra`."""
+    w = make(config, S, T, C, seed=seed, side_only=True)
+    rng = np.random.default_rng(seed + 7919)
+    sigma = {1: 3.0e5, 2: 3.0e5, 3: 1.0e5, 4: 0.75e5, 5: 1.0e5}[config]
+    qf = np.zeros((S, T, C), QFRAME_DTYPE)
+    q = np.rint(rng.standard_normal((S, T, C, 1024), dtype=np.float32) * np.float32(sigma_q))
+    qf["q"] = np.clip(q, -8190, 8190).astype(np.int16)
+    level = float(np.sqrt(np.mean(np.abs(q[:1]).astype(np.float64) ** (8.0 / 3.0))))
+    i0 = int(round(200 + 4 * np.log2(sigma / level))) - 4   # the +-2 octave spread below raises the rms by ~1.9
+    is_short = w["info"]["window_sequence"] == EIGHT_SHORT
+    qf["group_len"][..., 0] = np.where(is_short, 2, 1)          # EIGHT_SHORT: groups of 2, 3, 3 windows
+    qf["group_len"][..., 1] = np.where(is_short, 3, 0)
+    qf["group_len"][..., 2] = np.where(is_short, 3, 0)
+    qf["band"] = (BAND_SPECTRAL | np.clip(i0 + rng.integers(-8, 9, (S, T, C, 120)), 0, 427)).astype(np.uint16)
+    w["qframes"] = qf
+    return w
+
+
+def random_q_case(S, T, C, rng, tns_mode=0, sample_index=4, p_noise=0.08, p_zero=0.1, sigma_q=60.0):
+    """Irregular quantised input: random_case's window sequences / shapes / TNS, random window groups,
+    random maxSFB, every band kind (zero, spectral, noise), scalefactor indices over the whole table and a
+    sprinkling of extreme integers (+-8190, +-8191 = the reference's out-of-table read)."""
+    case = random_case(S, T, C, rng, tns_mode=tns_mode)
+    del case["spectra"]
+    info = case["info"]
+    qf = np.zeros((S, T, C), QFRAME_DTYPE)
+    q = np.rint(rng.standard_normal((S, T, C, 1024)) * sigma_q)
+    big = rng.random((S, T, C, 1024)) < 0.002
+    q[big] = rng.choice([-8191, -8190, -4000, 4000, 8190, 8191], size=int(big.sum()))
+    qf["q"] = q.astype(np.int16)
+    for s in range(S):
+        for t in range(T):
+            for c in range(C):
+                short = info["window_sequence"][s, t, c] == EIGHT_SHORT
+                if short:
+                    cuts = np.sort(rng.choice(np.arange(1, 8), size=int(rng.integers(0, 8)), replace=False))
+                    glen = np.diff(np.concatenate([[0], cuts, [8]]))
+                    info["max_sfb"][s, t, c] = rng.integers(0, SWB_SHORT_COUNT[sample_index] + 1)
+                else:
+                    glen = np.array([1])
+                    info["max_sfb"][s, t, c] = rng.integers(0, SWB_LONG_COUNT[sample_index] + 1)
+                qf["group_len"][s, t, c, :len(glen)] = glen
+                r = rng.random(120)
+                kind = np.where(r < p_zero, BAND_ZERO, np.where(r < p_zero + p_noise, BAND_NOISE, BAND_SPECTRAL))
+                idx = rng.integers(150, 300, 120)
+                odd = rng.random(120) < 0.02
+                idx[odd] = rng.choice([0, 427, 428, 511], size=int(odd.sum()))
+                qf["band"][s, t, c] = (kind | idx).astype(np.uint16)
+    case["qframes"] = qf
+    case["sample_index"] = sample_index
+    return case
