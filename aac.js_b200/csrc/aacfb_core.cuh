@@ -18,6 +18,7 @@
 #pragma once
 #include <math.h>
 #include <stdint.h>
+#include <string.h>
 
 #include "../../include/aacfb.h"
 #include "aacfb_tables.h"
@@ -36,6 +37,14 @@ AACFB_HD float f_mul(float a, float b) { volatile float r = a * b; return r; }
 AACFB_HD float f_add(float a, float b) { volatile float r = a + b; return r; }
 AACFB_HD float f_sub(float a, float b) { volatile float r = a - b; return r; }
 AACFB_HD float f_fma(float a, float b, float c) { return fmaf(a, b, c); }
+#endif
+
+#if defined(__CUDA_ARCH__)
+AACFB_HD uint32_t f_bits(float v) { return __float_as_uint(v); }
+AACFB_HD float f_from_bits(uint32_t b) { return __uint_as_float(b); }
+#else
+AACFB_HD uint32_t f_bits(float v) { uint32_t b; memcpy(&b, &v, 4); return b; }
+AACFB_HD float f_from_bits(uint32_t b) { float v; memcpy(&v, &b, 4); return v; }
 #endif
 
 // ---- packed pairs: the same quantity of chain 0 (.x) and chain 1 (.y) -----------------------
@@ -373,15 +382,22 @@ struct OutDst {
 
 // Float sample (un-normalised, decoder.js:210 before the division) -> int16 the way a JS sink does it:
 // Int16Array[i] = max(-32768, min(32767, Math.round(x))): round half UP, saturate, NaN -> 0
-// (include/aacfb.h, AACFB_PCM_S16).  rintf rounds half to even; the only inputs where that differs
-// from Math.round are the ties it rounded down, x - rint(x) == +0.5 exactly (the difference is exact).
+// (include/aacfb.h, AACFB_PCM_S16), i.e. floor(x + 0.5) with the sum taken exactly.
 AACFB_HD int pcm_s16(float x) {
+#if defined(__CUDA_ARCH__)
+    // floor(x + 0.5) exactly, in two instructions: the sum rounded DOWN is the largest float <= the exact
+    // sum, and no integer lies between the two (integers of that size are floats), so their floors agree.
+    // cvt.rmi saturates at the int32 range and turns NaN into 0.
+    int r = __float2int_rd(__fadd_rd(x, 0.5f));
+    r = r < -32768 ? -32768 : r;
+    return r > 32767 ? 32767 : r;
+#else
     if (!(x == x)) return 0;
-    float r = rintf(x);
-    if (f_sub(x, r) == 0.5f) r = f_add(r, 1.0f);
-    r = r < -32768.0f ? -32768.0f : r;
-    r = r > 32767.0f ? 32767.0f : r;
+    double r = floor((double)x + 0.5);
+    r = r < -32768.0 ? -32768.0 : r;
+    r = r > 32767.0 ? 32767.0 : r;
     return (int)r;
+#endif
 }
 
 // Effective windows of a long-transform frame as (value at m, value at 1023-m):
@@ -901,12 +917,35 @@ struct DqCtx {
     const float *sf;                          // SCALEFACTOR_TABLE padded to 512 entries (NaN from 428 on)
     uint32_t sfb_long4;                       // sfb_long[u + 64 j] in byte j
     uint32_t sfb_short1;                      // sfb_short[u & 31]
+    float iq_lane;                            // IQ_TABLE[lane]: values below 32 -- nearly all of a real stream -- are
+                                              // looked up with one warp shuffle instead of a bank-conflicted gather
 };
+// IQ_TABLE[a] for a < kDqIqLo (callers redo larger ones).  AACFB_DQ_SHFL: values below 32 through a warp
+// shuffle of a per-lane copy instead of the shared-memory gather -- measured SLOWER on B200 (0.397 vs
+// 0.345 ms on config 2, independent of the spread of the integers: the gather's bank conflicts are not
+// what bounds this phase), so it is off.
+#ifndef AACFB_DQ_SHFL
+#define AACFB_DQ_SHFL 0
+#endif
+AACFB_HD float dq_iq(const DqCtx &dq, int a) {
+#if defined(__CUDA_ARCH__) && AACFB_DQ_SHFL
+    float t = __shfl_sync(0xffffffffu, dq.iq_lane, a & 31);
+    if (a >= 32) t = dq.iq_lo[a & (kDqIqLo - 1)];
+    return t;
+#else
+    return dq.iq_lo[a & (kDqIqLo - 1)];
+#endif
+}
 AACFB_HD void dq_thread_consts(const DequantTables *D, int u, DqCtx &dq) {
     dq.sfb_long4 = 0;
 #pragma unroll
     for (int j = 0; j < 4; ++j) dq.sfb_long4 |= (uint32_t)dq_ld(&D->sfb_long[u + 64 * j]) << (8 * j);
     dq.sfb_short1 = dq_ld(&D->sfb_short[u & 31]);
+#if defined(__CUDA_ARCH__)
+    dq.iq_lane = dq_ld(&D->iq[threadIdx.x & 31]);
+#else
+    dq.iq_lane = 0.f;
+#endif
 }
 
 template <class Sync>
@@ -956,19 +995,39 @@ AACFB_HD void dequant_stage(int u, Sync &sync, float *stage, int nch, const Fram
                 raw[j] = *reinterpret_cast<const uint2 *>(rec + 256 + 8 * (u + 64 * j));
             }
             bool any_noise = false;
+            int big = 0;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                const bool spectral = (code[j] & AACFB_BAND_KIND_MASK) == AACFB_BAND_SPECTRAL;
-                any_noise |= (code[j] & AACFB_BAND_KIND_MASK) == AACFB_BAND_NOISE;
+                const uint32_t kind = code[j] & AACFB_BAND_KIND_MASK;
+                any_noise |= kind == AACFB_BAND_NOISE;
+                // zero / intensity / noise bands: scale 0 and no sign -> +0 whatever q holds (ics.js:222-227)
+                const uint32_t sign_mask = kind == AACFB_BAND_SPECTRAL ? 0x80000000u : 0u;
+                const float sc = kind == AACFB_BAND_SPECTRAL ? s[j] : 0.f;
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     const uint32_t word = k < 2 ? raw[j].x : raw[j].y;
-                    const int q = (int)(int16_t)((k & 1) ? (word >> 16) : (word & 0xffffu));
-                    int a = q < 0 ? -q : q;
-                    float t = dq.iq_lo[a & (kDqIqLo - 1)];
-                    if (a >= kDqIqLo) t = dq_ld(&dq.D->iq[a > 8191 ? 8191 : a]);   // outside IQ_TABLE: `undefined` -> NaN
-                    const float val = f_mul(q > 0 ? t : -t, s[j]);                  // ics.js:250-253 (q = 0 gives -0)
-                    v[c][4 * j + k] = spectral ? val : 0.f;                         // ics.js:222-227: zero bands are +0
+                    const int q = (k & 1) ? ((int)word >> 16) : (int)(int16_t)(word & 0xffffu);
+                    const int a = q < 0 ? -q : q;
+                    big |= a;
+                    // (buf[j] > 0) ? IQ[buf[j]] : -IQ[-buf[j]]  (ics.js:250-252): the table is >= +0, so the sign
+                    // is OR-ed in; q - 1 is negative exactly when q <= 0 (q = 0 gives -0 like the reference)
+                    const uint32_t t = f_bits(dq_iq(dq, a)) | ((uint32_t)(q - 1) & sign_mask);
+                    v[c][4 * j + k] = f_mul(f_from_bits(t), sc);
+                }
+            }
+            if (big >= kDqIqLo) {   // some |q| beyond the shared-memory part of IQ_TABLE (rare): redo those elements
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if ((code[j] & AACFB_BAND_KIND_MASK) != AACFB_BAND_SPECTRAL) continue;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const uint32_t word = k < 2 ? raw[j].x : raw[j].y;
+                        const int q = (k & 1) ? ((int)word >> 16) : (int)(int16_t)(word & 0xffffu);
+                        const int a = q < 0 ? -q : q;
+                        if (a < kDqIqLo) continue;
+                        const float t = dq_ld(&dq.D->iq[a > 8191 ? 8191 : a]);   // outside IQ_TABLE: `undefined` -> NaN
+                        v[c][4 * j + k] = f_mul(q > 0 ? t : -t, s[j]);
+                    }
                 }
             }
             if (any_noise) {   // perceptual noise substitution: the general (slow) path for those groups
