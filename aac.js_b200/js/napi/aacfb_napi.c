@@ -12,6 +12,7 @@
  */
 #include <node_api.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../../include/aacfb.h"
@@ -35,13 +36,35 @@ static void *typed(napi_env env, napi_value v, size_t *bytes) { /* NULL for null
     return data;
 }
 
-static aacfb_ctx *handle(napi_env env, napi_value v) {
+/* The handle JS holds: the context plus the shape every buffer size is checked against. */
+typedef struct { aacfb_ctx *ctx; int S, C; } handle_t;
+
+static handle_t *handle(napi_env env, napi_value v) {
     void *p = NULL;
-    napi_get_value_external(env, v, &p);
-    return (aacfb_ctx *)p;
+    if (napi_get_value_external(env, v, &p) != napi_ok || !p) { napi_throw_error(env, NULL, "not an aacfb handle"); return NULL; }
+    return (handle_t *)p;
 }
 
-static void finalize(napi_env env, void *data, void *hint) { (void)env; (void)hint; aacfb_destroy((aacfb_ctx *)data); }
+static void finalize(napi_env env, void *data, void *hint) {
+    (void)env; (void)hint;
+    handle_t *h = (handle_t *)data;
+    aacfb_destroy(h->ctx);
+    free(h);
+}
+
+/* A typed array that must hold at least `need` bytes (NULL allowed when `optional`).  A short array from JS
+ * would otherwise become an out-of-bounds read or write inside cudaMemcpy. */
+static int sized(napi_env env, napi_value v, size_t need, int optional, const char *what, void **out) {
+    size_t have = 0;
+    *out = typed(env, v, &have);
+    if (!*out) {
+        if (optional) return 1;
+        napi_throw_error(env, NULL, what);
+        return 0;
+    }
+    if (have < need) { napi_throw_error(env, NULL, what); return 0; }
+    return 1;
+}
 
 /* create(device, nStreams, channels, sampleIndex, smallFrames, flags) -> handle */
 static napi_value js_create(napi_env env, napi_callback_info info) {
@@ -51,22 +74,71 @@ static napi_value js_create(napi_env env, napi_callback_info info) {
     aacfb_ctx *ctx = NULL;
     int rc = aacfb_create(&ctx, v[0], v[1], v[2], v[3], v[4], (uint32_t)v[5]);
     if (rc != AACFB_OK) return fail(env, NULL, rc);   /* e.g. "WHA?? No small frames allowed." */
+    handle_t *h = (handle_t *)malloc(sizeof *h);
+    if (!h) { aacfb_destroy(ctx); napi_throw_error(env, NULL, "out of memory"); return NULL; }
+    h->ctx = ctx; h->S = v[1]; h->C = v[2];
     napi_value ext;
-    NAPI_OK(env, napi_create_external(env, ctx, finalize, NULL, &ext));
+    NAPI_OK(env, napi_create_external(env, h, finalize, NULL, &ext));
     return ext;
+}
+
+/* The one batched call everything else is a special case of:
+ * processIo(handle, input (Float32Array spectra | Uint8Array of aacfb_qframe records), inFormat 0|1, info u8,
+ *           stereoOps u8|null, tnsBlob u8|null, tnsOffsets u32|null, pcm (Float32Array | Int16Array), pcmFormat 0|1, nFrames) */
+static napi_value process_any(napi_env env, handle_t *h, napi_value input, uint32_t in_format, napi_value info,
+                              napi_value stereo, napi_value blob, napi_value offsets, napi_value pcm, uint32_t pcm_format,
+                              int32_t n) {
+    if (!h) return NULL;
+    if (n < 0 || in_format > AACFB_IN_Q16 || pcm_format > AACFB_PCM_S16) { napi_throw_error(env, NULL, "bad frame count / format"); return NULL; }
+    const size_t n_cf = (size_t)h->S * (size_t)n * (size_t)h->C;
+    void *in_p, *info_p, *st_p, *blob_p, *off_p, *pcm_p;
+    if (!sized(env, input, n_cf * (in_format == AACFB_IN_Q16 ? sizeof(aacfb_qframe) : 4096), 0, "input array too small for nFrames", &in_p)) return NULL;
+    if (!sized(env, info, n_cf * sizeof(aacfb_frame_info), 0, "info array too small for nFrames", &info_p)) return NULL;
+    if (!sized(env, stereo, n_cf / 2 * sizeof(aacfb_stereo_ops), 1, "stereo-ops array too small for nFrames", &st_p)) return NULL;
+    if (!sized(env, offsets, (n_cf + 1) * sizeof(uint32_t), 1, "TNS offsets array too small for nFrames", &off_p)) return NULL;
+    const size_t blob_need = off_p ? ((const uint32_t *)off_p)[n_cf] : 0;
+    if (!sized(env, blob, blob_need, 1, "TNS blob shorter than its offsets say", &blob_p)) return NULL;
+    if (!sized(env, pcm, n_cf * (pcm_format == AACFB_PCM_S16 ? 2048 : 4096), 0, "pcm array too small for nFrames", &pcm_p)) return NULL;
+    int rc = aacfb_process_io(h->ctx, in_p, in_format, (const aacfb_frame_info *)info_p, (const aacfb_stereo_ops *)st_p,
+                              (const uint8_t *)blob_p, (const uint32_t *)off_p, pcm_p, pcm_format, n);
+    if (rc != AACFB_OK) return fail(env, h->ctx, rc);
+    return NULL;
+}
+
+static napi_value js_process_io(napi_env env, napi_callback_info info) {
+    size_t argc = 10; napi_value a[10];
+    NAPI_OK(env, napi_get_cb_info(env, info, &argc, a, NULL, NULL));
+    uint32_t inf = 0, outf = 0; int32_t n = 0;
+    napi_get_value_uint32(env, a[2], &inf); napi_get_value_uint32(env, a[8], &outf); napi_get_value_int32(env, a[9], &n);
+    return process_any(env, handle(env, a[0]), a[1], inf, a[3], a[4], a[5], a[6], a[7], outf, n);
+}
+
+/* allocPinned(bytes) -> ArrayBuffer on page-locked memory (aacfb_host_alloc), freed with the buffer: the
+ * decoder's staging typed arrays live here, so the library's copies run at the PCIe rate. */
+static void free_pinned(napi_env env, void *data, void *hint) { (void)env; (void)hint; aacfb_host_free(data); }
+static napi_value js_alloc_pinned(napi_env env, napi_callback_info info) {
+    size_t argc = 1; napi_value a[1];
+    NAPI_OK(env, napi_get_cb_info(env, info, &argc, a, NULL, NULL));
+    uint32_t bytes = 0; napi_get_value_uint32(env, a[0], &bytes);
+    void *p = aacfb_host_alloc(bytes ? bytes : 16);
+    if (!p) return fail(env, NULL, AACFB_ERR_CUDA);
+    memset(p, 0, bytes ? bytes : 16);
+    napi_value ab;
+    if (napi_create_external_arraybuffer(env, p, bytes, free_pinned, NULL, &ab) != napi_ok) {
+        aacfb_host_free(p);
+        napi_throw_error(env, NULL, "external ArrayBuffers are not available in this runtime");
+        return NULL;
+    }
+    return ab;
 }
 
 /* process(handle, spectra f32, info u8 (8 B per channel-frame), tnsBlob u8|null, tnsOffsets u32|null, pcm f32, nFrames) */
 static napi_value js_process(napi_env env, napi_callback_info info) {
     size_t argc = 7; napi_value a[7];
     NAPI_OK(env, napi_get_cb_info(env, info, &argc, a, NULL, NULL));
-    aacfb_ctx *ctx = handle(env, a[0]);
     int32_t n = 0; napi_get_value_int32(env, a[6], &n);
-    int rc = aacfb_process(ctx, (const float *)typed(env, a[1], NULL), (const aacfb_frame_info *)typed(env, a[2], NULL),
-                           (const uint8_t *)typed(env, a[3], NULL), (const uint32_t *)typed(env, a[4], NULL),
-                           (float *)typed(env, a[5], NULL), n);
-    if (rc != AACFB_OK) return fail(env, ctx, rc);
-    return NULL;
+    napi_value none; napi_get_null(env, &none);
+    return process_any(env, handle(env, a[0]), a[1], AACFB_IN_F32, a[2], none, a[3], a[4], a[5], AACFB_PCM_F32, n);
 }
 
 /* processStereo(handle, spectra f32, info u8, stereoOps u8 (768 B per pair-frame), tnsBlob, tnsOffsets, pcm f32, nFrames):
@@ -74,13 +146,8 @@ static napi_value js_process(napi_env env, napi_callback_info info) {
 static napi_value js_process_stereo(napi_env env, napi_callback_info info) {
     size_t argc = 8; napi_value a[8];
     NAPI_OK(env, napi_get_cb_info(env, info, &argc, a, NULL, NULL));
-    aacfb_ctx *ctx = handle(env, a[0]);
     int32_t n = 0; napi_get_value_int32(env, a[7], &n);
-    int rc = aacfb_process_stereo(ctx, (const float *)typed(env, a[1], NULL), (const aacfb_frame_info *)typed(env, a[2], NULL),
-                                  (const aacfb_stereo_ops *)typed(env, a[3], NULL), (const uint8_t *)typed(env, a[4], NULL),
-                                  (const uint32_t *)typed(env, a[5], NULL), (float *)typed(env, a[6], NULL), n);
-    if (rc != AACFB_OK) return fail(env, ctx, rc);
-    return NULL;
+    return process_any(env, handle(env, a[0]), a[1], AACFB_IN_F32, a[2], a[3], a[4], a[5], a[6], AACFB_PCM_F32, n);
 }
 
 /* swbOffsets(sampleIndex, isShort) -> Uint16Array copy of info.swbOffsets (tables.js:126-154); the JS host
@@ -135,11 +202,14 @@ static napi_value js_adts_index(napi_env env, napi_callback_info info) {
 static napi_value js_filterbank(napi_env env, napi_callback_info info) {
     size_t argc = 6; napi_value a[6];
     NAPI_OK(env, napi_get_cb_info(env, info, &argc, a, NULL, NULL));
-    aacfb_ctx *ctx = handle(env, a[0]);
+    handle_t *h = handle(env, a[0]);
+    if (!h) return NULL;
     int32_t s = 0, c = 0; napi_get_value_int32(env, a[1], &s); napi_get_value_int32(env, a[2], &c);
-    int rc = aacfb_filterbank_process(ctx, s, c, (const aacfb_frame_info *)typed(env, a[3], NULL),
-                                      (const float *)typed(env, a[4], NULL), (float *)typed(env, a[5], NULL));
-    if (rc != AACFB_OK) return fail(env, ctx, rc);
+    void *fi, *in, *out;
+    if (!sized(env, a[3], sizeof(aacfb_frame_info), 0, "info must hold 8 bytes", &fi)) return NULL;
+    if (!sized(env, a[4], 4096, 0, "input must hold 1024 floats", &in) || !sized(env, a[5], 4096, 0, "output must hold 1024 floats", &out)) return NULL;
+    int rc = aacfb_filterbank_process(h->ctx, s, c, (const aacfb_frame_info *)fi, (const float *)in, (float *)out);
+    if (rc != AACFB_OK) return fail(env, h->ctx, rc);
     return NULL;
 }
 
@@ -147,20 +217,25 @@ static napi_value js_filterbank(napi_env env, napi_callback_info info) {
 static napi_value js_tns(napi_env env, napi_callback_info info) {
     size_t argc = 5; napi_value a[5];
     NAPI_OK(env, napi_get_cb_info(env, info, &argc, a, NULL, NULL));
-    aacfb_ctx *ctx = handle(env, a[0]);
+    handle_t *h = handle(env, a[0]);
+    if (!h) return NULL;
     size_t nb = 0; const uint8_t *blk = (const uint8_t *)typed(env, a[2], &nb);
     uint32_t mode = 0; napi_get_value_uint32(env, a[4], &mode);
-    int rc = aacfb_tns_process(ctx, (const aacfb_frame_info *)typed(env, a[1], NULL), blk, nb, (float *)typed(env, a[3], NULL), mode);
-    if (rc != AACFB_OK) return fail(env, ctx, rc);
+    void *fi, *data;
+    if (!sized(env, a[1], sizeof(aacfb_frame_info), 0, "info must hold 8 bytes", &fi)) return NULL;
+    if (!sized(env, a[3], 4096, 0, "data must hold 1024 floats", &data)) return NULL;
+    int rc = aacfb_tns_process(h->ctx, (const aacfb_frame_info *)fi, blk, nb, (float *)data, mode);
+    if (rc != AACFB_OK) return fail(env, h->ctx, rc);
     return NULL;
 }
 
 static napi_value js_reset(napi_env env, napi_callback_info info) {
     size_t argc = 1; napi_value a[1];
     NAPI_OK(env, napi_get_cb_info(env, info, &argc, a, NULL, NULL));
-    aacfb_ctx *ctx = handle(env, a[0]);
-    int rc = aacfb_reset(ctx);
-    if (rc != AACFB_OK) return fail(env, ctx, rc);
+    handle_t *h = handle(env, a[0]);
+    if (!h) return NULL;
+    int rc = aacfb_reset(h->ctx);
+    if (rc != AACFB_OK) return fail(env, h->ctx, rc);
     return NULL;
 }
 
@@ -168,17 +243,23 @@ static napi_value js_reset(napi_env env, napi_callback_info info) {
 static napi_value js_get_overlap(napi_env env, napi_callback_info info) {
     size_t argc = 2; napi_value a[2];
     NAPI_OK(env, napi_get_cb_info(env, info, &argc, a, NULL, NULL));
-    aacfb_ctx *ctx = handle(env, a[0]);
-    int rc = aacfb_get_overlap(ctx, (float *)typed(env, a[1], NULL));
-    if (rc != AACFB_OK) return fail(env, ctx, rc);
+    handle_t *h = handle(env, a[0]);
+    if (!h) return NULL;
+    void *ov;
+    if (!sized(env, a[1], (size_t)h->S * h->C * 4096, 0, "overlap array must hold S*C*1024 floats", &ov)) return NULL;
+    int rc = aacfb_get_overlap(h->ctx, (float *)ov);
+    if (rc != AACFB_OK) return fail(env, h->ctx, rc);
     return NULL;
 }
 static napi_value js_set_overlap(napi_env env, napi_callback_info info) {
     size_t argc = 2; napi_value a[2];
     NAPI_OK(env, napi_get_cb_info(env, info, &argc, a, NULL, NULL));
-    aacfb_ctx *ctx = handle(env, a[0]);
-    int rc = aacfb_set_overlap(ctx, (const float *)typed(env, a[1], NULL));
-    if (rc != AACFB_OK) return fail(env, ctx, rc);
+    handle_t *h = handle(env, a[0]);
+    if (!h) return NULL;
+    void *ov;
+    if (!sized(env, a[1], (size_t)h->S * h->C * 4096, 0, "overlap array must hold S*C*1024 floats", &ov)) return NULL;
+    int rc = aacfb_set_overlap(h->ctx, (const float *)ov);
+    if (rc != AACFB_OK) return fail(env, h->ctx, rc);
     return NULL;
 }
 
@@ -187,6 +268,8 @@ static napi_value init(napi_env env, napi_value exports) {
         {"create", NULL, js_create, NULL, NULL, NULL, napi_default, NULL},
         {"process", NULL, js_process, NULL, NULL, NULL, napi_default, NULL},
         {"processStereo", NULL, js_process_stereo, NULL, NULL, NULL, napi_default, NULL},
+        {"processIo", NULL, js_process_io, NULL, NULL, NULL, napi_default, NULL},
+        {"allocPinned", NULL, js_alloc_pinned, NULL, NULL, NULL, napi_default, NULL},
         {"swbOffsets", NULL, js_swb_offsets, NULL, NULL, NULL, napi_default, NULL},
         {"adtsIndex", NULL, js_adts_index, NULL, NULL, NULL, napi_default, NULL},
         {"filterbankProcess", NULL, js_filterbank, NULL, NULL, NULL, napi_default, NULL},

@@ -30,6 +30,9 @@ napi_status napi_get_value_uint32(napi_env env, napi_value value, uint32_t *resu
 napi_status napi_create_external(napi_env env, void *data, napi_finalize finalize_cb, void *finalize_hint, napi_value *result);
 napi_status napi_create_int32(napi_env env, int32_t value, napi_value *result);
 napi_status napi_create_arraybuffer(napi_env env, size_t byte_length, void **data, napi_value *result);
+napi_status napi_create_external_arraybuffer(napi_env env, void *external_data, size_t byte_length, napi_finalize finalize_cb,
+                                             void *finalize_hint, napi_value *result);
+napi_status napi_get_null(napi_env env, napi_value *result);
 napi_status napi_create_typedarray(napi_env env, napi_typedarray_type type, size_t length, napi_value arraybuffer,
                                    size_t byte_offset, napi_value *result);
 napi_status napi_define_properties(napi_env env, napi_value object, size_t property_count, const napi_property_descriptor *properties);

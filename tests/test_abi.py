@@ -95,6 +95,6 @@ def test_napi_addon_source_compiles_against_the_header():
     assert r.returncode == 0, r.stderr
     text = open(src).read()
     for sym in ("aacfb_create", "aacfb_process", "aacfb_filterbank_process", "aacfb_tns_process", "aacfb_reset",
-                "aacfb_get_overlap", "aacfb_set_overlap", "aacfb_destroy", "aacfb_last_error", "aacfb_process_stereo",
-                "aacfb_get_swb_offsets", "aacfb_adts_index"):
+                "aacfb_get_overlap", "aacfb_set_overlap", "aacfb_destroy", "aacfb_last_error", "aacfb_process_io",
+                "aacfb_host_alloc", "aacfb_host_free", "aacfb_get_swb_offsets", "aacfb_adts_index"):
         assert sym in text

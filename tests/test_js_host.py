@@ -140,11 +140,13 @@ def test_js_batching_decoder_stages_frames_as_the_library_expects(stereo_on_devi
                   process=J.native(lambda this, a: (calls.append(("process", a)), J.UNDEF)[1]),
                   processStereo=J.native(lambda this, a: (calls.append(("processStereo", a)), J.UNDEF)[1]))
     rt = J.Runtime(js_dir, stubs={"av": sc["AV"], "aac/src/decoder": sc["AACDecoder"], "aac/src/ics": sc["ICStream"],
-                                  "aac/src/cpe": sc["CPEElement"], "./build/Release/aacfb.node": addon})
+                                  "aac/src/cpe": sc["CPEElement"], "aac/src/huffman": J.obj(), "aac/src/tables": J.obj(),
+                                  "./build/Release/aacfb.node": addon})
     B200 = rt.require("./decoder_b200")
     proto = B200.get("prototype")
     dec = B200.construct([])
     dec.put("stereoOnDevice", stereo_on_device)
+    dec.put("quantOnDevice", False)         # Float32 staging (quantised staging: test_js_quant_packer_..., test_stream_e2e)
     dec.put("framesPerChunk", 8.0)
     proto.get("setCookie").call(dec, [J.obj(chanConfig=2, sampleIndex=4)])
     assert calls[0] == ("create", [0, 1, 2, 4, 0, 0])
@@ -222,7 +224,8 @@ def test_js_batching_decoder_stages_frames_as_the_library_expects(stereo_on_devi
             assert np.array_equal(got_ops["scale"][t][:k].view(np.uint32), want_ops["scale"][t][:k].view(np.uint32))
     else:
         spectra, info, tb, to, out, n = a[1], a[2], a[3], a[4], a[5], a[6]
-    assert J.to_number(n) == T and out is pcm
+    # the library writes into the decoder's (page-locked) staging buffer; readChunk hands out a copy
+    assert J.to_number(n) == T and out.a.size == pcm.a.size and out is not pcm
     assert np.array_equal(spectra.a[:T * 2048].view(np.uint32), case["spectra"][0].reshape(-1).view(np.uint32))
     assert np.array_equal(info.a[:T * 16], want_info.view(np.uint8).reshape(-1))
     if any(b is not None for b in blocks):
@@ -235,3 +238,46 @@ def test_js_batching_decoder_stages_frames_as_the_library_expects(stereo_on_devi
     else:
         assert host_calls.count("is") == T and host_calls.count("ms") == int(sum(
             bool(case["cpe"][0, t]["common_window"] and case["cpe"][0, t]["mask_present"]) for t in range(T)))
+
+
+def test_js_quant_packer_writes_the_same_record_as_the_python_twin():
+    """js/quant_pack.js `pack` executed by the interpreter: the aacfb_qframe record it writes for an ICStream
+    equals aacjs_b200.pack_qframe's byte for byte (group lengths, band codes incl. the scalefactor-table
+    index recovered from the Float32 value, the Huffman integers)."""
+    from oracle import oracle as O
+    from tools import jsmini as J
+
+    js_dir = os.path.join(ROOT, "aac.js_b200", "js")
+    sc = J.Runtime(js_dir).run(JS_STUBS + "ICStream.ZERO_BT = 0; ICStream.FIRST_PAIR_BT = 5;")
+    sf_tab = O.dequant_table(1)
+    tables = J.obj(SCALEFACTOR_TABLE=J.float32array(sf_tab))
+    rt = J.Runtime(js_dir, stubs={"aac/src/ics": sc["ICStream"], "aac/src/huffman": J.obj(), "aac/src/tables": tables})
+    pack = rt.require("./quant_pack")
+    assert J.to_number(pack.get("RECORD_BYTES")) == A.QFRAME_DTYPE.itemsize
+    rng = np.random.default_rng(8)
+    for trial in range(6):
+        short = trial % 2 == 1
+        groups = int(rng.integers(1, 9)) if short else 1
+        glen = np.zeros(8, np.int32)
+        if short:
+            cuts = np.sort(rng.choice(np.arange(1, 8), size=groups - 1, replace=False))
+            glen[:groups] = np.diff(np.concatenate([[0], cuts, [8]]))
+        else:
+            glen[0] = 1
+        max_sfb = int(rng.integers(0, 15 if short else 50))
+        bt = rng.choice([0, 1, 3, 5, 11, 13, 14, 15], size=120).astype(np.int32)
+        sf = sf_tab[rng.integers(0, 428, 120)] * np.where(bt == 13, -1, 1).astype(np.float32)
+        sf[5] = np.float32("nan")
+        quant = rng.integers(-8191, 8192, 1024).astype(np.int16)
+        ics_py = {"info": {"windowSequence": 2 if short else 0, "groupCount": groups, "groupLength": glen, "maxSFB": max_sfb},
+                  "bandTypes": bt, "scaleFactors": sf}
+        want = A.pack_qframe(ics_py, quant)
+        ics_js = J.obj(info=J.obj(windowSequence=2 if short else 0, groupCount=groups, groupLength=J.int32array(glen), maxSFB=max_sfb),
+                       bandTypes=J.int32array(bt), scaleFactors=J.float32array(sf), quant=J.JSTyped("Int16Array", quant.copy()))
+        buf = J.JSArrayBuffer(2304 * 2)
+        rt2 = J.Runtime(js_dir)
+        env = rt2.run("var bytes = new Uint8Array(buf), view = new DataView(buf);", {"buf": buf})
+        buf.b[:] = 0xAA
+        pack.get("pack").call(J.UNDEF, [ics_js, env["bytes"], env["view"], 2304.0])
+        assert (buf.b[:2304] == 0xAA).all()
+        assert bytes(buf.b[2304:]) == want.tobytes()

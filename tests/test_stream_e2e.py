@@ -103,6 +103,88 @@ def test_batching_decoder_equals_stock_decoder_live(channels, stereo_on_device):
         assert all((c["entry"] == "aacfb_process_stereo") <= (stereo_on_device and channels == 2) for c in h.calls)
 
 
+@pytest.mark.skipif(not HAVE_REF, reason="/root/reference is not on this machine")
+@pytest.mark.parametrize("channels", [2, 1])
+def test_batching_decoder_quantised_staging_s16_adts_index_and_cpu_frames_live(channels):
+    """The round-2 additions of decoder_b200.js, each against the stock decoder's PCM, sample for sample:
+    quantOnDevice (ICStream.decodeSpectralData swapped for quant_pack.js's walk while the reference parses;
+    the oracle's restatement of ics.js:203-266 stands in for the device), int16 PCM, the ADTS frame index
+    bounding each batch (no underflow probing), and frames that have to take the reference's own CPU path
+    (a coupling element in this.cces, simulated) with the overlap state handed over in both directions."""
+    from oracle import oracle as O
+    from tools import aac_bitstream as B
+    from tools.js_reference import B200DecoderHarness, OracleLibrary, StreamReference
+
+    data = B.write_adts_stream(B.random_frames(np.random.default_rng(600 + channels), 7, channels=channels),
+                               B.codebooks(), channels=channels)
+    ref = StreamReference(data, channels=channels).decode_all()
+    for kw in (dict(quant_on_device=True), dict(quant_on_device=True, pcm_format="s16"), dict(force_cpu_frames=(2, 5)),
+               dict(quant_on_device=True, force_cpu_frames=(0, 3, 6)), dict(quant_on_device=True, adts_index=False)):
+        for K in (3, 64):
+            h = B200DecoderHarness(data, OracleLibrary(channels), channels=channels, frames_per_chunk=K, **kw)
+            got = h.decode_all()
+            if kw.get("pcm_format") == "s16":
+                assert got.dtype == np.int16 and np.array_equal(got, O.pcm_s16(ref * 32768))
+            else:
+                assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))
+            if kw.get("quant_on_device"):
+                assert all(c["entry"] == "aacfb_process_io" and "qframes" in c for c in h.calls)
+            if kw.get("adts_index", True):   # the index told readChunk how many complete frames each chunk holds
+                assert h.index_calls[0] == min(K, 7) and sum(c["info"].shape[0] for c in h.calls) + h.cpu_frames == 7
+            assert h.cpu_frames == len(kw.get("force_cpu_frames", ()))
+
+
+QGOLD = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "stream", "jsref_streamq_*.npz")))
+
+
+def load_q(path):
+    z = np.load(path)
+    C, n, seed, K, n_calls, s16 = (int(v) for v in z["meta"])
+    calls = []
+    for i in range(n_calls):
+        q = z[f"c{i}_qframes"].view(A.QFRAME_DTYPE)
+        T = q.size // C
+        calls.append({"qframes": q.reshape(T, C), "info": z[f"c{i}_info"].view(W.INFO_DTYPE).reshape(T, C),
+                      "stereo_ops": z[f"c{i}_stereo"] if z[f"c{i}_stereo"].size else None, "tns_blob": None, "tns_offsets": None,
+                      "pcm_format": s16})
+    return z, C, n, s16, calls
+
+
+@pytest.mark.parametrize("path", QGOLD, ids=os.path.basename)
+def test_oracle_replay_of_the_quantised_staged_calls_equals_the_reference_decoder(path):
+    from oracle import oracle as O
+    from tools.js_reference import OracleLibrary
+
+    z, C, n, s16, calls = load_q(path)
+    assert len(QGOLD) == 2
+    lib = OracleLibrary(C)
+    pcm = np.concatenate([lib(c).reshape(-1) for c in calls])
+    want = O.pcm_s16(z["pcm"] * 32768) if s16 else z["pcm"]
+    assert pcm.size == n * 1024 * C and np.array_equal(pcm, want)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", QGOLD, ids=os.path.basename)
+def test_gpu_replay_of_the_quantised_staged_calls_equals_the_reference_decoder(path):
+    """What decoder_b200.js staged with quantOnDevice -- aacfb_qframe records straight from the reference's
+    bit parse -- through aacfb_process_io on the GPU, against the stock decoder's PCM."""
+    z, C, n, s16, calls = load_q(path)
+    ctx = A.Context(1, C, 4, 0)
+    out = []
+    for c in calls:
+        T = c["qframes"].shape[0]
+        ops = c["stereo_ops"].view(A.STEREO_DTYPE).reshape(1, T, 1) if c["stereo_ops"] is not None else None
+        out.append(ctx.process_io(c["qframes"][None], c["info"][None], stereo_ops=ops, in_format=A.IN_Q16,
+                                  pcm_format=A.PCM_S16 if s16 else A.PCM_F32).reshape(-1))
+    ctx.close()
+    pcm, ref = np.concatenate(out), z["pcm"]
+    if s16:
+        want = np.clip(np.floor(ref.astype(np.float64) * 32768 + 0.5), -32768, 32767)
+        assert np.abs(pcm.astype(np.int32) - want).max() <= max(1, int(np.ceil(np.abs(ref).max())))   # 1e-5 * 32768 * peak < 0.5 * peak
+    else:
+        assert np.abs(pcm.astype(np.float64) - ref).max() <= TOL * max(1.0, float(np.abs(ref).max()))
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("path", GOLD, ids=os.path.basename)
 def test_gpu_replay_of_the_staged_calls_equals_the_reference_decoder(path):

@@ -169,9 +169,17 @@ class PyBitstream:
             self.pos = int(J.to_number(a[0]))
             return J.UNDEF
 
+        def peek_buffer(this, a):          # AV.Stream.peekBuffer(offset, length) -> AV.Buffer {data: Uint8Array}
+            off, n = int(J.to_number(a[0])), int(J.to_number(a[1]))
+            at = self.pos // 8 + off
+            return J.obj(data=J.JSTyped("Uint8Array", np.frombuffer(self.data[at:at + n], np.uint8).copy()))
+
+        byte_stream = J.obj(remainingBytes=J.native(lambda this, a: float(len(self.data) - self.pos // 8)),
+                            peekBuffer=J.native(peek_buffer))
         return J.obj(read=J.native(read), peek=J.native(peek), advance=J.native(advance), align=J.native(align),
                      seek=J.native(seek), offset=J.native(lambda this, a: float(self.pos)),
-                     available=J.native(lambda this, a: self.pos + int(J.to_number(a[0])) <= 8 * len(self.data)))
+                     available=J.native(lambda this, a: self.pos + int(J.to_number(a[0])) <= 8 * len(self.data)),
+                     stream=byte_stream)
 
 
 STREAM_AV_STUB = AV_STUB + """
@@ -247,36 +255,79 @@ class B200DecoderHarness:
     and returns the PCM [T][1024][C] that is written into the typed array readChunk returns."""
 
     def __init__(self, data: bytes, compute, channels=2, sample_index=4, profile=2, frames_per_chunk=4,
-                 src_dir=REF_SRC, stereo_on_device=True):
+                 src_dir=REF_SRC, stereo_on_device=True, quant_on_device=False, pcm_format="f32", adts_index=True,
+                 force_cpu_frames=()):
+        import aacjs_b200 as A
+
         js_dir = os.path.join(ROOT, "aac.js_b200", "js")
         ref = J.Runtime(src_dir)
         av = ref.run(STREAM_AV_STUB)["AV"]
         av.put("Bitstream", J.JSFunction(native=lambda this, args, new=False: args[0]))
         ref.stubs["av"] = av
-        self.calls, self.channels = [], channels
+        self.calls, self.channels, self.index_calls, self.cpu_frames = [], channels, [], 0
+        C = channels
 
-        def run(name, a, stereo):
-            spectra, info = a[1], a[2]
-            k = 1 if stereo else 0
-            n = int(J.to_number(a[6 + k]))
-            C = channels
-            call = {"spectra": spectra.a[: n * C * 1024].reshape(n, C, 1024).copy(),
-                    "info": info.a[: n * C * 8].copy().view(W.INFO_DTYPE).reshape(n, C),
-                    "stereo_ops": a[3].a[: n * 768].copy() if stereo else None,
-                    "tns_blob": a[3 + k].a.copy() if a[3 + k] not in (None, J.UNDEF) else None,
-                    "tns_offsets": a[4 + k].a[: n * C + 1].copy() if a[4 + k] not in (None, J.UNDEF) else None,
-                    "entry": name}
+        def finish(call, pcm_arr):
             if call["tns_blob"] is not None:
                 call["tns_blob"] = call["tns_blob"][: int(call["tns_offsets"][-1])]
             self.calls.append(call)
-            a[5 + k].a[:] = np.ascontiguousarray(compute(call), np.float32).reshape(-1)
+            res = compute(call)
+            pcm_arr.a[:] = np.ascontiguousarray(res, pcm_arr.a.dtype).reshape(-1)
             return J.UNDEF
 
-        addon = J.obj(create=J.native(lambda this, a: J.obj()),
-                      process=J.native(lambda this, a: run("aacfb_process", a, False)),
-                      processStereo=J.native(lambda this, a: run("aacfb_process_stereo", a, True)))
+        def opt(v, n=None):
+            if v is None or v is J.UNDEF:
+                return None
+            return v.a.copy() if n is None else v.a[:n].copy()
+
+        def run(name, a, stereo):          # process / processStereo: Float32 spectra in, Float32 PCM out
+            k = 1 if stereo else 0
+            n = int(J.to_number(a[6 + k]))
+            call = {"spectra": a[1].a[: n * C * 1024].reshape(n, C, 1024).copy(),
+                    "info": a[2].a[: n * C * 8].copy().view(W.INFO_DTYPE).reshape(n, C),
+                    "stereo_ops": a[3].a[: n * 768].copy() if stereo else None,
+                    "tns_blob": opt(a[3 + k]), "tns_offsets": opt(a[4 + k], n * C + 1), "entry": name, "pcm_format": 0}
+            return finish(call, a[5 + k])
+
+        def run_io(this, a):               # processIo(handle, input, inFormat, info, stereo, tnsBlob, tnsOffsets, pcm, pcmFormat, n)
+            in_fmt, pcm_fmt, n = int(J.to_number(a[2])), int(J.to_number(a[8])), int(J.to_number(a[9]))
+            call = {"info": a[3].a[: n * C * 8].copy().view(W.INFO_DTYPE).reshape(n, C),
+                    "stereo_ops": opt(a[4], n * 768), "tns_blob": opt(a[5]), "tns_offsets": opt(a[6], n * C + 1),
+                    "entry": "aacfb_process_io", "pcm_format": pcm_fmt}
+            if in_fmt == 1:
+                call["qframes"] = a[1].a[: n * C * 2304].copy().view(A.QFRAME_DTYPE).reshape(n, C)
+            else:
+                call["spectra"] = a[1].a[: n * C * 1024].reshape(n, C, 1024).copy()
+            return finish(call, a[7])
+
+        def adts(this, a):                 # adtsIndex(bytes, out u32 triples) -> complete frames in the buffer
+            frames, consumed = A.adts_index(a[0].a)
+            cap = a[1].a.size // 3 - 1
+            k = min(len(frames), cap)
+            for i in range(k):
+                a[1].a[3 * i: 3 * i + 3] = [frames[i]["offset"], frames[i]["frame_length"], frames[i]["header_bytes"]]
+            a[1].a[3 * k] = frames[k]["offset"] if k < len(frames) else consumed
+            self.index_calls.append(k)
+            return float(k)
+
+        def get_overlap(this, a):
+            a[1].a[:] = compute.overlap.reshape(-1)
+            return J.UNDEF
+
+        def set_overlap(this, a):
+            compute.overlap[...] = a[1].a.reshape(compute.overlap.shape)
+            return J.UNDEF
+
+        fns = dict(create=J.native(lambda this, a: J.obj()),
+                   process=J.native(lambda this, a: run("aacfb_process", a, False)),
+                   processStereo=J.native(lambda this, a: run("aacfb_process_stereo", a, True)),
+                   processIo=J.native(run_io), getOverlap=J.native(get_overlap), setOverlap=J.native(set_overlap))
+        if adts_index:
+            fns["adtsIndex"] = J.native(adts)
+        addon = J.obj(**fns)
         stubs = {"av": av, "aac/src/decoder": ref.require("./decoder"), "aac/src/ics": ref.require("./ics"),
-                 "aac/src/cpe": ref.require("./cpe"), "./build/Release/aacfb.node": addon}
+                 "aac/src/cpe": ref.require("./cpe"), "aac/src/huffman": ref.require("./huffman"),
+                 "aac/src/tables": ref.require("./tables"), "./build/Release/aacfb.node": addon}
         js = J.Runtime(js_dir, stubs=stubs)
         self.Decoder = js.require("./decoder_b200")
         self.stream = PyBitstream(data, av.get("UnderflowError"))
@@ -284,9 +335,25 @@ class B200DecoderHarness:
         self.dec.put("format", J.obj())
         self.dec.put("framesPerChunk", float(frames_per_chunk))
         self.dec.put("stereoOnDevice", bool(stereo_on_device))
+        self.dec.put("quantOnDevice", bool(quant_on_device))
+        self.dec.put("pcmFormat", pcm_format)
         cookie = bytes([(profile << 3) | ((sample_index >> 1) & 7), ((sample_index & 1) << 7) | (channels << 3), 0])
         self.Decoder.get("prototype").get("setCookie").call(self.dec, [PyBitstream(cookie, av.get("UnderflowError")).js()])
         self.dec.put("bitstream", self.stream.js())
+        if force_cpu_frames:
+            # make stage() see a coupling element on the given access units: the frame then has to take the
+            # reference's CPU path (cpuFrame), which re-parses it and finds none -- same PCM as the stock decoder
+            proto_stage = self.Decoder.get("prototype").get("stage")
+            count = [0]
+
+            def stage(this, a):
+                count[0] += 1
+                if count[0] - 1 in force_cpu_frames:
+                    this.put("cces", J.JSArray([J.obj()]))
+                    self.cpu_frames += 1
+                return proto_stage.call(this, a)
+
+            self.dec.put("stage", J.native(stage))
 
     def decode_all(self):
         out = []
@@ -307,7 +374,10 @@ class OracleLibrary:
         self.overlap = np.zeros((1, channels, 1024), np.float32)
 
     def __call__(self, call):
-        sp = call["spectra"].copy()
+        if "qframes" in call:   # inverse quantisation first (ics.js:203-266), like the device
+            sp = self.O.dequant_batch(call["qframes"], call["info"], self.si)
+        else:
+            sp = call["spectra"].copy()
         if call["stereo_ops"] is not None:
             recs = call["stereo_ops"].view(np.dtype([("op", "u1", (256,)), ("scale", "f4", (128,))]))
             for t in range(sp.shape[0]):
@@ -319,8 +389,9 @@ class OracleLibrary:
                 sp[t, 0][ms] = l[ms] + r[ms]
                 sp[t, 1][ms] = l[ms] - r[ms]
                 sp[t, 1][it] = l[it] * recs[t]["scale"][op[it] - 2]
-        pcm, self.overlap = self.O.process(sp[None], call["info"][None], call["tns_blob"], call["tns_offsets"],
-                                           self.overlap, sample_index=self.si, flags=self.flags)
+        pcm, self.overlap = self.O.process_io(sp[None], 0, call["info"][None], call["tns_blob"], call["tns_offsets"],
+                                              self.overlap, pcm_format=call.get("pcm_format", 0), sample_index=self.si,
+                                              flags=self.flags)
         return pcm[0]
 
 
@@ -615,6 +686,32 @@ def main_stream():
         print(name, len(data), "bytes,", n, "frames,", len(h.calls), "calls, peak", float(np.abs(ref).max()))
 
 
+def main_stream_quant():
+    """tests/golden/stream/jsref_streamq_*.npz: the same experiment with quantOnDevice -- the batching decoder
+    swaps ICStream.decodeSpectralData for quant_pack.js's walk while the reference parses, stages
+    aacfb_qframe records (Huffman integers + band codes) and, for the s16 case, asks for int16 PCM.  With
+    the oracle as the library (its decode_spectral_data restates ics.js:203-266) the output equals the
+    stock decoder's bit for bit; the staged records are replayed through the CUDA library on the GPU box."""
+    from tools import aac_bitstream as B
+    from oracle import oracle as O
+
+    out_dir = os.path.join(ROOT, "tests", "golden", "stream")
+    for name, C, n, seed, K, fmt in (("stereo", 2, 12, 401, 5, "f32"), ("mono_s16", 1, 8, 402, 3, "s16")):
+        data = B.write_adts_stream(B.random_frames(np.random.default_rng(seed), n, channels=C), B.codebooks(), channels=C)
+        ref = StreamReference(data, channels=C).decode_all()
+        h = B200DecoderHarness(data, OracleLibrary(C), channels=C, frames_per_chunk=K, quant_on_device=True, pcm_format=fmt)
+        got = h.decode_all()
+        want = O.pcm_s16(ref * 32768) if fmt == "s16" else ref
+        assert np.array_equal(want.view(np.uint16 if fmt == "s16" else np.uint32), got.view(np.uint16 if fmt == "s16" else np.uint32))
+        arrays = {"adts": np.frombuffer(data, np.uint8), "pcm": ref, "meta": np.array([C, n, seed, K, len(h.calls), int(fmt == "s16")])}
+        for i, c in enumerate(h.calls):
+            arrays[f"c{i}_qframes"] = c["qframes"].view(np.uint8).reshape(-1)
+            arrays[f"c{i}_info"] = c["info"].view(np.uint8).reshape(-1)
+            arrays[f"c{i}_stereo"] = c["stereo_ops"] if c["stereo_ops"] is not None else np.zeros(0, np.uint8)
+        np.savez_compressed(os.path.join(out_dir, f"jsref_streamq_{name}.npz"), **arrays)
+        print(name, len(data), "bytes,", n, "frames,", len(h.calls), "calls, peak", float(np.abs(ref).max()))
+
+
 def main_adts():
     """ADTSDemuxer.readHeader run by the interpreter on every frame of a seeded synthetic ADTS stream."""
     out_dir = os.path.join(ROOT, "tests", "golden", "adts")
@@ -727,4 +824,4 @@ def main_dequant():
 
 
 if __name__ == "__main__":
-    {"stereo": main_stereo, "adts": main_adts, "decoder": main_decoder, "stream": main_stream, "dequant": main_dequant}.get((sys.argv[1:] or [""])[0], main)()
+    {"stereo": main_stereo, "adts": main_adts, "decoder": main_decoder, "stream": main_stream, "streamq": main_stream_quant, "dequant": main_dequant}.get((sys.argv[1:] or [""])[0], main)()
