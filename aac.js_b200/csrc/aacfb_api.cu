@@ -63,6 +63,8 @@ struct aacfb_ctx {
     size_t cap_dev_stereo_out = 0;
     float *d_dev_deq = nullptr;         // inverse-quantisation pre-pass output of the device-pointer path
     size_t cap_dev_deq = 0;
+    float *d_tns_ring[kLanes + 1] = {};  // synth_tns_kernel: the CTAs' rings of filtered rows, one set per lane stream
+                                         // (+ one for the device-pointer path), allocated on first use
     uint64_t launches = 0;
     char err[256] = "";
 };
@@ -102,8 +104,9 @@ struct DeviceGuard {
 // (frames cost the same, so equal static shares balance perfectly and cost one halo frame each);
 // tiny batches use fewer, longer slices so that the halo stays below ~1/8 of the work.
 // AACFB_SLICE_LEN overrides (tuning aid).
-int pick_slice(int n_pairs, int T, int workers) {
-    if (const char *env = std::getenv("AACFB_SLICE_LEN")) {
+// exact: the number of items must not exceed `workers` (synth_tns_kernel: one item per client), so no override
+int pick_slice(int n_pairs, int T, int workers, bool exact = false) {
+    if (const char *env = exact ? nullptr : std::getenv("AACFB_SLICE_LEN")) {
         const int v = std::atoi(env);
         if (v >= 1) return v;
     }
@@ -174,12 +177,28 @@ int enqueue(aacfb_ctx *ctx, Job j, cudaStream_t stream) {
         j.d_spectra = j.d_stereo_out;
         j.d_stereo = nullptr;
     }
-    if (tns_on) {
-        TnsParams tp{};
-        tp.spectra = j.d_spectra; tp.scratch = j.d_scratch; tp.ranges = j.d_ranges; tp.info = j.d_info; tp.blob = j.d_blob;
-        tp.offsets = j.d_offsets;
-        tp.blob_bytes = j.blob_bytes; tp.n_cf = n_cf; tp.sample_index = ctx->sample_index;
-        tp.ar = mode == AACFB_TNS_FIXED_AR; tp.bands = ctx->d_bands;
+    // TNS inside the synthesis kernel (synth_tns_kernel) when the rows are floats of two-channel streams with float
+    // PCM: no round trip of the filtered coefficients through HBM.  Items with EIGHT_SHORT frames are left to the
+    // pre-pass + generic instantiation, which then run gated on the count the fused kernel leaves (a batch whose
+    // window sequences the caller has seen -- no_short -- spares those launches).
+    // OPT-IN (AACFB_TNS_FUSED=1): parity-green, but measured 2 x slower than pre-pass + synthesis on config 4
+    // (0.82 ms against 0.41 ms: the one filtering worker per CTA needs ~8700 cycles per 32-coefficient tile where the
+    // chain alone takes 1570 -- DESIGN.md section 8), so the pre-pass stays the default.
+    static const bool fuse_env = [] { const char *e = std::getenv("AACFB_TNS_FUSED"); return e && std::atoi(e) != 0; }();
+    const bool fused = tns_on && fuse_env && j.nc == 2 && !j.d_q && !j.d_stereo && !j.s16 && !j.in_place_state;
+    int ring_i = kLanes;   // kernels of different lanes may overlap at their tails: each lane stream has its own rings
+    for (int i = 0; i < kLanes; ++i)
+        if (ctx->lane[i].stream == stream) ring_i = i;
+    if (fused && !ctx->d_tns_ring[ring_i])
+        CU(ctx, cudaMalloc(&ctx->d_tns_ring[ring_i], tns_ring_floats(ctx->num_sms) * sizeof(float)));
+    unsigned *slots = ctx->d_counters + 4 * (ctx->counter_next++ % (kCounters / 4));
+    TnsParams tp{};
+    tp.spectra = j.d_spectra; tp.scratch = j.d_scratch; tp.ranges = j.d_ranges; tp.info = j.d_info; tp.blob = j.d_blob;
+    tp.offsets = j.d_offsets;
+    tp.blob_bytes = j.blob_bytes; tp.n_cf = n_cf; tp.sample_index = ctx->sample_index;
+    tp.ar = mode == AACFB_TNS_FIXED_AR; tp.bands = ctx->d_bands;
+    tp.gate = fused ? slots + 2 : nullptr;
+    if (tns_on && !fused) {
         CU(ctx, launch_tns(tp, stream));
         ctx->launches++;
     }
@@ -192,17 +211,31 @@ int enqueue(aacfb_ctx *ctx, Job j, cudaStream_t stream) {
     sp.ovl_out = j.in_place_state ? ctx->d_ovl[ctx->cur] : ctx->d_ovl[ctx->cur ^ 1];
     sp.tab = j.scale == 1.0f ? ctx->d_tab_unit : ctx->d_tab;
     const int n_pairs = (j.S_sub * j.nc + 1) / 2;
-    // in-place state (inner seam): one item, so the state is read before it is written
-    const int Q = j.in_place_state ? n_pairs * j.T : pick_slice(n_pairs, j.T, ctx->num_sms * kWorkers);
+    // in-place state (inner seam): one item, so the state is read before it is written.  Fused: one item per client.
+    const int Q = j.in_place_state ? n_pairs * j.T
+                                   : pick_slice(n_pairs, j.T, ctx->num_sms * (fused ? kFusedClients : kWorkers), fused);
     sp.g = make_geometry(j.S_sub, j.T, j.nc, ctx->C, j.c0, j.s_base, Q);
     sp.scale = j.scale;
     // Two instantiations walk the same item list: the long-only one takes the items without
     // EIGHT_SHORT frames, the generic one the rest (each item is classified on the device).
     // If the long-only pass finds no such item the generic pass exits at once; a caller that has
     // looked at every window_sequence itself (the host path's validation) spares that launch.
-    unsigned *slots = ctx->d_counters + 4 * (ctx->counter_next++ % (kCounters / 4));
     CU(ctx, cudaMemsetAsync(slots, 0, 4 * sizeof(unsigned), stream));
     sp.short_items = slots + 2;
+    if (fused) {
+        sp.tns_ring = ctx->d_tns_ring[ring_i]; sp.tns_blob = j.d_blob; sp.tns_offsets = j.d_offsets; sp.tns_blob_bytes = j.blob_bytes;
+        sp.tns_bands = ctx->d_bands; sp.tns_ar = tp.ar; sp.sample_index = ctx->sample_index;
+        sp.counter = slots;
+        CU(ctx, launch_synth_tns(sp, ctx->num_sms, stream));
+        ctx->launches++;
+        if (!j.no_short) {   // only does anything if the fused kernel counted an item with an EIGHT_SHORT frame
+            CU(ctx, launch_tns(tp, stream));
+            sp.counter = slots + 1;
+            CU(ctx, launch_synth(sp, ctx->num_sms, true, stream));
+            ctx->launches += 2;
+        }
+        return AACFB_OK;
+    }
     for (int generic = 0; generic < (j.no_short ? 1 : 2); ++generic) {
         sp.counter = slots + generic;
         CU(ctx, launch_synth(sp, ctx->num_sms, generic != 0, stream));
@@ -482,6 +515,7 @@ API int aacfb_destroy(aacfb_ctx *ctx) {
         cudaFree(ln.d_stereo); cudaFree(ln.d_stereo_out); cudaFree(ln.d_deq);
     }
     cudaFree(ctx->d_dev_stereo_out); cudaFree(ctx->d_dev_deq); cudaFree(ctx->d_dq);
+    for (float *r : ctx->d_tns_ring) cudaFree(r);
     cudaFree(ctx->d_ovl[0]); cudaFree(ctx->d_ovl[1]); cudaFree(ctx->d_tab); cudaFree(ctx->d_tab_unit); cudaFree(ctx->d_bands);
     cudaFree(ctx->d_counters); cudaFree(ctx->d_blob); cudaFree(ctx->d_dev_scratch);
     delete ctx;

@@ -39,6 +39,14 @@ struct SynthParams {
     unsigned *counter;              // zeroed before launch (one per kernel instantiation)
     unsigned *short_items;          // zeroed; number of items with EIGHT_SHORT frames (set by the long-only pass)
     float scale;
+    // synth_tns_kernel only (TNS filtered inside the synthesis kernel, no pre-pass):
+    float *tns_ring;                // per CTA 2 x kFusedRingRows rows of 1024 floats: the filtered rows in flight
+    const uint8_t *tns_blob;        // packed TNS blocks + offsets, as in TnsParams
+    const uint32_t *tns_offsets;
+    size_t tns_blob_bytes;
+    const TnsBandTables *tns_bands;
+    int tns_ar;                     // 1: all-pole branch, 0: MA branch
+    int sample_index;
 };
 
 struct TnsParams {
@@ -53,6 +61,7 @@ struct TnsParams {
     int sample_index;
     int ar;                         // 1: all-pole branch (decode=true), 0: MA branch
     const TnsBandTables *bands;
+    const unsigned *gate;           // != nullptr: run only if *gate != 0 (items the fused kernel left to the generic pass)
 };
 
 struct StereoParams {            // stereo tools as a pre-pass (only when TNS has to run between them and the IMDCT)
@@ -73,6 +82,12 @@ cudaError_t launch_dequant(const DequantParams &P, cudaStream_t stream);
 cudaError_t launch_stereo(const StereoParams &P, cudaStream_t stream);
 cudaError_t launch_synth(const SynthParams &P, int num_sms, bool generic, cudaStream_t stream);
 cudaError_t launch_tns(const TnsParams &P, cudaStream_t stream);
+// TNS + synthesis in one kernel (float rows, two channels, items without EIGHT_SHORT frames; the others are
+// counted in P.short_items and left to the pre-pass + generic instantiation).
+constexpr int kFusedClients = kWorkers - 1;   // synthesis workers per CTA; the last worker filters
+constexpr int kFusedRingRows = 128;           // rows per ring slot (two per lane of the filtering worker)
+cudaError_t launch_synth_tns(const SynthParams &P, int num_sms, cudaStream_t stream);
+size_t tns_ring_floats(int num_sms);
 int synth_smem_bytes();
 
 }  // namespace aacfb

@@ -290,7 +290,7 @@ def roofline_record(workload, alg, launch_ms, tns, traffic_tab):
     t = traffic_tab.get(workload)
     return {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
             "traffic": t, "traffic_source": traffic_tab.get("_source") if t else None, "peak_source": peak_src,
-            "kernel": "aacfb::synth_kernel" + (" (TNS fused)" if tns else ""),
+            "kernel": "aacfb::tns_kernel + aacfb::synth_kernel" if tns else "aacfb::synth_kernel",
             "algorithmic_bytes_per_launch": alg, "launch_ms": launch_ms}
 
 

@@ -184,9 +184,14 @@ def test_gpu_stereo_tools_fused_into_synthesis(S, T):
 @pytest.mark.gpu
 @pytest.mark.parametrize("mode", [A.TNS_FIXED_AR, A.TNS_FIXED_MA])
 def test_gpu_stereo_tools_before_tns(mode):
-    """TNS runs between the stereo tools and the IMDCT (decoder.js:300-319): pre-pass kernel."""
+    """TNS runs between the stereo tools and the IMDCT (decoder.js:300-319): stereo pre-pass, TNS pre-pass,
+    long-only and generic instantiation.  AACFB_TNS_FUSED=1 (opt-in): stereo pre-pass kernel, then the synthesis
+    kernel that filters its own rows (synth_tns_kernel; with an EIGHT_SHORT frame in the batch also the TNS
+    pre-pass and the generic instantiation for the items that have one)."""
     case = W.random_stereo_case(5, 11, np.random.default_rng(200 + mode), tns_mode=mode, sigma=2e4)
-    assert gpu_vs_oracle(case, 5, 11, mode) == (4 if (case["info"]["window_sequence"] == 2).any() else 3)
+    any_short = (case["info"]["window_sequence"] == 2).any()
+    fused = os.environ.get("AACFB_TNS_FUSED", "0") != "0"
+    assert gpu_vs_oracle(case, 5, 11, mode) == ((4 if any_short else 2) if fused else (4 if any_short else 3))
 
 
 @pytest.mark.gpu
