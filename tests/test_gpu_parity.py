@@ -51,6 +51,28 @@ def test_baseline_configs_small(cfg, S, T, C):
     check(W.make(cfg, S, T, C, seed=cfg, shape_prev_mode="carried"), S, T, C)
 
 
+@pytest.mark.parametrize("slice_len", [7, 40, 97, 1000])
+def test_runs_of_long_and_short_frames_inside_an_item(slice_len, monkeypatch):
+    """Work items of different lengths (AACFB_SLICE_LEN: shorter than a block of EIGHT_SHORT frames, longer than
+    32 frames, longer than a stream, the whole batch as one item) over streams that mix the two kinds of
+    frames in every way: EIGHT_SHORT blocks at the first / last frame of a stream, cut by items and by pair
+    boundaries, one chain of a pair-frame short and the other not, streams without any, one all EIGHT_SHORT."""
+    monkeypatch.setenv("AACFB_SLICE_LEN", str(slice_len))
+    S, T, C = 6, 150, 2
+    rng = np.random.default_rng(slice_len)
+    w = W.random_case(S, T, C, rng)
+    seq = w["info"]["window_sequence"]
+    seq[0] = 0                                    # stream 0: ONLY_LONG throughout
+    seq[1] = W.config5_sequence(T)[:, None]       # stream 1: the config-5 pattern
+    seq[2] = 0
+    seq[2, :2] = 2; seq[2, 2] = 3; seq[2, -3] = 1; seq[2, -2:] = 2   # blocks at both ends of the stream
+    seq[3] = 2                                    # all EIGHT_SHORT
+    seq[4] = 0
+    seq[4, 70] = 1; seq[4, 71, 0] = 2; seq[4, 71, 1] = 3; seq[4, 72] = 3   # one chain of a pair-frame short, the other not
+    w["info"]["max_sfb"] = np.where(seq == 2, 14, 49)
+    check(w, S, T, C, seed=slice_len)
+
+
 @pytest.mark.parametrize("mode", [0, 1, 2])
 @pytest.mark.parametrize("S,T,C", [(2, 6, 2), (3, 4, 5), (1, 9, 1), (37, 33, 2)])
 def test_random_sequences_shapes_and_tns(mode, S, T, C):
