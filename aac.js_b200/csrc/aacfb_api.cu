@@ -28,6 +28,8 @@ thread_local char g_err[256] = "";
 
 struct Lane {                    // device staging of one in-flight sub-batch of the host path
     cudaStream_t stream = nullptr;
+    // copy streams (aacfb_process_io): inputs landed / kernels done (inputs free, PCM ready) / PCM copied out
+    cudaEvent_t ev_in = nullptr, ev_k = nullptr, ev_out = nullptr;
     float *d_spectra = nullptr, *d_pcm = nullptr, *d_scratch = nullptr;
     aacfb_frame_info *d_info = nullptr;
     uint32_t *d_offsets = nullptr;
@@ -55,6 +57,7 @@ struct aacfb_ctx {
     unsigned *d_counters = nullptr;
     unsigned counter_next = 0;
     Lane lane[kLanes];
+    cudaStream_t h2d = nullptr, d2h = nullptr;   // one stream per PCIe direction for the host path's copies
     uint8_t *d_blob = nullptr;
     size_t cap_blob = 0;
     float *d_dev_scratch = nullptr;  // scratch of the device-pointer path
@@ -497,9 +500,14 @@ API int aacfb_create(aacfb_ctx **out, int device, int n_streams, int channels, i
         if (e != cudaSuccess) return bail(e, "dequant tables");
     }
     if ((e = cudaMalloc(&ctx->d_counters, kCounters * sizeof(unsigned))) != cudaSuccess) return bail(e, "cudaMalloc");
-    for (int i = 0; i < kLanes; ++i)
-        if ((e = cudaStreamCreateWithFlags(&ctx->lane[i].stream, cudaStreamNonBlocking)) != cudaSuccess)
-            return bail(e, "cudaStreamCreate");
+    for (int i = 0; i < kLanes; ++i) {
+        Lane &ln = ctx->lane[i];
+        if ((e = cudaStreamCreateWithFlags(&ln.stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
+        for (cudaEvent_t *ev : {&ln.ev_in, &ln.ev_k, &ln.ev_out})
+            if ((e = cudaEventCreateWithFlags(ev, cudaEventDisableTiming)) != cudaSuccess) return bail(e, "cudaEventCreate");
+    }
+    for (cudaStream_t *st : {&ctx->h2d, &ctx->d2h})
+        if ((e = cudaStreamCreateWithFlags(st, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
     *out = ctx;
     return AACFB_OK;
 }
@@ -511,9 +519,13 @@ API int aacfb_destroy(aacfb_ctx *ctx) {
     for (int i = 0; i < kLanes; ++i) {
         Lane &ln = ctx->lane[i];
         if (ln.stream) cudaStreamDestroy(ln.stream);
+        for (cudaEvent_t ev : {ln.ev_in, ln.ev_k, ln.ev_out})
+            if (ev) cudaEventDestroy(ev);
         cudaFree(ln.d_spectra); cudaFree(ln.d_pcm); cudaFree(ln.d_scratch); cudaFree(ln.d_info); cudaFree(ln.d_offsets);
         cudaFree(ln.d_stereo); cudaFree(ln.d_stereo_out); cudaFree(ln.d_deq);
     }
+    if (ctx->h2d) cudaStreamDestroy(ctx->h2d);
+    if (ctx->d2h) cudaStreamDestroy(ctx->d2h);
     cudaFree(ctx->d_dev_stereo_out); cudaFree(ctx->d_dev_deq); cudaFree(ctx->d_dq);
     for (float *r : ctx->d_tns_ring) cudaFree(r);
     cudaFree(ctx->d_ovl[0]); cudaFree(ctx->d_ovl[1]); cudaFree(ctx->d_tab); cudaFree(ctx->d_tab_unit); cudaFree(ctx->d_bands);
@@ -659,15 +671,22 @@ API int aacfb_process_io(aacfb_ctx *ctx, const void *input, uint32_t in_format, 
     int rc;
     // Sub-batches of whole streams, two in flight: the copy-in of one overlaps
     // the kernel and copy-out of the other (PCIe is the bottleneck end to end).
-    // 16 equal sub-batches: measured best on B200 / PCIe 5 (8: +0.5 %, 32: +5 %, 64: +18 % time; a
-    // ramp of small first/last sub-batches: no gain).  The copies then run at 43 GB/s each way against
-    // 49.9 GB/s for two large concurrent copies (tools/pcie_bw.py).
+    // Equal sub-batches (a ramp of small first/last sub-batches: no gain); their number: below.
+    // The copies of ALL sub-batches run on two streams of their own, one per PCIe direction, tied to the lanes'
+    // kernels by events: with everything of a sub-batch on its lane's stream the next copy-in of a lane had to
+    // wait for the lane's copy-out (stream order), and the H2D link idled for (kernel + launch gaps) per
+    // sub-batch -- 7.2 ms instead of the ~6.5 ms the link allows for 303 MB in / 268 MB out.
+    // AACFB_COPY_STREAMS=0: the lane-ordered pipeline (A/B).
+    static const bool copy_streams = [] { const char *e = std::getenv("AACFB_COPY_STREAMS"); return !e || std::atoi(e) != 0; }();
     int lanes = 2;
     std::vector<int> parts;   // streams per sub-batch
-    int n_sub = std::min(S, 16);
+    // Sub-batch count: about 68 MB (in + out) each, between 8 and 16 -- measured on config 2: float in / float out
+    // (1075 MB) 16 sub-batches 12.22 ms, 8: 12.50; aacfb_qframe in / int16 out (571 MB) 8: 6.95 ms, 16: 7.02, 32: 7.89.
+    const size_t total_bytes = n_all * (in_bytes + out_bytes);
+    int n_sub = std::min(S, (int)std::min<size_t>(16, std::max<size_t>(8, (total_bytes + (34u << 20)) / (68u << 20))));
     if (const char *env = std::getenv("AACFB_SUB_BATCHES")) n_sub = std::max(1, std::min(S, std::atoi(env)));   // tuning aids
     if (const char *env = std::getenv("AACFB_LANES")) lanes = std::atoi(env) >= 4 ? 4 : std::atoi(env) >= 2 ? 2 : 1;  // divisors of the counter ring
-    if (n_all * (in_bytes + out_bytes) < (size_t)(16u << 20)) n_sub = 1;
+    if (total_bytes < (size_t)(16u << 20)) n_sub = 1;
     for (int i = 0, done = 0; i < n_sub; ++i) {
         const int upto = (int)((long long)S * (i + 1) / n_sub);
         if (upto > done) parts.push_back(upto - done);
@@ -690,7 +709,9 @@ API int aacfb_process_io(aacfb_ctx *ctx, const void *input, uint32_t in_format, 
     // caller's buffers are referenced by copies in flight) and leaves ctx->cur -- the overlap state
     // the next call starts from -- untouched.
     auto drain = [&](int code) {
+        cudaStreamSynchronize(ctx->h2d);
         for (int i = 0; i < kLanes; ++i) cudaStreamSynchronize(ctx->lane[i].stream);
+        cudaStreamSynchronize(ctx->d2h);
         return code;
     };
     if (tns_on) {
@@ -716,19 +737,28 @@ API int aacfb_process_io(aacfb_ctx *ctx, const void *input, uint32_t in_format, 
             return drain(fail(ctx, AACFB_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__)); \
     } while (0)
     int li = 0, s0 = 0;
+    bool used[kLanes] = {};
     for (size_t pi = 0; pi < parts.size(); s0 += parts[pi], ++pi, li = (li + 1) % lanes) {
         Lane &ln = ctx->lane[li];
         const int sn = parts[pi];
         const size_t n_cf = (size_t)sn * per_stream, off = (size_t)s0 * per_stream;
         if (!whole_check && (rc = check(off, off + n_cf)) != AACFB_OK) return drain(rc);
-        // stream order makes reuse of this lane's buffers safe
-        CUD(cudaMemcpyAsync(ln.d_spectra, in8 + off * in_bytes, n_cf * in_bytes, cudaMemcpyHostToDevice, ln.stream));
-        CUD(cudaMemcpyAsync(ln.d_info, info + off, n_cf * sizeof(aacfb_frame_info), cudaMemcpyHostToDevice, ln.stream));
+        // lane-ordered: stream order makes reuse of this lane's buffers safe.  Copy streams: the lane's inputs are
+        // free once its previous kernels are done, its PCM buffer once the previous copy-out is.
+        cudaStream_t sin = copy_streams ? ctx->h2d : ln.stream, sout = copy_streams ? ctx->d2h : ln.stream;
+        if (copy_streams && used[li]) CUD(cudaStreamWaitEvent(sin, ln.ev_k, 0));
+        CUD(cudaMemcpyAsync(ln.d_spectra, in8 + off * in_bytes, n_cf * in_bytes, cudaMemcpyHostToDevice, sin));
+        CUD(cudaMemcpyAsync(ln.d_info, info + off, n_cf * sizeof(aacfb_frame_info), cudaMemcpyHostToDevice, sin));
         if (tns_on)
-            CUD(cudaMemcpyAsync(ln.d_offsets, tns_offsets + off, (n_cf + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, ln.stream));
+            CUD(cudaMemcpyAsync(ln.d_offsets, tns_offsets + off, (n_cf + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, sin));
         if (stereo_ops)
             CUD(cudaMemcpyAsync(ln.d_stereo, stereo_ops + off / 2, (n_cf / 2) * sizeof(aacfb_stereo_ops),
-                                cudaMemcpyHostToDevice, ln.stream));
+                                cudaMemcpyHostToDevice, sin));
+        if (copy_streams) {
+            CUD(cudaEventRecord(ln.ev_in, sin));
+            CUD(cudaStreamWaitEvent(ln.stream, ln.ev_in, 0));
+            if (used[li]) CUD(cudaStreamWaitEvent(ln.stream, ln.ev_out, 0));
+        }
         Job j;
         if (q16) { j.d_q = reinterpret_cast<const aacfb_qframe *>(ln.d_spectra); j.d_deq = ln.d_deq; }
         else j.d_spectra = ln.d_spectra;
@@ -740,10 +770,18 @@ API int aacfb_process_io(aacfb_ctx *ctx, const void *input, uint32_t in_format, 
         j.scale = s16 ? 1.0f : 1.0f / 32768.0f;
         j.no_short = whole_check && !any_short;
         if ((rc = enqueue(ctx, j, ln.stream)) != AACFB_OK) return drain(rc);
-        CUD(cudaMemcpyAsync(out8 + off * out_bytes, ln.d_pcm, n_cf * out_bytes, cudaMemcpyDeviceToHost, ln.stream));
+        if (copy_streams) {
+            CUD(cudaEventRecord(ln.ev_k, ln.stream));
+            CUD(cudaStreamWaitEvent(sout, ln.ev_k, 0));
+        }
+        CUD(cudaMemcpyAsync(out8 + off * out_bytes, ln.d_pcm, n_cf * out_bytes, cudaMemcpyDeviceToHost, sout));
+        if (copy_streams) CUD(cudaEventRecord(ln.ev_out, sout));
+        used[li] = true;
     }
 #undef CUD
+    CU(ctx, cudaStreamSynchronize(ctx->h2d));
     for (int i = 0; i < kLanes; ++i) CU(ctx, cudaStreamSynchronize(ctx->lane[i].stream));
+    CU(ctx, cudaStreamSynchronize(ctx->d2h));
     ctx->cur ^= 1;
     return AACFB_OK;
 }

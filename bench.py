@@ -275,8 +275,8 @@ def time_steps(torch, step, steps, warmup, stream, barrier):
 
 def load_traffic():
     """Measured DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum of one
-    `ncu --set full` capture per workload; profiles/traffic.json is written by tools/ncu_traffic.py
-    from the committed captures -- a profiler cannot run inside a timed bench)."""
+    `ncu --set full` capture per kernel; profiles/traffic.json is written by tools/refresh_profiles.py
+    from the captures of tools/gpu_capture.sh -- a profiler cannot run inside a timed bench)."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
     try:
         return json.load(open(p))
