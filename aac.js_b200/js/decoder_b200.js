@@ -123,7 +123,7 @@ var B200Decoder = AACDecoder.extend(function() {
             else {
                 var onDevice = false;
                 if (this.deviceStereo) {
-                    var at = t * stereoPack.RECORD_BYTES;
+                    var at = (this.stereoBase || 0) + t * stereoPack.RECORD_BYTES;   // (stereoBase: decoder_pool.js)
                     onDevice = stereoPack.pack(e, new Uint8Array(this.stereoBuf, at, 256),
                                                new Float32Array(this.stereoBuf, at + 256, 128));
                     if (onDevice) this.anyStereo = true;

@@ -134,6 +134,38 @@ def test_batching_decoder_quantised_staging_s16_adts_index_and_cpu_frames_live(c
             assert h.cpu_frames == len(kw.get("force_cpu_frames", ()))
 
 
+@pytest.mark.skipif(not HAVE_REF, reason="/root/reference is not on this machine")
+@pytest.mark.parametrize("channels,kw", [(2, dict()), (1, dict(pcm_format="s16")),
+                                         (2, dict(quant_on_device=False, stereo_on_device=False, adts_index=False))])
+def test_decoder_pool_equals_the_stock_decoder_on_every_stream_live(channels, kw):
+    """decoder_pool.js: S decoders in lock step behind ONE library context (the operating point bench.py
+    measures).  Three streams of different lengths, each parsed by the reference's own code; every round is one
+    addon call over [S][T][C] with T what every stream can deliver; each stream's PCM equals the stock
+    decoder's, sample for sample, for as many frames as the shortest stream has."""
+    from oracle import oracle as O
+    from tools import aac_bitstream as B
+    from tools.js_reference import B200PoolHarness, OracleLibrary, StreamReference
+
+    lengths = (4, 3, 5)
+    streams = [B.write_adts_stream(B.random_frames(np.random.default_rng(700 + 10 * channels + i), n, channels=channels),
+                                   B.codebooks(), channels=channels) for i, n in enumerate(lengths)]
+    refs = [StreamReference(d, channels=channels).decode_all() for d in streams]
+    for K in (2, 64):
+        h = B200PoolHarness(streams, OracleLibrary(channels, n_streams=3), channels=channels, frames_per_chunk=K, **kw)
+        got = h.decode_all()
+        assert h.created == [[0, 3, channels, 4, 0, 0]]           # one context, n_streams = 3
+        n = min(lengths) * 1024 * channels                         # the pool stops when a stream runs dry
+        for s in range(3):
+            if kw.get("pcm_format") == "s16":
+                assert got[s].dtype == np.int16 and np.array_equal(got[s], O.pcm_s16(refs[s][:n] * 32768))
+            else:
+                assert got[s].size == n and np.array_equal(got[s].view(np.uint32), refs[s][:n].view(np.uint32))
+        assert [c["info"].shape[:2] for c in h.calls] == [(3, t) for t in ([2, 1] if K == 2 else [3])]
+        assert all(("qframes" in c) == kw.get("quant_on_device", True) for c in h.calls)
+        # nothing beyond the delivered frames was consumed: the longer streams continue where the pool left them
+        assert h.read_chunks() is None
+
+
 QGOLD = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "stream", "jsref_streamq_*.npz")))
 
 

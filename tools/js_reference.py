@@ -362,37 +362,149 @@ class B200DecoderHarness:
         return np.concatenate(out) if out else np.zeros(0, np.float32)
 
 
+class B200PoolHarness:
+    """aac.js_b200/js/decoder_pool.js -- S pooled decoders, one library context -- run by the interpreter on
+    top of the unmodified reference with a stand-in for the addon.  `compute(call)` plays the library for a
+    batch: arrays shaped [S][T][C]... as aacfb_process* takes them; it returns PCM [S][T][1024][C]."""
+
+    def __init__(self, streams, compute, channels=2, sample_index=4, profile=2, frames_per_chunk=4, src_dir=REF_SRC,
+                 stereo_on_device=True, quant_on_device=True, pcm_format="f32", adts_index=True):
+        import aacjs_b200 as A
+
+        js_dir = os.path.join(ROOT, "aac.js_b200", "js")
+        ref = J.Runtime(src_dir)
+        av = ref.run(STREAM_AV_STUB)["AV"]
+        av.put("Bitstream", J.JSFunction(native=lambda this, args, new=False: args[0]))
+        ref.stubs["av"] = av
+        S, C = len(streams), channels
+        self.calls, self.S, self.C, self.created = [], S, C, []
+
+        def opt(v, n=None):
+            if v is None or v is J.UNDEF:
+                return None
+            return v.a.copy() if n is None else v.a[:n].copy()
+
+        def finish(call, pcm_arr):
+            if call["tns_blob"] is not None:
+                call["tns_blob"] = call["tns_blob"][: int(call["tns_offsets"][-1])]
+            self.calls.append(call)
+            pcm_arr.a[:] = np.ascontiguousarray(compute(call), pcm_arr.a.dtype).reshape(-1)
+            return J.UNDEF
+
+        def run(name, a, stereo):
+            k = 1 if stereo else 0
+            T = int(J.to_number(a[6 + k]))
+            n = S * T * C
+            call = {"spectra": a[1].a[: n * 1024].reshape(S, T, C, 1024).copy(),
+                    "info": a[2].a[: n * 8].copy().view(W.INFO_DTYPE).reshape(S, T, C),
+                    "stereo_ops": a[3].a[: S * T * 768].copy() if stereo else None,
+                    "tns_blob": opt(a[3 + k]), "tns_offsets": opt(a[4 + k], n + 1), "entry": name, "pcm_format": 0}
+            return finish(call, a[5 + k])
+
+        def run_io(this, a):
+            in_fmt, pcm_fmt, T = int(J.to_number(a[2])), int(J.to_number(a[8])), int(J.to_number(a[9]))
+            n = S * T * C
+            call = {"info": a[3].a[: n * 8].copy().view(W.INFO_DTYPE).reshape(S, T, C),
+                    "stereo_ops": opt(a[4], S * T * 768), "tns_blob": opt(a[5]), "tns_offsets": opt(a[6], n + 1),
+                    "entry": "aacfb_process_io", "pcm_format": pcm_fmt}
+            if in_fmt == 1:
+                call["qframes"] = a[1].a[: n * 2304].copy().view(A.QFRAME_DTYPE).reshape(S, T, C)
+            else:
+                call["spectra"] = a[1].a[: n * 1024].reshape(S, T, C, 1024).copy()
+            return finish(call, a[7])
+
+        def adts(this, a):
+            frames, consumed = A.adts_index(a[0].a)
+            cap = a[1].a.size // 3 - 1
+            k = min(len(frames), cap)
+            for i in range(k):
+                a[1].a[3 * i: 3 * i + 3] = [frames[i]["offset"], frames[i]["frame_length"], frames[i]["header_bytes"]]
+            a[1].a[3 * k] = frames[k]["offset"] if k < len(frames) else consumed
+            return float(k)
+
+        def create(this, a):
+            self.created.append([int(J.to_number(v)) for v in a])
+            return J.obj()
+
+        fns = dict(create=J.native(create), process=J.native(lambda this, a: run("aacfb_process", a, False)),
+                   processStereo=J.native(lambda this, a: run("aacfb_process_stereo", a, True)),
+                   processIo=J.native(run_io))
+        if adts_index:
+            fns["adtsIndex"] = J.native(adts)
+        addon = J.obj(**fns)
+        stubs = {"av": av, "aac/src/decoder": ref.require("./decoder"), "aac/src/ics": ref.require("./ics"),
+                 "aac/src/cpe": ref.require("./cpe"), "aac/src/huffman": ref.require("./huffman"),
+                 "aac/src/tables": ref.require("./tables"), "./build/Release/aacfb.node": addon}
+        js = J.Runtime(js_dir, stubs=stubs)
+        self.Pool = js.require("./decoder_pool")
+        opts = J.obj(framesPerChunk=float(frames_per_chunk), stereoOnDevice=bool(stereo_on_device),
+                     quantOnDevice=bool(quant_on_device), pcmFormat=pcm_format)
+        self.pool = self.Pool.construct([float(S), opts])
+        proto = self.Pool.get("prototype")
+        cookie = bytes([(profile << 3) | ((sample_index >> 1) & 7), ((sample_index & 1) << 7) | (channels << 3), 0])
+        self.streams = []
+        for data in streams:
+            dec = proto.get("createDecoder").call(self.pool, [])
+            dec.put("format", J.obj())
+            J.get_member(dec, "setCookie").call(dec, [PyBitstream(cookie, av.get("UnderflowError")).js()])
+            st = PyBitstream(data, av.get("UnderflowError"))
+            dec.put("bitstream", st.js())
+            self.streams.append(st)
+
+    def read_chunks(self):
+        """One round: list of S arrays, or None (some stream has no complete frame left)."""
+        res = self.Pool.get("prototype").get("readChunks").call(self.pool, [])
+        if res is None or res is J.UNDEF:
+            return None
+        return [x.a.copy() for x in res.items]
+
+    def decode_all(self):
+        out = [[] for _ in range(self.S)]
+        while True:
+            r = self.read_chunks()
+            if r is None:
+                break
+            for s in range(self.S):
+                out[s].append(r[s])
+        return [np.concatenate(o) if o else np.zeros(0, np.float32) for o in out]
+
+
 class OracleLibrary:
     """CPU stand-in for libaacfb behind B200DecoderHarness (tests only): the op semantics of
     include/aacfb.h for the stereo records, then the oracle's TNS / filterbank / interleave, with the
     overlap state carried from call to call like an aacfb_ctx does."""
 
-    def __init__(self, channels, sample_index=4, flags=0):
+    def __init__(self, channels, sample_index=4, flags=0, n_streams=None):
         from oracle import oracle as O
 
         self.O, self.C, self.si, self.flags = O, channels, sample_index, flags
-        self.overlap = np.zeros((1, channels, 1024), np.float32)
+        self.batched = n_streams is not None          # calls carry a leading stream axis (B200PoolHarness)
+        self.overlap = np.zeros((n_streams or 1, channels, 1024), np.float32)
 
     def __call__(self, call):
+        info = call["info"] if self.batched else call["info"][None]
         if "qframes" in call:   # inverse quantisation first (ics.js:203-266), like the device
-            sp = self.O.dequant_batch(call["qframes"], call["info"], self.si)
+            q = call["qframes"] if self.batched else call["qframes"][None]
+            sp = np.stack([self.O.dequant_batch(q[s], info[s], self.si) for s in range(q.shape[0])])
         else:
-            sp = call["spectra"].copy()
+            sp = (call["spectra"] if self.batched else call["spectra"][None]).copy()
         if call["stereo_ops"] is not None:
             recs = call["stereo_ops"].view(np.dtype([("op", "u1", (256,)), ("scale", "f4", (128,))]))
-            for t in range(sp.shape[0]):
-                if not call["info"][t, 0]["stereo_present"]:
-                    continue
-                op = np.repeat(recs[t]["op"], 4)
-                l, r = sp[t, 0].copy(), sp[t, 1].copy()
-                ms, it = op == 1, op >= 2
-                sp[t, 0][ms] = l[ms] + r[ms]
-                sp[t, 1][ms] = l[ms] - r[ms]
-                sp[t, 1][it] = l[it] * recs[t]["scale"][op[it] - 2]
-        pcm, self.overlap = self.O.process_io(sp[None], 0, call["info"][None], call["tns_blob"], call["tns_offsets"],
+            recs = recs.reshape(sp.shape[0], sp.shape[1])
+            for s in range(sp.shape[0]):
+                for t in range(sp.shape[1]):
+                    if not info[s, t, 0]["stereo_present"]:
+                        continue
+                    op = np.repeat(recs[s, t]["op"], 4)
+                    l, r = sp[s, t, 0].copy(), sp[s, t, 1].copy()
+                    ms, it = op == 1, op >= 2
+                    sp[s, t, 0][ms] = l[ms] + r[ms]
+                    sp[s, t, 1][ms] = l[ms] - r[ms]
+                    sp[s, t, 1][it] = l[it] * recs[s, t]["scale"][op[it] - 2]
+        pcm, self.overlap = self.O.process_io(sp, 0, info, call["tns_blob"], call["tns_offsets"],
                                               self.overlap, pcm_format=call.get("pcm_format", 0), sample_index=self.si,
                                               flags=self.flags)
-        return pcm[0]
+        return pcm if self.batched else pcm[0]
 
 
 class AdtsReference:
