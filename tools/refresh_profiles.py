@@ -25,8 +25,9 @@ def main():
         out = os.path.join(ROOT, "profiles", f"{tag}_{name}_ncu.txt")
         subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_summary.py"), rep, str(UNITS), out],
                        check=True, cwd=ROOT, stdout=subprocess.DEVNULL)
-        m = re.search(r"traffic \(dram read \+ write\) per launch: ([0-9.]+) MB", open(out).read())
-        traffic[cap] = int(float(m.group(1)) * 1e6) if m else None
+        mult = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}
+        rw = re.findall(r"dram__bytes_(?:read|write)\.sum\s+([0-9.]+)\s+(\w+)", open(out).read())
+        traffic[cap] = int(sum(float(v) * mult[u] for v, u in rw)) if len(rw) == 2 else None
         print(name, traffic[cap])
     tab = {"_comment": "dram__bytes_read.sum + dram__bytes_write.sum of the kernels of ONE step, bytes, from one "
                        "`ncu --set full --clock-control none` capture per kernel (tools/gpu_capture.sh -> "
