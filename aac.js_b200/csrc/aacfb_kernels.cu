@@ -397,8 +397,23 @@ __global__ void __launch_bounds__(W * 64, 1) synth_kernel(const __grid_constant_
 // [lo4, hi4) (float4 units) of the row's runs -- coefficients inside it that no filter touches
 // are copied -- and `ranges[cf]` = lo4 | hi4 << 16 tells synth_kernel which part of the row to
 // fetch from scratch (the rest comes straight from the spectra).
-constexpr int kTnsPitch = 36;                           // floats per tile row: 32 + 4 (144 B)
-constexpr int kTnsRing = 3;
+#ifndef AACFB_TNS_COLS
+#define AACFB_TNS_COLS 32   // coefficients per tile row (32: 128-byte pieces of a row, 64: 256-byte pieces)
+#endif
+constexpr int kTnsCols = AACFB_TNS_COLS;
+constexpr int kTnsQuads = kTnsCols / 4;                 // float4s per tile row
+constexpr int kTnsRowsPerCopy = 32 / kTnsQuads;         // tile rows one warp-wide 16-byte copy covers
+constexpr int kTnsCopies = 32 / kTnsRowsPerCopy;        // copies per tile and lane
+constexpr int kTnsPitch = kTnsCols + 4;                 // floats per tile row (+ 16 B: conflict-free, see above)
+static_assert(kTnsCols == 32 || kTnsCols == 64, "tile width");
+#ifndef AACFB_TNS_RING
+#define AACFB_TNS_RING 3    // tiles per warp: one being filtered, AACFB_TNS_RING - 1 in flight
+#endif
+#ifndef AACFB_TNS_CTAS
+#define AACFB_TNS_CTAS 4    // resident CTAs per SM the register budget is set for (4: 128 registers per thread)
+#endif
+constexpr int kTnsRing = AACFB_TNS_RING;
+constexpr int kTnsAhead = kTnsRing - 1;
 constexpr int kTnsTileFloats = 32 * kTnsPitch;
 constexpr int kTnsSmemRing = kTnsWarps * kTnsRing * kTnsTileFloats * 4;
 constexpr int kTnsSmemBytes = kTnsSmemRing + 256;      // + the band tables of one sample rate
@@ -440,100 +455,101 @@ __device__ __noinline__ void tns_tile_run(float *ring, int lane, const float *x_
 #pragma unroll
     for (int i = 0; i < ORD; ++i) { h[i] = 0.f; c[i] = i < order ? lpc[i] : 0.f; }
     const bool nan_from = order == AACFB_TNS_MAX_ORDER;
-    // The 8 rows this lane moves: r = (lane >> 3) + 4k, 16-byte column cc = lane & 7.
+    // The rows this lane moves: r = lane / kTnsQuads + kTnsRowsPerCopy * k, 16-byte column cc = lane % kTnsQuads.
     //   g_off : element offset (from row 0 of the warp) of float4 `cc` of the current block
-    //   g_step: +32 / -32 elements per block (direction of the served row's run)
+    //   g_step: +- kTnsCols elements per block (direction of the served row's run)
     //   g_nv  : my float4 is inside the run for blocks b < g_nv (its position in run order is
-    //           quad cc of an upward run, quad 7 - cc of a downward one)
-    const int cc = lane & 7;
-    int g_off[8], g_step[8], g_nv[8];
+    //           quad cc of an upward run, quad kTnsQuads - 1 - cc of a downward one)
+    const int cc = lane & (kTnsQuads - 1), rr = lane / kTnsQuads;
+    int g_off[kTnsCopies], g_step[kTnsCopies], g_nv[kTnsCopies];
     int nv_min = 1 << 30;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        const int r = (lane >> 3) + 4 * k;
+    for (int k = 0; k < kTnsCopies; ++k) {
+        const int r = rr + kTnsRowsPerCopy * k;
         const int st_k = __shfl_sync(0xffffffffu, start, r);
         const int sz_k = __shfl_sync(0xffffffffu, size, r), in_k = __shfl_sync(0xffffffffu, inc, r);
-        g_off[k] = r * 1024 + (in_k > 0 ? st_k : st_k - 31) + 4 * cc;
-        g_step[k] = in_k > 0 ? 32 : -32;
-        const int quad = in_k > 0 ? cc : 7 - cc;
-        g_nv[k] = sz_k > 4 * quad ? (sz_k - 4 * quad + 31) >> 5 : 0;
+        g_off[k] = r * 1024 + (in_k > 0 ? st_k : st_k - (kTnsCols - 1)) + 4 * cc;
+        g_step[k] = in_k > 0 ? kTnsCols : -kTnsCols;
+        const int quad = in_k > 0 ? cc : kTnsQuads - 1 - cc;
+        g_nv[k] = sz_k > 4 * quad ? (sz_k - 4 * quad + kTnsCols - 1) / kTnsCols : 0;
         nv_min = min(nv_min, g_nv[k]);
     }
-    int nblk = (size + 31) >> 5;
+    int nblk = (size + kTnsCols - 1) / kTnsCols;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         nblk = max(nblk, __shfl_xor_sync(0xffffffffu, nblk, o));
         nv_min = min(nv_min, __shfl_xor_sync(0xffffffffu, nv_min, o));
     }
-    const uint32_t ring_s = smem_u32(ring) + 4u * (uint32_t)((lane >> 3) * kTnsPitch + 4 * cc);
-    const float *tile_rd = ring + (lane >> 3) * kTnsPitch + 4 * cc;  // my float4 of served row k = 0
+    const uint32_t ring_s = smem_u32(ring) + 4u * (uint32_t)(rr * kTnsPitch + 4 * cc);
+    const float *tile_rd = ring + rr * kTnsPitch + 4 * cc;  // my float4 of served row k = 0
+    constexpr int kCopyStride = kTnsRowsPerCopy * kTnsPitch;   // floats between the rows of copy k and k + 1
     // Blocks b < nv_min are whole for every row of the warp: no predicates there.
     auto load_tile = [&](int b, int slot) {  // tile b -> ring slot
         if (b < nv_min) {
 #pragma unroll
-            for (int k = 0; k < 8; ++k)
-                cp_async16(ring_s + 4u * (uint32_t)(slot * kTnsTileFloats + 4 * k * kTnsPitch),
-                           x_base + (g_off[k] + 2 * g_step[k]));
+            for (int k = 0; k < kTnsCopies; ++k)
+                cp_async16(ring_s + 4u * (uint32_t)(slot * kTnsTileFloats + k * kCopyStride),
+                           x_base + (g_off[k] + kTnsAhead * g_step[k]));
         } else if (b < nblk) {
 #pragma unroll
-            for (int k = 0; k < 8; ++k)
+            for (int k = 0; k < kTnsCopies; ++k)
                 if (b < g_nv[k])
-                    cp_async16(ring_s + 4u * (uint32_t)(slot * kTnsTileFloats + 4 * k * kTnsPitch),
-                               x_base + (g_off[k] + 2 * g_step[k]));
+                    cp_async16(ring_s + 4u * (uint32_t)(slot * kTnsTileFloats + k * kCopyStride),
+                               x_base + (g_off[k] + kTnsAhead * g_step[k]));
         }
         cp_async_commit();
     };
-    // g_off describes block b while tile b + 2 is being fetched: start it two blocks back
+    // g_off describes block b while tile b + kTnsAhead is being fetched: start it that many blocks back
 #pragma unroll
-    for (int k = 0; k < 8; ++k) g_off[k] -= 2 * g_step[k];
-    load_tile(0, 0);
+    for (int k = 0; k < kTnsCopies; ++k) g_off[k] -= kTnsAhead * g_step[k];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) g_off[k] += g_step[k];
-    load_tile(1, 1);
+    for (int i = 0; i < kTnsAhead; ++i) {
+        load_tile(i, i);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) g_off[k] += g_step[k];
+        for (int k = 0; k < kTnsCopies; ++k) g_off[k] += g_step[k];
+    }
     int slot = 0;
     for (int b = 0; b < nblk; ++b) {
-        cp_async_wait1();
+        asm volatile("cp.async.wait_group %0;" ::"n"(kTnsAhead - 1) : "memory");
         __syncwarp();  // tile b has landed for every lane; tile b-1's write-out has been read
-        load_tile(b + 2, slot >= 1 ? slot - 1 : kTnsRing - 1);  // == (b + 2) % kTnsRing
+        load_tile(b + kTnsAhead, slot >= 1 ? slot - 1 : kTnsRing - 1);  // == (b + kTnsAhead) % kTnsRing
         float *tile = ring + slot * kTnsTileFloats;
         float4 *row = reinterpret_cast<float4 *>(tile + lane * kTnsPitch);
-        const int left = size - 32 * b;
-        if (left >= 32) {  // straight-line: the history shift is pure register renaming
-            // all loads first (shared-memory latency is paid once per half block, not per quad)
+        const int left = size - kTnsCols * b;
+        if (left >= kTnsCols) {  // straight-line: the history shift is pure register renaming
+            // all loads first (shared-memory latency is paid once per group of quads, not per quad)
             constexpr int kHalf = ORD > 12 ? 4 : 8;
 #pragma unroll
-            for (int q0 = 0; q0 < 8; q0 += kHalf) {
+            for (int q0 = 0; q0 < kTnsQuads; q0 += kHalf) {
                 float4 v[kHalf];
 #pragma unroll
-                for (int q = 0; q < kHalf; ++q) v[q] = row[inc > 0 ? q0 + q : 7 - q0 - q];
+                for (int q = 0; q < kHalf; ++q) v[q] = row[inc > 0 ? q0 + q : kTnsQuads - 1 - q0 - q];
 #pragma unroll
-                for (int q = 0; q < kHalf; ++q) v[q] = tns_quad<ORD, AR>(v[q], inc, h, c, nan_from, 32 * b + 4 * (q0 + q));
+                for (int q = 0; q < kHalf; ++q) v[q] = tns_quad<ORD, AR>(v[q], inc, h, c, nan_from, kTnsCols * b + 4 * (q0 + q));
 #pragma unroll
-                for (int q = 0; q < kHalf; ++q) row[inc > 0 ? q0 + q : 7 - q0 - q] = v[q];
+                for (int q = 0; q < kHalf; ++q) row[inc > 0 ? q0 + q : kTnsQuads - 1 - q0 - q] = v[q];
             }
         } else if (left > 0) {
             for (int q = 0; 4 * q < left; ++q) {
-                float4 *p = row + (inc > 0 ? q : 7 - q);
-                *p = tns_quad<ORD, AR>(*p, inc, h, c, nan_from, 32 * b + 4 * q);
+                float4 *p = row + (inc > 0 ? q : kTnsQuads - 1 - q);
+                *p = tns_quad<ORD, AR>(*p, inc, h, c, nan_from, kTnsCols * b + 4 * q);
             }
         }
         __syncwarp();
         if (b < nv_min) {
 #pragma unroll
-            for (int k = 0; k < 8; ++k)
+            for (int k = 0; k < kTnsCopies; ++k)
                 *reinterpret_cast<float4 *>(y_base + g_off[k]) =
-                    *reinterpret_cast<const float4 *>(tile_rd + slot * kTnsTileFloats + 4 * k * kTnsPitch);
+                    *reinterpret_cast<const float4 *>(tile_rd + slot * kTnsTileFloats + k * kCopyStride);
         } else {
 #pragma unroll
-            for (int k = 0; k < 8; ++k)
+            for (int k = 0; k < kTnsCopies; ++k)
                 if (b < g_nv[k])
                     *reinterpret_cast<float4 *>(y_base + g_off[k]) =
-                        *reinterpret_cast<const float4 *>(tile_rd + slot * kTnsTileFloats + 4 * k * kTnsPitch);
+                        *reinterpret_cast<const float4 *>(tile_rd + slot * kTnsTileFloats + k * kCopyStride);
         }
 #pragma unroll
-        for (int k = 0; k < 8; ++k) g_off[k] += g_step[k];
+        for (int k = 0; k < kTnsCopies; ++k) g_off[k] += g_step[k];
         slot = slot + 1 == kTnsRing ? 0 : slot + 1;
     }
     cp_async_wait0();
@@ -550,7 +566,7 @@ __device__ __forceinline__ void tns_tile_dispatch(int ord_max, float *ring, int 
     else tns_tile_run<20, AR>(ring, lane, x, y, start, size, inc, lpc, order);
 }
 
-__global__ void __launch_bounds__(kTnsWarps * 32, 4) tns_kernel(const __grid_constant__ TnsParams P) {
+__global__ void __launch_bounds__(kTnsWarps * 32, AACFB_TNS_CTAS) tns_kernel(const __grid_constant__ TnsParams P) {
     extern __shared__ __align__(128) uint8_t smem[];
     if (P.gate != nullptr && *P.gate == 0u) return;   // nothing was left to the pre-pass (see launch_synth_tns)
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;

@@ -21,7 +21,8 @@ is the whole-job frames/s over the max-over-ranks device time.
 `config5_scatter`: (N > 1) BASELINE.json configs[4] at full size: 1 048 576 stereo mixed frames that start
             on rank 0, through the NCCL scatter -> kernel -> gather path and through the fused
             peer-memory path (synth_kernel on rank 0's buffers over NVLink), each timed and bit-checked.
-`pcie_concurrent`: (N > 1) host<->device copy rates per GPU with all ranks copying at once.
+`pcie_concurrent`: host<->device copy rates per GPU with all ranks copying at once (256 MB pinned copies, each
+            direction alone and both together): the link ceiling the `e2e` leg is to be read against.
 """
 from __future__ import annotations
 
@@ -636,7 +637,7 @@ def run_ours(args):
 
     # --- N > 1: what the box's host<->device path gives all ranks at once, and config 5 from rank 0 ---
     pcie = scatter = None
-    if world > 1 and not args.no_pcie_probe:
+    if not args.no_pcie_probe and not args.no_e2e:   # (N = 1 too: the link ceiling `e2e` is to be read against)
         pcie = pcie_probe(torch, dev, world)
     if world > 1 and not args.no_scatter:
         try:
@@ -703,7 +704,7 @@ def main():
     ap.add_argument("--no-numa", action="store_true", help="do not bind the process to the GPU's NUMA node")
     ap.add_argument("--no-configs", action="store_true", help="N = 1: skip the configs record (configs 3, 4, 5, config2_stereo)")
     ap.add_argument("--no-scatter", action="store_true", help="N > 1: skip BASELINE configs[4] (1 048 576 frames from rank 0)")
-    ap.add_argument("--no-pcie-probe", action="store_true", help="N > 1: skip the concurrent host<->device copy probe")
+    ap.add_argument("--no-pcie-probe", action="store_true", help="skip the concurrent host<->device copy probe")
     ap.add_argument("--scatter-streams", type=int, default=4096, help="streams of the config-5 batch on rank 0 (x 256 frames)")
     args = ap.parse_args()
     if args.impl == "reference":
