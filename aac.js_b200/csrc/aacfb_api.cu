@@ -692,6 +692,16 @@ API int aacfb_process_io(aacfb_ctx *ctx, const void *input, uint32_t in_format, 
         if (upto > done) parts.push_back(upto - done);
         done = upto;
     }
+    // The copy-out of the LAST sub-batch overlaps nothing (and so does the copy-in of the first): taper both ends
+    // by halving the outermost parts AACFB_TAPER times (tuning aid; 0 = equal parts).
+    int taper = 0;
+    if (const char *env = std::getenv("AACFB_TAPER")) taper = std::max(0, std::min(4, std::atoi(env)));
+    for (int k = 0; k < taper && parts.size() > 1; ++k) {
+        const int last = parts.back();
+        if (last >= 2) { parts.back() = last - last / 2; parts.push_back(last / 2); }
+        const int first = parts.front();
+        if (first >= 2) { parts.front() = first - first / 2; parts.insert(parts.begin(), first / 2); }
+    }
     // The side info is validated sub-batch by sub-batch, each right before its copies are queued, so
     // only the first one's check delays the first H2D; the rest overlaps the transfers in flight.
     // A small call (one sub-batch) is checked as a whole, which also tells whether the generic
