@@ -699,8 +699,36 @@ AACFB_HD void exs_read(int u, float2 *const *buf, Pts &z) {
 #ifndef AACFB_SWZ9
 #define AACFB_SWZ9 1
 #endif
-AACFB_HD int short_swz(int t) {
+AACFB_HD constexpr int short_swz(int t) {
     return AACFB_SWZ9 ? t ^ (((t >> 5) ^ (t >> 9)) & 1) ^ (((t >> 7) & 1) << 4) : t ^ ((t >> 5) & 1) ^ (((t >> 7) & 1) << 4);
+}
+// AACFB_SWZ_LINEAR: the swizzle is linear over GF(2) (XORs of bit extractions), so for an index that is a sum of
+// parts with disjoint bits -- a per-thread part and a part known at compile time -- it splits into
+// short_swz(thread part) ^ short_swz(constant part): one XOR per address instead of the whole bit fiddle
+// (the address arithmetic of the product arrays was ~30 % of the instructions of an EIGHT_SHORT frame).
+//   producer   128 w + pa = (128 w + 2 g) + c_q        128 w + pb = (128 w + 15 - 2 g) + c'_q      (c_q, c'_q: bits 4-6)
+//   consumer   t = C + 2u: C = 128 j + 64 for every index the sums use -> 128 (j + [u >= 32]) + ((64 + 2u) & 127)
+//              t = C - 2u: C = 128 j + 63                              -> 128 (j - [u >= 32]) + ((63 - 2u) & 127)
+#ifndef AACFB_SWZ_LINEAR
+#define AACFB_SWZ_LINEAR 1
+#endif
+struct ShortIdx {          // per-thread parts of the consumer's indices
+    int lo_up, lo_dn;      // short_swz((64 + 2u) & 127), short_swz((63 - 2u) & 127)
+    bool hi;               // u >= 32
+};
+AACFB_HD ShortIdx short_idx(int u) {
+    ShortIdx s;
+    s.lo_up = short_swz((64 + 2 * u) & 127); s.lo_dn = short_swz((63 - 2 * u) & 127); s.hi = u >= 32;
+    return s;
+}
+// swizzled index of t = CT + 2u (NEG = false) or CT - 2u (NEG = true); only meaningful for 0 <= t < 1024
+template <int CT, bool NEG>
+AACFB_HD int short_swz_at(const ShortIdx &s) {
+    constexpr int cl = NEG ? 63 : 64;
+    static_assert((CT - cl) % 128 == 0, "index constant");
+    constexpr int j0 = (CT - cl) / 128, j1 = NEG ? j0 - 1 : j0 + 1;
+    constexpr int k0 = (j0 >= 0 && j0 < 8) ? short_swz(128 * j0) : 0, k1 = (j1 >= 0 && j1 < 8) ? short_swz(128 * j1) : 0;
+    return (NEG ? s.lo_dn : s.lo_up) ^ (s.hi ? k1 : k0);
 }
 
 // Producer: thread u = 8w + g, bins k = 8q + g of window w.  `wsp[shape][k]` = (W[pa(k)], W[pb(k)]):
@@ -715,6 +743,8 @@ AACFB_HD void short_products(int u, const Pts &z, const float2 *cs256, const flo
     const bool first_differs = fb_shape_prev(fi) != fb_shape_cur(fi);   // (uniform over the worker)
     const float2 *wfirst = w == 0 ? wsp[fb_shape_prev(fi)] : wcur;      // filter_bank.js:153 vs :157-160
     float *p1 = buf, *p2 = buf + 1024;
+    const int ta = short_swz(128 * w + 2 * g), tb = short_swz(128 * w + 15 - 2 * g);   // (AACFB_SWZ_LINEAR)
+    (void)ta; (void)tb;
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
         const int k = 8 * q + g;
@@ -729,7 +759,12 @@ AACFB_HD void short_products(int u, const Pts &z, const float2 *cs256, const flo
         float2 wf = wc;
         if (first_differs) wf = wfirst[k];
         const float wa = wc.x, wb = wc.y, fa = wf.x, fb = wf.y;
+#if AACFB_SWZ_LINEAR
+        const int ia = ta ^ short_swz(q < 4 ? 64 + 16 * q : 16 * (q - 4)), ib = tb ^ short_swz(q < 4 ? 48 - 16 * q : 176 - 16 * q);
+        (void)pa; (void)pb;
+#else
         const int ia = short_swz(128 * w + pa), ib = short_swz(128 * w + pb);
+#endif
         if (q < 4) {  // k < 32: y[64+2k] = pr, y[63-2k] = -pr, y[192+2k] = y[191-2k] = -pi
             p1[ia] = f_mul(pr, fa);
             p1[ib] = f_mul(-pr, fb);
@@ -746,36 +781,46 @@ AACFB_HD void short_products(int u, const Pts &z, const float2 *cs256, const flo
 
 // Consumer for output position n (range [LO, HI] known at compile time): returns the sample
 // out[n] (if EMIT) and replaces the overlap.  Loads that cannot apply to the range fold away.
-template <int LO, int HI>
-AACFB_HD void short_ola(int n, const float *buf, bool emit, float &ovl, float &out) {
+// NEG: n = HI - 2u (the mirrored positions), otherwise n = LO + 2u.
+template <int LO, int HI, bool NEG>
+AACFB_HD void short_ola(int n, const ShortIdx &sx, const float *buf, bool emit, float &ovl, float &out) {
     const float *p1 = buf, *p2 = buf + 1024;
+    constexpr int C = NEG ? HI : LO;   // n = C -+ 2u
+#if AACFB_SWZ_LINEAR
+#define AACFB_SIDX(off) short_swz_at<C + (off), NEG>(sx)
+#else
+#define AACFB_SIDX(off) short_swz(n + (off))
+    (void)sx;
+#endif
     // out[n] = (overlap + y_{j-1} term) + y_j term, t = n - 448   (filter_bank.js:153-161)
     float o = ovl;
-    if (HI >= 576) { const bool on = LO >= 576 || n >= 576; const float v = on ? p2[short_swz(on ? n - 576 : 0)] : 0.f; o = f_add(o, v); }
-    if (HI >= 448) { const bool on = LO >= 448 || n >= 448; const float v = on ? p1[short_swz(on ? n - 448 : 0)] : 0.f; o = f_add(o, v); }
+    if (HI >= 576) { const bool on = LO >= 576 || n >= 576; const float v = on ? p2[on ? AACFB_SIDX(-576) : 0] : 0.f; o = f_add(o, v); }
+    if (HI >= 448) { const bool on = LO >= 448 || n >= 448; const float v = on ? p1[on ? AACFB_SIDX(-448) : 0] : 0.f; o = f_add(o, v); }
     if (emit) out = o;
     // overlap'[n] = y_{j-1} term + y_j term, t = n + 576             (filter_bank.js:164-176)
     float nv = 0.f;
-    if (LO < 576) { const bool on = HI < 576 || n < 576; nv = on ? p2[short_swz(on ? n + 448 : 0)] : 0.f; }
-    if (LO < 448) { const bool on = HI < 448 || n < 448; const float v = on ? p1[short_swz(on ? n + 576 : 0)] : 0.f; nv = f_add(nv, v); }
+    if (LO < 576) { const bool on = HI < 576 || n < 576; nv = on ? p2[on ? AACFB_SIDX(448) : 0] : 0.f; }
+    if (LO < 448) { const bool on = HI < 448 || n < 448; const float v = on ? p1[on ? AACFB_SIDX(576) : 0] : 0.f; nv = f_add(nv, v); }
     ovl = nv;
+#undef AACFB_SIDX
 }
 // Window + overlap-add of ONE chain of an EIGHT_SHORT frame from its product arrays.
 template <int C>
 AACFB_HD void short_finish(int u, const float *buf, Ovl &ov, bool emit, Out &o) {
+    const ShortIdx sx = short_idx(u);
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
         // m = long_pos_of_bin(64q + u): 512 + 128q + 2u (q < 4), 128(q - 4) + 2u (q >= 4); mirror 1023 - m
         const int m = long_pos_of_bin(64 * q + u), mm = 1023 - m;
         switch (q) {  // compile-time ranges of m and 1023 - m (u = 0..63)
-        case 0: short_ola<512, 638>(m, buf, emit, ov.a[C][0], o.a[C][0]); short_ola<385, 511>(mm, buf, emit, ov.b[C][0], o.b[C][0]); break;
-        case 1: short_ola<640, 766>(m, buf, emit, ov.a[C][1], o.a[C][1]); short_ola<257, 383>(mm, buf, emit, ov.b[C][1], o.b[C][1]); break;
-        case 2: short_ola<768, 894>(m, buf, emit, ov.a[C][2], o.a[C][2]); short_ola<129, 255>(mm, buf, emit, ov.b[C][2], o.b[C][2]); break;
-        case 3: short_ola<896, 1022>(m, buf, emit, ov.a[C][3], o.a[C][3]); short_ola<1, 127>(mm, buf, emit, ov.b[C][3], o.b[C][3]); break;
-        case 4: short_ola<0, 126>(m, buf, emit, ov.a[C][4], o.a[C][4]); short_ola<897, 1023>(mm, buf, emit, ov.b[C][4], o.b[C][4]); break;
-        case 5: short_ola<128, 254>(m, buf, emit, ov.a[C][5], o.a[C][5]); short_ola<769, 895>(mm, buf, emit, ov.b[C][5], o.b[C][5]); break;
-        case 6: short_ola<256, 382>(m, buf, emit, ov.a[C][6], o.a[C][6]); short_ola<641, 767>(mm, buf, emit, ov.b[C][6], o.b[C][6]); break;
-        default: short_ola<384, 510>(m, buf, emit, ov.a[C][7], o.a[C][7]); short_ola<513, 639>(mm, buf, emit, ov.b[C][7], o.b[C][7]); break;
+        case 0: short_ola<512, 638, false>(m, sx, buf, emit, ov.a[C][0], o.a[C][0]); short_ola<385, 511, true>(mm, sx, buf, emit, ov.b[C][0], o.b[C][0]); break;
+        case 1: short_ola<640, 766, false>(m, sx, buf, emit, ov.a[C][1], o.a[C][1]); short_ola<257, 383, true>(mm, sx, buf, emit, ov.b[C][1], o.b[C][1]); break;
+        case 2: short_ola<768, 894, false>(m, sx, buf, emit, ov.a[C][2], o.a[C][2]); short_ola<129, 255, true>(mm, sx, buf, emit, ov.b[C][2], o.b[C][2]); break;
+        case 3: short_ola<896, 1022, false>(m, sx, buf, emit, ov.a[C][3], o.a[C][3]); short_ola<1, 127, true>(mm, sx, buf, emit, ov.b[C][3], o.b[C][3]); break;
+        case 4: short_ola<0, 126, false>(m, sx, buf, emit, ov.a[C][4], o.a[C][4]); short_ola<897, 1023, true>(mm, sx, buf, emit, ov.b[C][4], o.b[C][4]); break;
+        case 5: short_ola<128, 254, false>(m, sx, buf, emit, ov.a[C][5], o.a[C][5]); short_ola<769, 895, true>(mm, sx, buf, emit, ov.b[C][5], o.b[C][5]); break;
+        case 6: short_ola<256, 382, false>(m, sx, buf, emit, ov.a[C][6], o.a[C][6]); short_ola<641, 767, true>(mm, sx, buf, emit, ov.b[C][6], o.b[C][6]); break;
+        default: short_ola<384, 510, false>(m, sx, buf, emit, ov.a[C][7], o.a[C][7]); short_ola<513, 639, true>(mm, sx, buf, emit, ov.b[C][7], o.b[C][7]); break;
         }
     }
 }
