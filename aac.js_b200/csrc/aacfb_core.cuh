@@ -103,6 +103,12 @@ AACFB_HD F2 f_mul(F2 a, float s) { return f_mul(a, F2{s, s}); }
 #ifndef AACFB_SHORT_PAIRLOAD
 #define AACFB_SHORT_PAIRLOAD 1   // tuning switch: EIGHT_SHORT rows read as 8-byte pairs + one shuffle
 #endif
+#ifndef AACFB_LONG_STAGGER
+#define AACFB_LONG_STAGGER 1     // tuning switch: half of the lanes read x[2n] / x[1023 - 2n] in the opposite order (long_load, long-only instantiation)
+#endif
+#ifndef AACFB_SHORT_STAGGER
+#define AACFB_SHORT_STAGGER 0    // tuning switch: odd windows read their row pairs in the opposite order (short_load); see profiles/r04_ab_experiments.txt
+#endif
 
 constexpr int kWorkerThreads = 64;
 constexpr int kRowFloats = 1024;        // one channel-frame of spectrum
@@ -277,23 +283,34 @@ AACFB_HD float2 cs_at(const float2 *cs2048, float2 cs0, int u, int j) {
 
 // Pre-twiddle (mdct.js:73-76) straight from the staged spectrum row into the
 // bit-reversed register order pass A needs: reg q <- input n = u + 64*brev3(q).
-template <int C0, int NCH, bool PK, bool ROT>
+template <int C0, int NCH, bool PK, bool ROT, bool STAG = false>
 AACFB_HD void long_load(int u, const float *const *row, const float2 *cs2048, Pts &z) {
     float2 cs0 = {0.f, 0.f};
     if (ROT) cs0 = cs2048[u];
+    // AACFB_LONG_STAGGER: x[2n] lives on the even banks and x[1023 - 2n] on the odd ones, and lanes u, u + 16 of a warp
+    // share a bank in either: 2 wavefronts per scalar load.  Half of the lanes (bit 4 of u) fetch the two in the
+    // opposite order -- 1023 - 2n = 2n ^ 1023 -- so that every load instruction covers 16 even and 16 odd banks (1
+    // wavefront: 32 of the 312 wavefronts of a long channel-frame), and swap the results back with two selects.
+    // STAG: only the long-only instantiation does it (config 2 +0.75 %); in the generic ones, at the register cap,
+    // the extra live values cost the long path 5 % (config 5), see profiles/r04_ab_experiments.txt.
+    const bool sw = STAG && (u & 16) != 0;
+    const int flip = sw ? 1023 : 0;
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
         const int n = u + 64 * brev3(q);
         const float2 cs = cs_at<ROT>(cs2048, cs0, u, brev3(q));
+        const int ia = (2 * n) ^ flip, ib = ia ^ 1023;
         if constexpr (PK && NCH == 2) {
-            const F2 x0{row[0][2 * n], row[1][2 * n]}, x1{row[0][1023 - 2 * n], row[1][1023 - 2 * n]};
+            const float a0 = row[0][ia], a1 = row[1][ia], b0 = row[0][ib], b1 = row[1][ib];
+            const F2 x0{sw ? b0 : a0, sw ? b1 : a1}, x1{sw ? a0 : b0, sw ? a1 : b1};
             const F2 zi = f_fma(x0, cs.x, f_mul(x1, cs.y));
             const F2 zr = f_fma(x1, cs.x, f_neg(f_mul(x0, cs.y)));
             z.i[0][q] = zi.x; z.i[1][q] = zi.y; z.r[0][q] = zr.x; z.r[1][q] = zr.y;
         } else {
 #pragma unroll
             for (int c = C0; c < C0 + NCH; ++c) {
-                const float x0 = row[c][2 * n], x1 = row[c][1023 - 2 * n];
+                const float a = row[c][ia], b = row[c][ib];
+                const float x0 = sw ? b : a, x1 = sw ? a : b;
                 z.i[c][q] = f_fma(x0, cs.x, f_mul(x1, cs.y));
                 z.r[c][q] = f_fma(x1, cs.x, -f_mul(x0, cs.y));
             }
@@ -608,11 +625,22 @@ AACFB_HD void short_load(int u, Sync &sync, const float *const *row, const float
     const int w = u >> 3, g = u & 7;
     if constexpr (PK && NCH == 2 && AACFB_SHORT_PAIRLOAD != 0) {
         const float2 *r0 = reinterpret_cast<const float2 *>(row[0]) + 64 * w, *r1 = reinterpret_cast<const float2 *>(row[1]) + 64 * w;
+        // AACFB_SHORT_STAGGER: pair n = g + 8 b sits on banks 2g, 2g + 1 (+ 16 if b is odd) whatever the window, so the
+        // two windows of a half-warp collide (4 wavefronts per LDS.64 instead of 2: 52 of the 486 wavefronts of an
+        // EIGHT_SHORT channel-frame).  b and 7 - b have opposite parity and are fetched as a pair anyway: odd windows
+        // fetch them in the opposite order (n ^ 56) and swap the results back.
+        const bool sw = AACFB_SHORT_STAGGER != 0 && (w & 1) != 0;
+        const int flip = sw ? 56 : 0;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             const int qa = q, qb = 7 - q;   // brev3(7 - q) = 7 - brev3(q)
             const int na = g + 8 * brev3(qa), nb = g + 8 * brev3(qb);
-            const float2 a0 = r0[na], a1 = r1[na], b0 = r0[nb], b1 = r1[nb];
+            float2 a0 = r0[na ^ flip], a1 = r1[na ^ flip], b0 = r0[nb ^ flip], b1 = r1[nb ^ flip];
+            if (AACFB_SHORT_STAGGER != 0) {
+                const float2 t0 = a0, t1 = a1;
+                a0.x = sw ? b0.x : t0.x; a0.y = sw ? b0.y : t0.y; a1.x = sw ? b1.x : t1.x; a1.y = sw ? b1.y : t1.y;
+                b0.x = sw ? t0.x : b0.x; b0.y = sw ? t0.y : b0.y; b1.x = sw ? t1.x : b1.x; b1.y = sw ? t1.y : b1.y;
+            }
             const F2 x1a{sync.partner7(u, b0.y), sync.partner7(u, b1.y)};
             const F2 x1b{sync.partner7(u, a0.y), sync.partner7(u, a1.y)};
             const F2 x0a{a0.x, a1.x}, x0b{b0.x, b1.x};

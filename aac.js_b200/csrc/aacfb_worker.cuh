@@ -70,12 +70,12 @@ AACFB_HD void load_tw(const float2 *p, int stride, float2 *tw) {
 
 // 512-point inverse FFT of chains C0..C0+NCH-1 (fft.js:105-192 on the
 // pre-twiddled rows, mdct.js:73-79): two barriers.
-template <int C0, int NCH, bool PK, bool ROT, class Sync>
+template <int C0, int NCH, bool PK, bool ROT, bool STAG = false, class Sync>
 AACFB_HD void long_fft(int u, Sync &sync, const FrameIO &io, const SynthTables *ts, Pts &z) {
     const float *row[2] = {io.stage, io.stage + kRowFloats};
     float2 *bufx[2] = {reinterpret_cast<float2 *>(io.scratch), reinterpret_cast<float2 *>(io.scratch + kRowFloats)};
     float2 *bufs[2] = {reinterpret_cast<float2 *>(io.stage), reinterpret_cast<float2 *>(io.stage + kRowFloats)};
-    long_load<C0, NCH, PK, ROT>(u, row, ts->cs2048, z);
+    long_load<C0, NCH, PK, ROT, STAG>(u, row, ts->cs2048, z);
     pass_a<C0, NCH, PK>(z, ts->rootsA);
     ex1_write<C0, NCH, PK>(u, z, bufx);
     sync.barrier();  // exchange 1 complete; every thread has consumed its part of the rows
@@ -124,10 +124,10 @@ AACFB_HD void short_fft(int u, Sync &sync, const FrameIO &io, const SynthTables 
 // UNIFORM_PATH: also instantiate the specialisation for frames whose chains are all ONLY_LONG with
 // equal shapes.  The generic pass leaves it out: its code footprint (long + short paths running
 // side by side on one SM) is what the instruction cache has to hold.
-template <int NCH, bool UNIFORM_PATH, bool PK, bool ROTL, bool ROTF, class Sync>
+template <int NCH, bool UNIFORM_PATH, bool PK, bool ROTL, bool ROTF, bool STAG = false, class Sync>
 AACFB_HD void frame_all_long(int u, Sync &sync, const FrameIO &io, const SynthTables *ts, const SynthTables *tg,
                              Pts &z, Ovl &ov) {
-    long_fft<0, NCH, PK, ROTL>(u, sync, io, ts, z);
+    long_fft<0, NCH, PK, ROTL, STAG>(u, sync, io, ts, z);
     sync.stage_free();  // exchange 2 has been read back: the stage may be refilled
     Out none;
     const bool uniform = UNIFORM_PATH && fb_seq(io.fi[0]) == AACFB_ONLY_LONG_SEQUENCE &&
@@ -214,8 +214,11 @@ AACFB_HD void worker_frame(int u, Sync &sync, const FrameIO &io, const SynthTabl
         if (any_short) { frame_with_short<PK>(u, sync, io, ts, tg, z, ov); return; }
     }
     constexpr bool UNI = !GENERIC || AACFB_GENERIC_UNIFORM != 0;
-    if (io.nch == 2) frame_all_long<2, UNI, PK, ROTL, ROTF>(u, sync, io, ts, tg, z, ov);
-    else frame_all_long<1, UNI, false, ROTL, ROTF>(u, sync, io, ts, tg, z, ov);
+    // staggered row reads (long_load): only where registers are to spare -- the plain long-only instantiation
+    // (config 2 +0.7 %; the stereo one loses 0.5 %, the generic ones 5 %: profiles/r04_ab_experiments.txt)
+    constexpr bool STAG = !GENERIC && !STEREO && !IOV && AACFB_LONG_STAGGER != 0;
+    if (io.nch == 2) frame_all_long<2, UNI, PK, ROTL, ROTF, STAG>(u, sync, io, ts, tg, z, ov);
+    else frame_all_long<1, UNI, false, ROTL, ROTF, STAG>(u, sync, io, ts, tg, z, ov);
 }
 
 }  // namespace aacfb
