@@ -216,7 +216,12 @@ __global__ void __launch_bounds__(W * 64, 1) synth_kernel(const __grid_constant_
     }
     __syncthreads();
 
-    DevSync<STEREO, GENERIC, IOV> sync;
+    // PARK: the plain generic instantiation has had registers to spare since the product-array addresses became XORs
+    // (config 5 0.2727 -> 0.2699 ms without it); the stereo / quantised-input ones still spill and keep it.
+#ifndef AACFB_GENERIC_PARK
+#define AACFB_GENERIC_PARK 0   // tuning switch: 1 = also the plain generic instantiation parks the refill in shared memory
+#endif
+    DevSync<STEREO, GENERIC && (STEREO || IOV || AACFB_GENERIC_PARK != 0), IOV> sync;
     sync.bar_id = 1 + w;
     sync.free_id = 1 + kWorkers + w;
     sync.leader_warp = ((tid >> 5) & 1) == 0;
