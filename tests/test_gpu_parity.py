@@ -135,6 +135,30 @@ def test_edge_cases():
     ctx.close()
 
 
+def test_error_in_a_late_sub_batch_drains_the_pipeline_and_leaves_the_state():
+    """The host path pipelines sub-batches of streams (copies on one stream per PCIe direction, kernels on the
+    buffer sets' streams) and validates each one's side info right before queueing it.  A bad record in the LAST
+    stream is found when earlier sub-batches are already in flight: the call has to drain them, report the
+    reference-style error, leave the overlap state as it was, and the context has to keep working."""
+    S, T, C = 48, 48, 2                      # 36 MiB in + out: several sub-batches
+    w = W.make(5, S, T, C, seed=9)
+    ctx = A.Context(S, C)
+    first = ctx.process(w["spectra"], w["info"])
+    state = ctx.get_overlap()
+    bad = w["info"].copy()
+    bad["window_sequence"][S - 1, T - 1, 1] = 9
+    with pytest.raises(A.AacfbError, match="AACFB_ERR_SEQUENCE"):
+        ctx.process(w["spectra"], bad)
+    assert np.array_equal(ctx.get_overlap(), state)
+    # the same frames again, from the state the first call left: equals a fresh context fed both calls
+    again = ctx.process(w["spectra"], w["info"])
+    ref = A.Context(S, C)
+    assert np.array_equal(ref.process(w["spectra"], w["info"]), first)
+    assert np.array_equal(ref.process(w["spectra"], w["info"]), again)
+    ref.close()
+    ctx.close()
+
+
 def test_max_magnitude_inputs_stay_finite():
     w = W.make(2, 2, 4, 2, seed=5)
     w["spectra"] = np.sign(w["spectra"]) * np.float32(3.0e7)
