@@ -1,14 +1,15 @@
 #!/bin/bash
+# compact switching-window tables in shared memory: parity + A/B
 mkdir -p gpurun_out
+timeout 900 python -m pytest tests -x -q -m gpu --timeout 180 --timeout-method=thread > gpurun_out/pytest_gpu.log 2>&1; tail -2 gpurun_out/pytest_gpu.log
 run() {  # tag workload [env...]
   tag=$1; wl=$2; shift 2
   env "$@" timeout 200 python bench.py --steps 100 --warmup 3 --no-e2e --no-cpu --no-configs --workload $wl > gpurun_out/ab_$tag.json 2>> gpurun_out/bench.err
   python -c "import json;d=json.load(open('gpurun_out/ab_$tag.json'));print('%-28s %.4f ms  frac %.3f  launches %d' % ('$tag', d['ms_per_step'],d['roofline']['frac'],d['gpu_launches']))"
 }
 for rep in 1 2; do
-for wl in config5 config3; do
-run ${wl}_default $wl A=1
-run ${wl}_generic_uniform $wl AACFB_LIB=$PWD/aac.js_b200/libaacfb_gu1.so
-run ${wl}_no_park $wl AACFB_LIB=$PWD/aac.js_b200/libaacfb_np.so
+for wl in config5 config2 config3; do
+run ${wl}_compact $wl A=1
+run ${wl}_global $wl AACFB_LIB=$PWD/aac.js_b200/libaacfb_wc0.so
 done
 done
