@@ -159,9 +159,10 @@ __device__ __forceinline__ uint2 info_raw(const SynthParams &P, size_t cf) {
 }
 __device__ __forceinline__ FrameBits info_lo(const SynthParams &P, size_t cf) { return info_raw(P, cf).x; }
 // which float4 interval of row cf lives in the TNS scratch (0: the whole row comes from the spectra)
+// (tns_kernel writes ranges[cf] for EVERY row, 0 for those without TNS, so tns_present need not be looked at first:
+// one global load on the leader's path instead of two dependent ones)
 __device__ __forceinline__ uint32_t row_range(const SynthParams &P, size_t cf) {
-    const bool tns = P.scratch != nullptr && (info_raw(P, cf).y & 0xffu) != 0;
-    return tns ? __ldg(P.ranges + cf) : 0u;
+    return P.scratch != nullptr ? __ldg(P.ranges + cf) : 0u;
 }
 
 }  // namespace

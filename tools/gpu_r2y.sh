@@ -1,5 +1,5 @@
 #!/bin/bash
-# compact switching-window tables in shared memory: parity + A/B
+# row_range with one load: parity (TNS cases) + A/B on config 4
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests -x -q -m gpu --timeout 180 --timeout-method=thread > gpurun_out/pytest_gpu.log 2>&1; tail -2 gpurun_out/pytest_gpu.log
 run() {  # tag workload [env...]
@@ -8,8 +8,6 @@ run() {  # tag workload [env...]
   python -c "import json;d=json.load(open('gpurun_out/ab_$tag.json'));print('%-28s %.4f ms  frac %.3f  launches %d' % ('$tag', d['ms_per_step'],d['roofline']['frac'],d['gpu_launches']))"
 }
 for rep in 1 2; do
-for wl in config5 config2 config3; do
-run ${wl}_compact $wl A=1
-run ${wl}_global $wl AACFB_LIB=$PWD/aac.js_b200/libaacfb_wc0.so
-done
+run config4_new config4 A=1
+run config4_prev config4 AACFB_LIB=$PWD/aac.js_b200/libaacfb_prev.so
 done
