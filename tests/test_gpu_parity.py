@@ -251,6 +251,28 @@ def test_full_size_linearity_and_batch_cut_invariance():
     ctx.close()
 
 
+@pytest.mark.parametrize("env", [dict(AACFB_SUB_BATCHES="1"), dict(AACFB_SUB_BATCHES="5", AACFB_LANES="1"),
+                                 dict(AACFB_SUB_BATCHES="7", AACFB_LANES="4"), dict(AACFB_SUB_BATCHES="8", AACFB_TAPER="2"),
+                                 dict(AACFB_SUB_BATCHES="48", AACFB_TAPER="1")])
+def test_host_pipeline_shape_does_not_change_the_pcm(env, monkeypatch):
+    """aacfb_process_io pipelines sub-batches of streams over buffer sets, with one copy stream per PCIe direction
+    tied to the kernels by events.  However the call is cut (sub-batch count, buffer sets, tapered ends), the PCM
+    and the overlap state are those of the default shape, bit for bit, over two consecutive calls (buffer reuse)."""
+    S, T, C = 48, 40, 2                       # 30 MiB in + out: pipelined by default
+    w = W.make(5, S, T, C, seed=21, shape_prev_mode="carried")
+    ctx = A.Context(S, C)
+    want = [ctx.process(w["spectra"], w["info"]), ctx.process(w["spectra"], w["info"])]
+    want_ov = ctx.get_overlap()
+    ctx.close()
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    ctx = A.Context(S, C)
+    got = [ctx.process(w["spectra"], w["info"]), ctx.process(w["spectra"], w["info"])]
+    assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1])
+    assert np.array_equal(ctx.get_overlap(), want_ov)
+    ctx.close()
+
+
 def test_full_size_tns_sample_against_oracle():
     """config 4 at full batch (65536 stereo frames, TNS order 12): spot-check streams against the oracle."""
     import torch
